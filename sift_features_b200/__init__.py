@@ -1,0 +1,363 @@
+"""sift_features_b200 -- B200-native drop-in for the extraction path of the Rust crate
+tnibler/sift-features (reference sources cited as src/lib.rs:LINE).
+
+Host-side mirror of the crate's public interface (same names, argument meaning and
+result types) over the C ABI of include/sift_b200.h:
+
+    sift(img, features_limit=None)                      src/lib.rs:71
+    sift_with_processing(img, features_limit, P)        src/lib.rs:76
+    precompute_images(img) -> PrecomputedImages         src/lib.rs:131
+    sift_with_precomputed(pre, features_limit)          src/lib.rs:147
+    compute_descriptor(img_f32, x, y, scale, ori)       src/lib.rs:785
+    SiftResult / KeyPoint                               src/lib.rs:39-56
+
+plus the batched / multi-GPU entry points the B200 build adds (sift_batch).
+All computation happens in hand-written sm_100a CUDA kernels inside
+libsift_b200.so; this package only marshals buffers.  There is NO CPU fallback:
+without the built library or without a CUDA device every call raises.
+
+Processing flavour: the crate's only pinned flavour is OpenCVProcessing
+(src/opencv_processing.rs; the flavour its test and snapshots use) and that is
+what the kernels implement bit-for-bit.  `sift()` in the crate defaults to
+ImageprocProcessing (src/lib.rs:71-73, 992-1007), whose third-party arithmetic is
+not available to pin; here `sift()` is `sift_with_processing::<OpenCVProcessing>`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+
+__all__ = [
+    "KeyPoint", "SiftResult", "PrecomputedImages", "OpenCVProcessing", "ImageprocProcessing", "Extractor",
+    "SiftError", "sift", "sift_with_processing", "precompute_images", "sift_with_precomputed",
+    "compute_descriptor", "compute_descriptors", "sift_batch", "KEYPOINT_DTYPE",
+]
+
+#: layout of sb200_keypoint == the crate's KeyPoint (src/lib.rs:48-56)
+KEYPOINT_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4")])
+SIFT_KEYPOINT_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"),
+                                ("octave", "i4"), ("scale", "i4")])
+CANDIDATE_DTYPE = np.dtype([("octave", "i4"), ("scale", "i4"), ("y", "i4"), ("x", "i4")])
+DESC_IN_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("scale", "f4"), ("orientation", "f4")])
+STAGE_NAMES = ("seed", "blur", "extrema", "refine", "orient", "descriptor")
+
+
+class SiftError(RuntimeError):
+    """A C-ABI call returned a non-zero status (the crate would have panicked)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"sift_b200 status {status}: {message}")
+        self.status = status
+
+
+@dataclass(frozen=True)
+class KeyPoint:
+    """src/lib.rs:48-56.  x, y, size in input-image pixels; size is sigma (half of OpenCV's)."""
+    x: float
+    y: float
+    size: float
+    angle: float
+    response: float
+
+
+class SiftResult:
+    """src/lib.rs:39-46: keypoints and the (n, 128) u8 descriptors in the same order."""
+
+    def __init__(self, keypoints: np.ndarray, descriptors: np.ndarray):
+        self.keypoint_array = keypoints            # structured array, KEYPOINT_DTYPE
+        self.descriptors = descriptors             # (n, 128) uint8
+
+    @property
+    def keypoints(self) -> List[KeyPoint]:
+        a = self.keypoint_array
+        return [KeyPoint(float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]))
+                for k in a]
+
+    def __len__(self) -> int:
+        return len(self.keypoint_array)
+
+    def __eq__(self, other) -> bool:  # #[derive(PartialEq)]
+        return (isinstance(other, SiftResult) and np.array_equal(self.keypoint_array, other.keypoint_array)
+                and np.array_equal(self.descriptors, other.descriptors))
+
+
+class OpenCVProcessing:
+    """Marker for the blur/resize flavour of src/opencv_processing.rs (implemented on the GPU)."""
+
+
+class ImageprocProcessing:
+    """Marker for src/lib.rs:992-1007 (imageproc/image crates).  Not implemented: its arithmetic
+    lives in third-party crates that are not part of the reference tree and no reference test
+    pins it."""
+
+
+def _as_gray(img) -> np.ndarray:
+    a = np.asarray(img)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise ValueError("expected a 2-D uint8 (gray) image, like image::GrayImage")
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class Extractor:
+    """One sb200 context: a device, its arenas and streams.  Not re-entrant (use one per thread)."""
+
+    def __init__(self, max_width: int, max_height: int, max_batch: int = 1, device: int = 0,
+                 max_keypoints_per_image: int = 0):
+        self._lib = _ffi.load()
+        self._h = C.c_void_p()
+        st = self._lib.sb200_create(device, max_width, max_height, max_batch, max_keypoints_per_image,
+                                    C.byref(self._h))
+        if st != _ffi.OK:
+            raise SiftError(st, f"sb200_create(device={device}, {max_width}x{max_height}, batch={max_batch}) failed: "
+                            + self._lib.sb200_status_string(st).decode())
+        self.device, self.max_width, self.max_height, self.max_batch = device, max_width, max_height, max_batch
+
+    # -- plumbing ---------------------------------------------------------
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def _check(self, st: int):
+        if st != _ffi.OK:
+            raise SiftError(st, self._lib.sb200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.sb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _take(self, res: _ffi.Result):
+        n, ni = int(res.n), int(res.n_images)
+        offs = np.ctypeslib.as_array(res.offsets, shape=(ni + 1,)).copy()
+        if n:
+            kp = np.frombuffer((C.c_char * (n * KEYPOINT_DTYPE.itemsize)).from_address(res.keypoints),
+                               dtype=KEYPOINT_DTYPE).copy()
+            de = np.frombuffer((C.c_char * (n * 128)).from_address(res.descriptors), dtype=np.uint8)
+            de = de.reshape(n, 128).copy()
+        else:
+            kp = np.zeros(0, KEYPOINT_DTYPE)
+            de = np.zeros((0, 128), np.uint8)
+        return offs, kp, de
+
+    # -- the crate's entry points ----------------------------------------
+    def sift(self, img, features_limit: Optional[int] = None) -> SiftResult:
+        """sift / sift_with_processing::<OpenCVProcessing> (src/lib.rs:71-81)."""
+        a = _as_gray(img)
+        res = _ffi.Result()
+        self._check(self._lib.sb200_extract(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0],
+                                            -1 if features_limit is None else int(features_limit), C.byref(res)))
+        _, kp, de = self._take(res)
+        return SiftResult(kp, de)
+
+    def sift_batch(self, images, features_limit: Optional[int] = None):
+        """n same-sized images (n,H,W) u8 -> (offsets[n+1], keypoints, descriptors)."""
+        a = np.asarray(images)
+        if a.dtype != np.uint8 or a.ndim != 3:
+            raise ValueError("expected an (n, H, W) uint8 array")
+        if a.strides[2] != 1 or a.strides[1] < a.shape[2]:
+            a = np.ascontiguousarray(a)
+        res = _ffi.Result()
+        self._check(self._lib.sb200_extract_batch(self._h, a.ctypes.data, a.shape[0], a.shape[2], a.shape[1],
+                                                  a.strides[1], a.strides[0],
+                                                  -1 if features_limit is None else int(features_limit),
+                                                  C.byref(res)))
+        return self._take(res)
+
+    def precompute_images(self, img) -> "PrecomputedImages":
+        """precompute_images::<OpenCVProcessing> (src/lib.rs:131-143); the pyramid stays on the device."""
+        a = _as_gray(img)
+        self._check(self._lib.sb200_precompute(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0]))
+        return PrecomputedImages(self)
+
+    def sift_with_precomputed(self, features_limit: Optional[int] = None) -> SiftResult:
+        """sift_with_precomputed (src/lib.rs:147-177) on the resident pyramid."""
+        res = _ffi.Result()
+        self._check(self._lib.sb200_extract_precomputed(
+            self._h, -1 if features_limit is None else int(features_limit), C.byref(res)))
+        _, kp, de = self._take(res)
+        return SiftResult(kp, de)
+
+    def compute_descriptors(self, img_f32, keypoints) -> np.ndarray:
+        """compute_descriptor (src/lib.rs:785-990) for many (x, y, scale, orientation_deg) rows."""
+        img = np.ascontiguousarray(img_f32, np.float32)
+        k = np.ascontiguousarray(np.asarray(keypoints, np.float32).reshape(-1, 4))
+        out = np.zeros((len(k), 128), np.uint8)
+        self._check(self._lib.sb200_compute_descriptors(self._h, img.ctypes.data, img.shape[1], img.shape[0],
+                                                        img.shape[1], k.ctypes.data, len(k), out.ctypes.data))
+        return out
+
+    # -- parity / debug views ------------------------------------------
+    def last_candidates(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(self._lib.sb200_last_candidates(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, CANDIDATE_DTYPE)
+        if n.value:
+            self._check(self._lib.sb200_last_candidates(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def last_sift_keypoints(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(self._lib.sb200_last_sift_keypoints(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, SIFT_KEYPOINT_DTYPE)
+        if n.value:
+            self._check(self._lib.sb200_last_sift_keypoints(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    # -- measurement ----------------------------------------------------
+    def set_profiling(self, on: bool):
+        self._check(self._lib.sb200_set_profiling(self._h, int(on)))
+
+    def stage_stats(self):
+        ms = (C.c_double * _ffi.STAGE_COUNT)()
+        ln = (C.c_uint64 * _ffi.STAGE_COUNT)()
+        self._check(self._lib.sb200_stage_stats(self._h, ms, ln, _ffi.STAGE_COUNT))
+        return {STAGE_NAMES[i]: {"ms": ms[i], "launches": int(ln[i])} for i in range(_ffi.STAGE_COUNT)}
+
+    def reset_stats(self):
+        self._check(self._lib.sb200_reset_stats(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sb200_launch_count(self._h))
+
+
+class PrecomputedImages:
+    """src/lib.rs:124-128: `scale_space[o]` is the (6,h,w) Gaussian stack, `dog[o]` the (5,h,w) DoG stack of
+    octave o.  The data lives on the device; indexing downloads the requested octave."""
+
+    class _Stack:
+        def __init__(self, ex: Extractor, dims, layers, fn):
+            self._ex, self._dims, self._layers, self._fn = ex, dims, layers, fn
+
+        def __len__(self):
+            return len(self._dims)
+
+        def __getitem__(self, o: int) -> np.ndarray:
+            w, h = self._dims[o]
+            out = np.zeros((self._layers, h, w), np.float32)
+            for l in range(self._layers):
+                self._ex._check(self._fn(self._ex.handle, o, l, out[l].ctypes.data))
+            return out
+
+    def __init__(self, ex: Extractor):
+        lib = ex._lib
+        n = C.c_uint32()
+        ws = (C.c_uint32 * 16)()
+        hs = (C.c_uint32 * 16)()
+        ex._check(lib.sb200_pyramid_info(ex.handle, C.byref(n), ws, hs, 16))
+        self.extractor = ex
+        self.n_octaves = int(n.value)
+        self.dims = [(int(ws[o]), int(hs[o])) for o in range(self.n_octaves)]
+        self.scale_space = PrecomputedImages._Stack(ex, self.dims, 6, lib.sb200_pyramid_layer)
+        self.dog = PrecomputedImages._Stack(ex, self.dims, 5, lib.sb200_pyramid_dog)
+
+
+# ---------------------------------------------------------------------------
+# module-level functions with the crate's names; contexts are cached per shape
+# ---------------------------------------------------------------------------
+_cache: dict = {}
+
+
+def _extractor(w: int, h: int, batch: int = 1, device: int = 0) -> Extractor:
+    key = (device, w, h, batch)
+    ex = _cache.get(key)
+    if ex is None:
+        if len(_cache) >= 4:  # contexts hold device arenas: keep only a few alive
+            _cache.pop(next(iter(_cache))).close()
+        ex = _cache[key] = Extractor(w, h, batch, device)
+    return ex
+
+
+def sift(img, features_limit: Optional[int] = None, device: int = 0) -> SiftResult:
+    """src/lib.rs:71 (OpenCVProcessing flavour, see the module docstring)."""
+    a = _as_gray(img)
+    return _extractor(a.shape[1], a.shape[0], 1, device).sift(a, features_limit)
+
+
+def sift_with_processing(img, features_limit: Optional[int] = None, processing=OpenCVProcessing,
+                         device: int = 0) -> SiftResult:
+    """src/lib.rs:76.  `processing` selects the blur/resize flavour (the crate's type parameter P)."""
+    if processing is not OpenCVProcessing:
+        raise NotImplementedError("only OpenCVProcessing (src/opencv_processing.rs) is implemented on the GPU; "
+                                  "ImageprocProcessing's third-party arithmetic is unpinned")
+    return sift(img, features_limit, device)
+
+
+def precompute_images(img, device: int = 0) -> PrecomputedImages:
+    """src/lib.rs:131."""
+    a = _as_gray(img)
+    return _extractor(a.shape[1], a.shape[0], 1, device).precompute_images(a)
+
+
+def sift_with_precomputed(pre: PrecomputedImages, features_limit: Optional[int] = None) -> SiftResult:
+    """src/lib.rs:147."""
+    return pre.extractor.sift_with_precomputed(features_limit)
+
+
+def compute_descriptors(img_f32, keypoints, device: int = 0) -> np.ndarray:
+    img = np.asarray(img_f32)
+    return _extractor(max(img.shape[1], 8), max(img.shape[0], 8), 1, device).compute_descriptors(img, keypoints)
+
+
+def compute_descriptor(img_f32, x: float, y: float, scale: float, orientation: float, device: int = 0) -> np.ndarray:
+    """src/lib.rs:785: one keypoint; returns the 128 descriptor bytes."""
+    return compute_descriptors(img_f32, [[x, y, scale, orientation]], device)[0]
+
+
+def sift_batch(images, features_limit: Optional[int] = None, devices: Optional[Sequence[int]] = None,
+               max_batch: int = 16) -> List[SiftResult]:
+    """n same-sized images -> one SiftResult per image.  With several devices the batch is split into
+    contiguous shards, one host thread per device, results gathered in image order on the host
+    (sb200_extract_batch_multi; no device-to-device traffic)."""
+    a = np.asarray(images)
+    if a.dtype != np.uint8 or a.ndim != 3:
+        raise ValueError("expected an (n, H, W) uint8 array")
+    a = np.ascontiguousarray(a)
+    devices = list(devices) if devices else [0]
+    n, h, w = a.shape
+    exs = [_extractor(w, h, max(1, min(max_batch, n)), d) for d in devices]
+    lib = _ffi.load()
+    if len(exs) == 1:
+        offs, kp, de = exs[0].sift_batch(a, features_limit)
+    else:
+        handles = (C.c_void_p * len(exs))(*[e.handle for e in exs])
+        res = _ffi.Result()
+        exs[0]._check(lib.sb200_extract_batch_multi(handles, len(exs), a.ctypes.data, n, w, h, a.strides[1],
+                                                    a.strides[0],
+                                                    -1 if features_limit is None else int(features_limit),
+                                                    C.byref(res)))
+        offs, kp, de = exs[0]._take(res)
+    return [SiftResult(kp[offs[i]:offs[i + 1]], de[offs[i]:offs[i + 1]]) for i in range(n)]
+
+
+def shard_ranges(n: int, parts: int) -> List[range]:
+    """The partition sb200_extract_batch_multi uses: contiguous blocks of ceil(n/parts) images."""
+    per = (n + parts - 1) // parts
+    return [range(min(d * per, n), min((d + 1) * per, n)) for d in range(parts)]
+
+
+def algorithmic_bytes(w: int, h: int):
+    """A(W,H) of SURVEY.md section 8(d): (total, seed, blur+decimate, extrema) bytes for one image."""
+    lib = _ffi.load()
+    parts = (C.c_uint64 * 3)()
+    total = lib.sb200_algorithmic_bytes(w, h, parts, 3)
+    return int(total), int(parts[0]), int(parts[1]), int(parts[2])

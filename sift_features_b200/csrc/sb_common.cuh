@@ -1,0 +1,77 @@
+// sb_common.cuh -- layout structs and constants shared by the kernels and the host runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+// src/lib.rs:92-112, 179-193
+constexpr int SCALES_PER_OCTAVE = 3;
+constexpr int N_LAYERS = SCALES_PER_OCTAVE + 3;      // Gaussian layers per octave
+constexpr int N_DOG = SCALES_PER_OCTAVE + 2;
+constexpr int IMAGE_BORDER = 5;
+constexpr int ORI_BINS = 36;
+constexpr int MAX_ORI = ORI_BINS / 2;                // a circular 36-bin histogram has <= 18 strict local maxima
+constexpr int DESC_SIZE = 128;
+constexpr int MAX_OCT = 16;
+
+// Blur radii of the six Gaussian kernels (index 0 = seed blur, 1..5 = octave
+// layers): OpenCV ksize = round(8 sigma + 1) | 1 -> 11, 11, 13, 17, 21, 27 taps.
+__host__ __device__ constexpr int blur_radius(int l) {
+    return l == 0 ? 5 : l == 1 ? 5 : l == 2 ? 6 : l == 3 ? 8 : l == 4 ? 10 : 13;
+}
+constexpr int MAX_TAPS = 27;
+
+// One octave of one image inside the per-image arenas.
+//   Gaussian layer l:  gauss + off + l*layer_stride, row pitch `pitch` floats (multiple of 32)
+//   extrema mask:      mask + mask_off + ((s-1)*h + y)*mask_pitch words, bit x%32 of word x/32
+//   row counters:      rows + row_base + (s-1)*h + y
+struct OctLayout {
+    int w, h, pitch, mask_pitch;
+    int row_base;
+    int scanned;  // src/lib.rs:315-317: octaves smaller than 10 px are blurred but never scanned
+    long long off, layer_stride, mask_off;
+};
+
+struct PyrLayout {
+    int n_oct;
+    int img_rows;              // row counters per image
+    long long img_floats;      // Gaussian arena floats per image
+    long long img_mask_words;  // mask words per image
+    OctLayout o[MAX_OCT];
+};
+
+// candidate key: octave:4 | scale:2 | y:13 | x:13  (natural order == integer order)
+__host__ __device__ inline uint32_t pack_key(int o, int s, int y, int x) {
+    return ((uint32_t)o << 28) | ((uint32_t)s << 26) | ((uint32_t)y << 13) | (uint32_t)x;
+}
+__host__ __device__ inline void unpack_key(uint32_t k, int& o, int& s, int& y, int& x) {
+    o = (int)(k >> 28);
+    s = (int)((k >> 26) & 3u);
+    y = (int)((k >> 13) & 0x1fffu);
+    x = (int)(k & 0x1fffu);
+}
+
+// refined scale-space point (output of the refinement kernel, one per candidate)
+struct Refined {
+    float x, y;        // seed-image coordinates: (px + off_x) * 2^octave   (src/lib.rs:376-377)
+    float size;        // kp_scale * 2^octave                                (:422)
+    float response;    // |contrast|                                         (:357-358)
+    float kp_scale;    // sigma in octave pixels                             (:372-374)
+    int px, py;        // refined integer position in the octave
+    int octave_scale;  // octave << 8 | scale (layer index); -1 when rejected
+};
+
+// SiftKeyPoint as kept on the device (src/lib.rs:58-68)
+struct DevKeyPoint {
+    float x, y, size, angle, response;
+    int octave, scale;
+    int pad;
+};
+
+// KeyPoint as returned to the caller (src/lib.rs:48-56); same layout as sb200_keypoint
+struct OutKeyPoint {
+    float x, y, size, angle, response;
+};
+
+}  // namespace sb

@@ -1,0 +1,655 @@
+// sb_keypoints.cuh -- refinement, orientation assignment, ordering, descriptors.
+//
+// All arithmetic follows src/lib.rs operation by operation in f32 (the file is
+// compiled with --fmad=false, IEEE division and square root); the transcendental
+// calls the crate makes through libm (f32::exp, f32::powf, f64::atan2, f32::sin_cos)
+// are reproduced by sb_math.cuh or by double-precision evaluation rounded once.
+#pragma once
+#include "sb_common.cuh"
+#include "sb_math.cuh"
+
+namespace sb {
+
+struct KpParams {
+    PyrLayout L;
+    const float* gauss;        // Gaussian arena, image 0
+    const uint32_t* keys;      // [img][cap] packed candidate keys (natural order)
+    const uint32_t* cand_count;// [img]
+    uint32_t cap;              // candidate capacity per image
+    Refined* refined;          // [img][cap]
+    uint32_t* n_ori;           // [img][cap] orientations per candidate
+    float* angles;             // [img][cap][MAX_ORI]
+    uint32_t* kp_off;          // [img][cap] exclusive scan of n_ori
+    uint32_t* kp_count;        // [img]
+    DevKeyPoint* kps;          // [img][kcap] SiftKeyPoints in natural order
+    uint32_t kcap;
+};
+
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((127 + e) << 23); }
+
+// DoG value (src/lib.rs:275): layer l of the octave whose Gaussian layer 0 is `g`
+struct DogView {
+    const float* g;
+    long long ls;
+    int pitch;
+    __device__ __forceinline__ float operator()(int l, int y, int x) const {
+        const float* p = g + (long long)l * ls + (long long)y * pitch + x;
+        return __ldg(p + ls) - __ldg(p);
+    }
+};
+
+// interpolate_extremum + extremum_contrast + extremum_is_on_edge + keypoint geometry
+// (src/lib.rs:334-380, 525-653).  One thread per candidate.
+__global__ void __launch_bounds__(128) k_refine(const KpParams P) {
+    __shared__ uint64_t s_tab[32];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
+    __syncthreads();
+    const long long img = blockIdx.y;
+    const uint32_t n = min(P.cand_count[img], P.cap);
+    const uint32_t* keys = P.keys + img * (long long)P.cap;
+    Refined* out = P.refined + img * (long long)P.cap;
+    const float* gimg = P.gauss + img * P.L.img_floats;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int o, scale, y, x;
+        unpack_key(keys[i], o, scale, y, x);
+        const OctLayout& ol = P.L.o[o];
+        DogView D{gimg + ol.off, ol.layer_stride, ol.pitch};
+        const int w = ol.w, h = ol.h;
+        bool ok = false;
+        float off_s = 0.f, off_x = 0.f, off_y = 0.f;
+        for (int it = 0; it < 5; it++) {  // MAX_INTERPOLATION_STEPS, src/lib.rs:516
+            const int p = scale - 1, c = scale, nn = scale + 1;
+            const float vn = D(nn, y, x), vp = D(p, y, x), vc = D(c, y, x);
+            const float cyp = D(c, y + 1, x), cym = D(c, y - 1, x);
+            const float cxp = D(c, y, x + 1), cxm = D(c, y, x - 1);
+            const float g1 = (vn - vp) / 2.f;
+            const float g2 = (cyp - cym) / 2.f;
+            const float g3 = (cxp - cxm) / 2.f;
+            const float value2x = vc * 2.f;
+            const float h11 = vn + vp - value2x;
+            const float h12 = (D(nn, y + 1, x) - D(nn, y - 1, x) - D(p, y + 1, x) + D(p, y - 1, x)) / 4.f;
+            const float h13 = (D(nn, y, x + 1) - D(nn, y, x - 1) - D(p, y, x + 1) + D(p, y, x - 1)) / 4.f;
+            const float h22 = cyp + cym - value2x;
+            const float h33 = cxp + cxm - value2x;
+            const float h23 = (D(c, y + 1, x + 1) - D(c, y + 1, x - 1) - D(c, y - 1, x + 1) + D(c, y - 1, x - 1)) / 4.f;
+            const float det = h11 * h22 * h33 - h11 * h23 * h23 - h12 * h12 * h33 + 2.f * h12 * h13 * h23 -
+                              h13 * h13 * h22;
+            const float hinv11 = (h22 * h33 - h23 * h23) / det;
+            const float hinv12 = (h13 * h23 - h12 * h33) / det;
+            const float hinv13 = (h12 * h23 - h13 * h22) / det;
+            const float hinv22 = (h11 * h33 - h13 * h13) / det;
+            const float hinv23 = (h12 * h13 - h11 * h23) / det;
+            const float hinv33 = (h11 * h22 - h12 * h12) / det;
+            off_s = -(hinv11 * g1 + hinv12 * g2 + hinv13 * g3);
+            off_x = -(hinv13 * g1 + hinv23 * g2 + hinv33 * g3);
+            off_y = -(hinv12 * g1 + hinv22 * g2 + hinv23 * g3);
+            if (fabsf(off_s) < 0.5f && fabsf(off_x) < 0.5f && fabsf(off_y) < 0.5f) { ok = true; break; }
+            // src/lib.rs:588-599: move by round() (half away from zero; NaN -> 0;
+            // an unrepresentable step can only land outside the image => reject)
+            float rx = roundf(off_x), ry = roundf(off_y), rs = roundf(off_s);
+            if (isnan(rx)) rx = 0.f;
+            if (isnan(ry)) ry = 0.f;
+            if (isnan(rs)) rs = 0.f;
+            if (fabsf(rx) > 1e5f || fabsf(ry) > 1e5f || fabsf(rs) > 1e5f) break;
+            const int nx = x + (int)rx, ny = y + (int)ry, ns = scale + (int)rs;
+            if (ns < 1 || ns > SCALES_PER_OCTAVE || nx < IMAGE_BORDER || nx >= w - IMAGE_BORDER ||
+                ny < IMAGE_BORDER || ny >= h - IMAGE_BORDER)
+                break;
+            x = nx; y = ny; scale = ns;
+        }
+        Refined r;
+        r.octave_scale = -1;
+        r.x = r.y = r.size = r.response = r.kp_scale = 0.f;
+        r.px = x; r.py = y;
+        if (ok) {
+            // extremum_contrast, src/lib.rs:606-626 (gradient recomputed at the final point)
+            const float g1 = (D(scale + 1, y, x) - D(scale - 1, y, x)) / 2.f;
+            const float cyp = D(scale, y + 1, x), cym = D(scale, y - 1, x);
+            const float cxp = D(scale, y, x + 1), cxm = D(scale, y, x - 1);
+            const float vc = D(scale, y, x);
+            const float g2 = (cyp - cym) / 2.f;
+            const float g3 = (cxp - cxm) / 2.f;
+            const float interp = off_s * g1 + off_y * g2 + off_x * g3;
+            const float contrast = fabsf(vc + interp / 2.f);
+            bool keep = !(contrast * 3.f <= 0.04f);  // src/lib.rs:360
+            if (keep) {
+                // extremum_is_on_edge, src/lib.rs:630-653
+                const float val2x = vc * 2.0f;
+                const float h11 = cyp + cym - val2x;
+                const float d22 = cxp + cxm - val2x;
+                const float h12 = (D(scale, y + 1, x + 1) - D(scale, y + 1, x - 1) - D(scale, y - 1, x + 1) +
+                                   D(scale, y - 1, x - 1)) / 4.f;
+                const float tr = d22 + h11;
+                const float det = d22 * h11 - h12 * h12;
+                if (det <= 0.f) keep = false;
+                else if ((tr * tr * 10.0f) > (11.0f * 11.0f) * det) keep = false;
+            }
+            if (keep) {
+                const float osf = pow2i(o);
+                const float kp_scale = 0.8f * sbm::pow2f_glibc(s_tab, ((float)scale + off_s) / 3.f) * 2.f;
+                r.x = ((float)x + off_x) * osf;
+                r.y = ((float)y + off_y) * osf;
+                r.size = kp_scale * osf;
+                r.response = contrast;
+                r.kp_scale = kp_scale;
+                r.octave_scale = (o << 8) | scale;
+            }
+        }
+        out[i] = r;
+    }
+}
+
+// gradient_direction_histogram + peak extraction (src/lib.rs:380-431, 657-757).
+// One warp per candidate.  The histogram is accumulated in the reference's raster
+// order per bin (the owner lane of a bin adds its samples in ascending sample
+// order), so the smoothed histogram, the peak set and the angles are the
+// reference's f32 results, not an approximation of them.
+constexpr int ORI_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P) {
+    __shared__ uint64_t s_tab[32];
+    __shared__ float s_val[ORI_WARPS][32];
+    __shared__ uint32_t s_msk[ORI_WARPS][40];
+    __shared__ float s_raw[ORI_WARPS][40];
+    __shared__ float s_hist[ORI_WARPS][ORI_BINS];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long img = blockIdx.y;
+    const uint32_t n = min(P.cand_count[img], P.cap);
+    const Refined* refined = P.refined + img * (long long)P.cap;
+    uint32_t* n_ori = P.n_ori + img * (long long)P.cap;
+    float* angles = P.angles + img * (long long)P.cap * MAX_ORI;
+    const float* gimg = P.gauss + img * P.L.img_floats;
+    const float PI32 = 3.14159265358979323846f;
+    const float bin_angle_step = 36.0f / (PI32 * 2.f);  // src/lib.rs:718
+
+    for (uint32_t i = blockIdx.x * ORI_WARPS + warp; i < n; i += gridDim.x * ORI_WARPS) {
+        const Refined r = refined[i];
+        if (r.octave_scale < 0) {
+            if (lane == 0) n_ori[i] = 0;
+            continue;
+        }
+        const int o = r.octave_scale >> 8, layer = r.octave_scale & 255;
+        const OctLayout& ol = P.L.o[o];
+        const float* I = gimg + ol.off + (long long)layer * ol.layer_stride;
+        const int w = ol.w, h = ol.h, pitch = ol.pitch;
+        const int x = r.px, y = r.py;
+        const int radius = (int)roundf(3.f * 1.5f * r.kp_scale);  // src/lib.rs:380
+        const float sigma = 1.5f * r.kp_scale;                    // LAMBDA_ORI * kp_scale, :386
+        const float gws = -1.0f / (2.0f * sigma * sigma);         // :667
+        const int side = 2 * radius + 1, total = side * side;
+        float acc0 = 0.f, acc1 = 0.f;  // bins `lane` and `32 + lane`
+        for (int base = 0; base < total; base += 32) {
+            const int idx = base + lane;
+            int bin = -1;
+            float val = 0.f;
+            if (idx < total) {
+                const int yq = idx / side;
+                const int yp = yq - radius, xp = idx - yq * side - radius;
+                const int yi = y + yp, xi = x + xp;
+                if (yi > 0 && yi < h - 1 && xi > 0 && xi < w - 1) {
+                    const float* c = I + (long long)yi * pitch + xi;
+                    const float dx = __ldg(c + 1) - __ldg(c - 1);
+                    const float dy = __ldg(c - pitch) - __ldg(c + pitch);
+                    const float wexp = (float)(yp * yp + xp * xp) * gws;
+                    const float weight = sbm::expf_glibc(s_tab, wexp);
+                    const float mag = sqrtf(dx * dx + dy * dy);
+                    // bin = round(36/(2pi) * (atan2_f64(dy,dx) as f32)), src/lib.rs:715-726.
+                    // f32 atan2 decides unless the scaled angle is close to a rounding
+                    // boundary; then the f64 evaluation the reference uses decides.
+                    float raw = bin_angle_step * atan2f(dy, dx);
+                    if (fabsf(fabsf(raw - truncf(raw)) - 0.5f) < 1e-3f)
+                        raw = bin_angle_step * (float)atan2((double)dy, (double)dx);
+                    bin = (int)roundf(raw);
+                    if (bin >= ORI_BINS) bin -= ORI_BINS;
+                    else if (bin < 0) bin += ORI_BINS;
+                    val = weight * mag;
+                }
+            }
+            // ordered accumulation: publish values, group lanes by bin, owners add in lane order
+            s_msk[warp][lane] = 0u;
+            if (lane < 8) s_msk[warp][32 + lane] = 0u;
+            s_val[warp][lane] = val;
+            __syncwarp();
+            const uint32_t grp = __match_any_sync(0xffffffffu, bin);
+            if (bin >= 0 && lane == __ffs(grp) - 1) s_msk[warp][bin] = grp;
+            __syncwarp();
+            uint32_t m0 = s_msk[warp][lane];
+            while (m0) { const int j = __ffs(m0) - 1; m0 &= m0 - 1; acc0 += s_val[warp][j]; }
+            uint32_t m1 = (lane < ORI_BINS - 32) ? s_msk[warp][32 + lane] : 0u;
+            while (m1) { const int j = __ffs(m1) - 1; m1 &= m1 - 1; acc1 += s_val[warp][j]; }
+            __syncwarp();
+        }
+        // raw_hist with 2-bin circular padding, src/lib.rs:742-749
+        s_raw[warp][lane + 2] = acc0;
+        if (lane < ORI_BINS - 32) s_raw[warp][32 + lane + 2] = acc1;
+        __syncwarp();
+        if (lane == 0) {
+            s_raw[warp][1] = s_raw[warp][ORI_BINS + 1];
+            s_raw[warp][0] = s_raw[warp][ORI_BINS];
+            s_raw[warp][ORI_BINS + 2] = s_raw[warp][2];
+            s_raw[warp][ORI_BINS + 3] = s_raw[warp][3];
+        }
+        __syncwarp();
+        // smoothing, src/lib.rs:751-755
+        float hmax_local = -1.f;
+        for (int k = lane; k < ORI_BINS; k += 32) {
+            const float* rw = s_raw[warp] + k + 2;
+            const float hv = (rw[-2] + rw[2]) * (1.f / 16.f) + (rw[-1] + rw[1]) * (4.f / 16.f) + rw[0] * 6.f / 16.f;
+            s_hist[warp][k] = hv;
+            hmax_local = fmaxf(hmax_local, hv);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) hmax_local = fmaxf(hmax_local, __shfl_xor_sync(0xffffffffu, hmax_local, d));
+        __syncwarp();
+        const float thr = hmax_local * 0.8f;  // src/lib.rs:394
+        // peaks, ascending bin order (src/lib.rs:397-431)
+        uint32_t count = 0;
+        for (int kb = 0; kb < ORI_BINS; kb += 32) {
+            const int k = kb + lane;
+            bool peak = false;
+            float ang = 0.f;
+            if (k < ORI_BINS) {
+                const int km = k > 0 ? k - 1 : ORI_BINS - 1;
+                const int kp = k < ORI_BINS - 1 ? k + 1 : 0;
+                const float hk = s_hist[warp][k], hm = s_hist[warp][km], hp = s_hist[warp][kp];
+                if (hk > hm && hk > hp && hk >= thr) {
+                    peak = true;
+                    const float interp = (hm - hp) / (hm - 2.0f * hk + hp);
+                    float b = (float)k + 0.5f * interp;
+                    if (b < 0.0f) b = 36.0f + b;
+                    else if (b >= 36.0f) b = b - 36.0f;
+                    ang = 360.0f - (360.0f / 36.0f) * b;
+                }
+            }
+            const uint32_t pm = __ballot_sync(0xffffffffu, peak);
+            if (peak) {
+                const uint32_t slot = count + __popc(pm & ((1u << lane) - 1u));
+                if (slot < MAX_ORI) angles[(long long)i * MAX_ORI + slot] = ang;
+            }
+            count += __popc(pm);
+        }
+        if (lane == 0) n_ori[i] = min(count, (uint32_t)MAX_ORI);
+        __syncwarp();
+    }
+}
+
+// exclusive scan of n_ori over the candidates of one image (one CTA per image)
+__global__ void __launch_bounds__(1024) k_kpscan(const KpParams P) {
+    __shared__ uint32_t wsum[32];
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = min(P.cand_count[img], P.cap);
+    const uint32_t* cnt = P.n_ori + (long long)img * P.cap;
+    uint32_t* off = P.kp_off + (long long)img * P.cap;
+    const uint32_t per = (n + 1023u) / 1024u;
+    const uint32_t start = min(tid * per, n), end = min(start + per, n);
+    uint32_t local = 0;
+    for (uint32_t i = start; i < end; i++) local += cnt[i];
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = wsum[lane], s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += t;
+        }
+        wsum[lane] = s - v;
+        if (lane == 31) P.kp_count[img] = s;
+    }
+    __syncthreads();
+    uint32_t run = wsum[warp] + incl - local;
+    for (uint32_t i = start; i < end; i++) {
+        uint32_t c = cnt[i];
+        off[i] = run;
+        run += c;
+    }
+}
+
+// SiftKeyPoint records in natural order (src/lib.rs:419-427)
+__global__ void __launch_bounds__(256) k_emit(const KpParams P) {
+    const long long img = blockIdx.y;
+    const uint32_t n = min(P.cand_count[img], P.cap);
+    const Refined* refined = P.refined + img * (long long)P.cap;
+    const uint32_t* n_ori = P.n_ori + img * (long long)P.cap;
+    const uint32_t* kp_off = P.kp_off + img * (long long)P.cap;
+    const float* angles = P.angles + img * (long long)P.cap * MAX_ORI;
+    DevKeyPoint* kps = P.kps + img * (long long)P.kcap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = n_ori[i];
+        if (!c) continue;
+        const Refined r = refined[i];
+        const uint32_t base = kp_off[i];
+        for (uint32_t k = 0; k < c; k++) {
+            if (base + k >= P.kcap) break;
+            DevKeyPoint kp;
+            kp.x = r.x; kp.y = r.y; kp.size = r.size; kp.response = r.response;
+            kp.angle = angles[(long long)i * MAX_ORI + k];
+            kp.octave = r.octave_scale >> 8; kp.scale = r.octave_scale & 255; kp.pad = 0;
+            kps[base + k] = kp;
+        }
+    }
+}
+
+// features_limit (src/lib.rs:156-161): stable LSD radix sort of the keypoint
+// indices by descending response; ties keep natural order.  One CTA per image.
+__global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __restrict__ kps_all,
+                                                         const uint32_t* __restrict__ kp_count, uint32_t kcap,
+                                                         uint32_t* __restrict__ scratch /* [img][4*kcap] */,
+                                                         uint32_t* __restrict__ order /* [img][kcap] */) {
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_wcnt[32][257];
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = min(kp_count[img], kcap);
+    const DevKeyPoint* kps = kps_all + (long long)img * kcap;
+    uint32_t* keyA = scratch + (long long)img * 4 * kcap;
+    uint32_t* idxA = keyA + kcap;
+    uint32_t* keyB = idxA + kcap;
+    uint32_t* idxB = keyB + kcap;
+    for (uint32_t i = tid; i < n; i += 1024) {
+        keyA[i] = ~__float_as_uint(kps[i].response);  // responses are >= 0: bit pattern is monotonic
+        idxA[i] = i;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 8 * pass;
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += 1024) atomicAdd(&s_hist[(keyA[i] >> shift) & 255u], 1u);
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of 256 bins: 8 per lane
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = s_hist[lane * 8 + k]; sum += v[k]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { s_hist[lane * 8 + k] = run; run += v[k]; }
+        }
+        __syncthreads();
+        for (uint32_t c0 = 0; c0 < n; c0 += 1024) {
+            for (int k = tid; k < 32 * 257; k += 1024) (&s_wcnt[0][0])[k] = 0;
+            __syncthreads();
+            const uint32_t i = c0 + tid;
+            const bool valid = i < n;
+            const uint32_t key = valid ? keyA[i] : 0u, id = valid ? idxA[i] : 0u;
+            const uint32_t dg = valid ? ((key >> shift) & 255u) : 256u;
+            const uint32_t grp = __match_any_sync(0xffffffffu, dg);
+            const uint32_t rank = __popc(grp & ((1u << lane) - 1u));
+            if (valid && lane == __ffs(grp) - 1) s_wcnt[warp][dg] = __popc(grp);
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t run = s_hist[tid];
+                for (int wv = 0; wv < 32; wv++) {
+                    uint32_t t = s_wcnt[wv][tid];
+                    s_wcnt[wv][tid] = run;
+                    run += t;
+                }
+                s_hist[tid] = run;
+            }
+            __syncthreads();
+            if (valid) {
+                const uint32_t pos = s_wcnt[warp][dg] + rank;
+                keyB[pos] = key;
+                idxB[pos] = id;
+            }
+            __syncthreads();
+        }
+        uint32_t* t;
+        t = keyA; keyA = keyB; keyB = t;
+        t = idxA; idxA = idxB; idxB = t;
+        __syncthreads();
+    }
+    uint32_t* out = order + (long long)img * kcap;
+    for (uint32_t i = tid; i < n; i += 1024) out[i] = idxA[i];
+}
+
+// ---------------------------------------------------------------------------
+// compute_descriptor (src/lib.rs:785-990) + output pack (src/lib.rs:164-174).
+// One warp per keypoint; the (6,6,8) histogram lives in shared memory.
+// ---------------------------------------------------------------------------
+constexpr int DESC_WARPS = 8;
+constexpr int DESC_HIST = 6 * 6 * 8;
+
+struct DescTarget {
+    const float* img;  // layer base
+    int w, h, pitch;
+    float x, y, scale, orientation;  // arguments of compute_descriptor
+};
+
+__device__ __forceinline__ void descriptor_warp(const DescTarget t, float* hist /* smem [288] */, int lane,
+                                                const uint64_t* s_tab, uint8_t* out /* 128 B */) {
+    for (int k = lane; k < DESC_HIST; k += 32) hist[k] = 0.f;
+    // `x.round() as usize` (src/lib.rs:796-797): saturating, negative -> 0
+    const float xr = roundf(t.x), yr = roundf(t.y);
+    const int x = xr > 0.f ? (int)fminf(xr, 1e9f) : 0;
+    const int y = yr > 0.f ? (int)fminf(yr, 1e9f) : 0;
+    const float BIN_ANGLE_STEP = 8.0f / 360.0f;
+    const float hist_width = 3.0f * t.scale;
+    const int radius = (int)roundf(3.0f * t.scale * sqrtf(2.0f) * 5.0f * 0.5f);  // :800
+    const float rad = t.orientation * (3.14159265358979323846f / 180.0f);          // f32::to_radians
+    double sd, cd;
+    sincos((double)rad, &sd, &cd);  // libm sinf/cosf are (nearly always) correctly rounded: round once from f64
+    const float sin_s = (float)sd / hist_width, cos_s = (float)cd / hist_width;
+    const int side = 2 * radius + 1, total = side * side;
+    const int w = t.w, h = t.h, pitch = t.pitch;
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        if (idx < total) {
+            const int yq = idx / side;
+            const int yw = yq - radius, xw = idx - yq * side - radius;
+            const float col_rot = (float)xw * cos_s - (float)yw * sin_s;
+            const float row_rot = (float)xw * sin_s + (float)yw * cos_s;
+            const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
+            const int ay = y + yw, ax = x + xw;
+            if (row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f && ay > 0 && ay < h - 1 &&
+                ax > 0 && ax < w - 1) {
+                const float* c = t.img + (long long)ay * pitch + ax;
+                const float dx = __ldg(c + 1) - __ldg(c - 1);
+                const float dy = __ldg(c - pitch) - __ldg(c + pitch);
+                const float wgt = col_rot * col_rot + row_rot * row_rot;
+                const float weight = sbm::expf_glibc(s_tab, wgt * -0.125f);  // -2 / 4^2, :859
+                // ((atan2_f64(dy,dx).to_degrees() + 360) % 360) as f32 - orientation, :871
+                float deg = atan2f(dy, dx) * 57.29577951308232f;
+                if (deg < 0.f) deg += 360.0f;
+                if (deg >= 360.0f) deg -= 360.0f;
+                const float orient = deg - t.orientation;
+                float mag = sqrtf(dx * dx + dy * dy);
+                const float rb = row_bin - 0.5f, cb = col_bin - 0.5f;
+                mag = mag * weight;
+                const float obin = orient * BIN_ANGLE_STEP;
+                const float row_floor = floorf(rb), col_floor = floorf(cb), ori_floor = floorf(obin);
+                const float row_frac = rb - row_floor, col_frac = cb - col_floor, ori_frac = obin - ori_floor;
+                const float c1 = mag * row_frac, c0 = mag - c1;
+                const float c11 = c1 * col_frac, c10 = c1 - c11;
+                const float c01 = c0 * col_frac, c00 = c0 - c01;
+                const float c111 = c11 * ori_frac, c110 = c11 - c111;
+                const float c101 = c10 * ori_frac, c100 = c10 - c101;
+                const float c011 = c01 * ori_frac, c010 = c01 - c011;
+                const float c001 = c00 * ori_frac, c000 = c00 - c001;
+                const int r1 = (int)(row_floor + 1.f), q1 = (int)(col_floor + 1.f);
+                float of = ori_floor;
+                if (of < 0.f) of += 8.f;
+                else if (of >= 8.f) of -= 8.f;
+                int o0 = (int)of;
+                o0 = min(max(o0, 0), 7);
+                const int o1 = (o0 + 1 >= 8) ? 0 : o0 + 1;
+                float* h0 = hist + (r1 * 6 + q1) * 8;
+                atomicAdd(h0 + o0, c000);
+                atomicAdd(h0 + o1, c001);
+                atomicAdd(h0 + 8 + o0, c010);
+                atomicAdd(h0 + 8 + o1, c011);
+                atomicAdd(h0 + 48 + o0, c100);
+                atomicAdd(h0 + 48 + o1, c101);
+                atomicAdd(h0 + 56 + o0, c110);
+                atomicAdd(h0 + 56 + o1, c111);
+            }
+        }
+    }
+    __syncwarp();
+    // hist[1..5, 1..5, :] flattened (src/lib.rs:951): lane owns flat[4*lane .. 4*lane+3]
+    const int fr = lane >> 3, fc = (lane >> 1) & 3, fo = (lane & 1) * 4;
+    float f[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) f[k] = hist[((fr + 1) * 6 + fc + 1) * 8 + fo + k];
+    // l2 norm in chunks of four, chunks added in order (src/lib.rs:957-962)
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) s += f[k] * f[k];
+    float acc = 0.f;
+    for (int j = 0; j < 32; j++) {
+        const float sj = __shfl_sync(0xffffffffu, s, j);
+        acc = (j == 0) ? sj : acc + sj;
+    }
+    const float cap = sqrtf(acc) * 0.2f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) f[k] = fminf(f[k], cap);
+    s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) s += f[k] * f[k];
+    acc = 0.f;
+    for (int j = 0; j < 32; j++) {
+        const float sj = __shfl_sync(0xffffffffu, s, j);
+        acc = (j == 0) ? sj : acc + sj;
+    }
+    const float norm = 512.0f / fmaxf(sqrtf(acc), 1.1920929e-07f);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float q = roundf(f[k] * norm);  // f >= 0; NaN (never produced) would map to 0 like `as i32`
+        const int qi = (q > 255.f) ? 255 : (q >= 0.f ? (int)q : 0);
+        packed |= (uint32_t)qi << (8 * k);
+    }
+    reinterpret_cast<uint32_t*>(out)[lane] = packed;
+    __syncwarp();
+}
+
+struct DescParams {
+    PyrLayout L;
+    const float* gauss;         // Gaussian arena, image 0
+    const DevKeyPoint* kps;     // [img][kcap] natural order
+    const uint32_t* kp_count;   // [img]
+    const uint32_t* order;      // [img][kcap] response-sorted permutation (used when limit < count)
+    uint32_t kcap;
+    long long limit;            // features_limit, < 0 == None
+    const uint32_t* out_count;  // [img] keypoints returned per image
+    const uint32_t* out_off;    // [img] offset of image's first keypoint in the dense outputs
+    OutKeyPoint* out_kps;       // dense, batch-wide
+    uint8_t* out_desc;          // dense, batch-wide, 128 B per keypoint
+};
+
+// per-image output counts (features_limit applied, src/lib.rs:156-161) and their
+// exclusive scan over the images of the batch; out_off[n_img] = total.  One CTA.
+__global__ void __launch_bounds__(1024) k_out_offsets(const uint32_t* __restrict__ kp_count, uint32_t kcap,
+                                                       long long limit, int n_img, uint32_t* __restrict__ out_count,
+                                                       uint32_t* __restrict__ out_off) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t s_run;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < n_img; base += 1024) {
+        const int i = base + tid;
+        uint32_t c = 0;
+        if (i < n_img) {
+            c = min(kp_count[i], kcap);
+            if (limit >= 0 && (unsigned long long)limit < c) c = (uint32_t)limit;
+            out_count[i] = c;
+        }
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = wsum[lane], sc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, sc, d);
+                if (lane >= d) sc += t;
+            }
+            wsum[lane] = sc - v;
+        }
+        __syncthreads();
+        const uint32_t run = s_run;
+        if (i < n_img) out_off[i] = run + wsum[warp] + incl - c;
+        __syncthreads();
+        if (tid == 1023) s_run = run + wsum[31] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) out_off[n_img] = s_run;
+}
+
+// compute_descriptors (src/lib.rs:759-782) over the keypoint list of each image and
+// the final KeyPoint records (src/lib.rs:164-174).
+__global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams P) {
+    __shared__ uint64_t s_tab[32];
+    __shared__ float s_hist[DESC_WARPS][DESC_HIST];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long img = blockIdx.y;
+    const uint32_t n = min(P.kp_count[img], P.kcap);
+    const uint32_t n_out = P.out_count[img];
+    const bool limited = n_out < n;
+    const DevKeyPoint* kps = P.kps + img * (long long)P.kcap;
+    const uint32_t* order = P.order + img * (long long)P.kcap;
+    const float* gimg = P.gauss + img * P.L.img_floats;
+    const long long obase = P.out_off[img];
+    for (uint32_t j = blockIdx.x * DESC_WARPS + warp; j < n_out; j += gridDim.x * DESC_WARPS) {
+        const DevKeyPoint kp = kps[limited ? order[j] : j];
+        const OctLayout& ol = P.L.o[kp.octave];
+        DescTarget t;
+        t.img = gimg + ol.off + (long long)kp.scale * ol.layer_stride;
+        t.w = ol.w; t.h = ol.h; t.pitch = ol.pitch;
+        const float f = pow2i(-kp.octave);  // 2_f32.powi(-octave), src/lib.rs:768
+        t.x = kp.x * f; t.y = kp.y * f; t.scale = kp.size * f;
+        t.orientation = 360.0f - kp.angle;   // :766
+        descriptor_warp(t, s_hist[warp], lane, s_tab, P.out_desc + (obase + j) * DESC_SIZE);
+        if (lane == 0) {
+            OutKeyPoint o;  // DELTA_MIN = 0.5 undoes the seed upsampling, src/lib.rs:168-170
+            o.x = kp.x * 0.5f; o.y = kp.y * 0.5f; o.size = kp.size * 0.5f;
+            o.angle = kp.angle; o.response = kp.response;
+            P.out_kps[obase + j] = o;
+        }
+    }
+}
+
+// compute_descriptor on caller-supplied keypoints and a dense f32 image
+// (benches/descriptor.rs:18-32 shape; src/lib.rs:785).
+struct DescIn { float x, y, scale, orientation; };
+__global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor_list(const float* __restrict__ img, int w, int h,
+                                                                      int pitch, const DescIn* __restrict__ kps,
+                                                                      unsigned long long n, uint8_t* __restrict__ out) {
+    __shared__ uint64_t s_tab[32];
+    __shared__ float s_hist[DESC_WARPS][DESC_HIST];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * DESC_WARPS + warp; j < n;
+         j += (unsigned long long)gridDim.x * DESC_WARPS) {
+        const DescIn k = kps[j];
+        DescTarget t;
+        t.img = img; t.w = w; t.h = h; t.pitch = pitch;
+        t.x = k.x; t.y = k.y; t.scale = k.scale; t.orientation = k.orientation;
+        descriptor_warp(t, s_hist[warp], lane, s_tab, out + j * DESC_SIZE);
+    }
+}
+
+}  // namespace sb

@@ -1,0 +1,1134 @@
+// sift_b200.cu -- host runtime + C ABI (include/sift_b200.h) of the B200-native SIFT extractor.
+//
+// One context = one device, two "slots" (stream + device arenas) so that the
+// upload / compute / download of consecutive image groups overlap.  Every image
+// of a group is processed by the same launches (grid.z / grid.y = image), the
+// per-image results are written densely in image order, and the only host
+// synchronisation per group is the read of the per-image keypoint counts.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --fmad=false -shared ...
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sift_b200.h"
+#include "sb_common.cuh"
+#include "sb_keypoints.cuh"
+#include "sb_pyramid.cuh"
+
+using namespace sb;
+
+static_assert(sizeof(OutKeyPoint) == sizeof(sb200_keypoint), "keypoint layout");
+static_assert(sizeof(DescIn) == sizeof(sb200_desc_in), "desc_in layout");
+
+namespace {
+
+const char* kStageNames[SB200_STAGE_COUNT] = {"seed", "blur", "extrema", "refine", "orient", "descriptor"};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_counts = nullptr;
+    // input
+    uint8_t* d_in = nullptr;
+    uint8_t* h_in = nullptr;  // pinned staging for pageable callers
+    size_t in_cap = 0;
+    // pyramid
+    float* d_gauss = nullptr;
+    uint32_t* d_mask = nullptr;
+    uint32_t* d_rows = nullptr;  // [B][img_rows] counters, followed by [B] cand_count, kp_count
+    uint32_t* d_rowoff = nullptr;
+    uint32_t* d_counts = nullptr;  // cand_count[B], kp_count[B], out_count[B], out_off[B+1]
+    // candidates / keypoints
+    uint32_t* d_keys = nullptr;
+    Refined* d_refined = nullptr;
+    uint32_t* d_nori = nullptr;
+    float* d_angles = nullptr;
+    uint32_t* d_kpoff = nullptr;
+    DevKeyPoint* d_kps = nullptr;
+    uint32_t* d_sort = nullptr;
+    uint32_t* d_order = nullptr;
+    OutKeyPoint* d_out_kps = nullptr;
+    uint8_t* d_out_desc = nullptr;
+    uint32_t* h_counts = nullptr;  // pinned mirror of d_counts
+    // state of the group in flight
+    uint32_t n_imgs = 0;
+    uint64_t first_img = 0;
+    bool busy = false;
+};
+
+struct StageEvents {
+    cudaEvent_t a, b;
+    int stage;
+};
+
+}  // namespace
+
+struct sb200_ctx {
+    int device = 0;
+    uint32_t max_w = 0, max_h = 0, max_batch = 0, cap = 0;
+    std::string err;
+    Slot slot[2];
+    // layout of the current image size
+    PyrLayout L{};
+    uint32_t cur_w = 0, cur_h = 0;
+    // capacities the arenas were sized for
+    long long gauss_floats_cap = 0, mask_words_cap = 0;
+    int rows_cap = 0;
+    // results (pinned, grow-only)
+    uint64_t* h_offsets = nullptr;
+    size_t offsets_cap = 0;
+    sb200_keypoint* h_kps = nullptr;
+    uint8_t* h_desc = nullptr;
+    size_t res_cap = 0;
+    uint64_t res_n = 0;
+    // staged API state
+    bool have_pyramid = false;
+    bool have_single = false;  // slot[0] holds the intermediates of a single-image run
+    int64_t last_limit = -1;
+    // descriptor-only scratch
+    float* d_dimg = nullptr;
+    size_t dimg_cap = 0;
+    DescIn* d_dkps = nullptr;
+    uint8_t* d_ddesc = nullptr;
+    size_t dkps_cap = 0;
+    // measurement
+    bool profiling = false;
+    std::vector<StageEvents> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double stage_ms[SB200_STAGE_COUNT] = {0};
+    uint64_t stage_launches[SB200_STAGE_COUNT] = {0};
+    uint64_t launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    void* d_flush = nullptr;
+    size_t flush_bytes = 0;
+    int sm_count = 148;
+};
+
+namespace {
+
+int fail(sb200_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, SB200_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),      \
+                        __FILE__, __LINE__);                                                             \
+    } while (0)
+
+// ---- layout (src/lib.rs:133-134, 245-248) ---------------------------------
+int octave_count(uint32_t W2, uint32_t H2) {
+    const uint32_t min_axis = std::min(W2, H2);
+    const float lg = log2f((float)min_axis) - 2.0f;
+    const float r = roundf(lg);
+    long long n = (r > 0.f ? (long long)r : 0) + 1;  // `as usize` saturates at 0
+    if (n > MAX_OCT) n = MAX_OCT;
+    return (int)n;
+}
+
+PyrLayout make_layout(uint32_t w, uint32_t h) {
+    PyrLayout L{};
+    int cw = (int)w * 2, ch = (int)h * 2;
+    L.n_oct = octave_count((uint32_t)cw, (uint32_t)ch);
+    long long off = 0, moff = 0;
+    int rows = 0;
+    for (int o = 0; o < L.n_oct; o++) {
+        OctLayout& ol = L.o[o];
+        ol.w = cw; ol.h = ch;
+        ol.pitch = (std::max(cw, 1) + 31) / 32 * 32;
+        ol.mask_pitch = (std::max(cw, 1) + 31) / 32;
+        ol.layer_stride = (long long)ol.pitch * std::max(ch, 1);
+        ol.off = off;
+        off += ol.layer_stride * N_LAYERS;
+        ol.mask_off = moff;
+        moff += (long long)ol.mask_pitch * std::max(ch, 1) * SCALES_PER_OCTAVE;
+        ol.row_base = rows;
+        rows += std::max(ch, 1) * SCALES_PER_OCTAVE;
+        ol.scanned = !(ch < 2 * IMAGE_BORDER || cw < 2 * IMAGE_BORDER);
+        cw /= 2; ch /= 2;
+    }
+    L.img_floats = off;
+    L.img_mask_words = moff;
+    L.img_rows = rows;
+    return L;
+}
+
+// OpenCV getGaussianKernel(ksize, sigma, CV_32F) (what gaussian_blur_def builds,
+// src/opencv_processing.rs:51-57): exp(-x^2 / 2 sigma^2) in double, normalised, stored f32.
+void gaussian_taps(double sigma, float* out, int& ksize) {
+    ksize = ((int)lrint(sigma * 8.0 + 1.0)) | 1;
+    const int r = ksize / 2;
+    double t[64], sum = 0.0;
+    const double scale2x = -0.5 / (sigma * sigma);
+    for (int i = 0; i < ksize; i++) {
+        const double x = (double)(i - r);
+        t[i] = exp(scale2x * x * x);
+        sum += t[i];
+    }
+    const double inv = 1.0 / sum;
+    for (int i = 0; i < ksize; i++) out[i] = (float)(t[i] * inv);
+}
+
+// sigmas of src/lib.rs:207 and :220-229
+double seed_sigma() { return sqrt(0.8 * 0.8 - 0.5 * 0.5) * 2.0; }
+double octave_sigma(int s) {
+    const double m = pow(2.0, 2.0 / 3.0);
+    int e = s - 1;
+    const bool recip = e < 0;
+    int b = recip ? -e : e;
+    double base = m, a = 1.0;
+    for (;;) {  // powi == square-and-multiply
+        if (b & 1) a *= base;
+        b /= 2;
+        if (b == 0) break;
+        base *= base;
+    }
+    if (recip) a = 1.0 / a;
+    const double bb = a * m;
+    return sqrt(bb - a) * 0.8 * 2.0;
+}
+
+// ---- stage timing ----------------------------------------------------------
+cudaEvent_t get_event(sb200_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageScope {
+    sb200_ctx* ctx;
+    cudaStream_t st;
+    int stage;
+    cudaEvent_t a = nullptr;
+    StageScope(sb200_ctx* c, cudaStream_t s, int stg) : ctx(c), st(s), stage(stg) {
+        if (ctx->profiling) {
+            a = get_event(ctx);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~StageScope() {
+        if (ctx->profiling) {
+            cudaEvent_t b = get_event(ctx);
+            cudaEventRecord(b, st);
+            ctx->pending.push_back({a, b, stage});
+        }
+    }
+};
+
+void drain_stage_events(sb200_ctx* ctx) {
+    for (auto& p : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
+            ctx->stage_ms[p.stage] += ms;
+        ctx->ev_pool.push_back(p.a);
+        ctx->ev_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+inline void count_launch(sb200_ctx* ctx, int stage, int n = 1) {
+    ctx->launches += n;
+    ctx->stage_launches[stage] += n;
+}
+
+// ---- allocation --------------------------------------------------------------
+template <class T>
+cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+int alloc_slot(sb200_ctx* ctx, Slot& s) {
+    const size_t B = ctx->max_batch, cap = ctx->cap;
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s.ev_counts, cudaEventDisableTiming));
+    s.in_cap = (size_t)ctx->max_w * ctx->max_h * B;
+    CU(dalloc(&s.d_in, s.in_cap));
+    CU(cudaHostAlloc((void**)&s.h_in, std::max<size_t>(s.in_cap, 1), cudaHostAllocDefault));
+    CU(dalloc(&s.d_gauss, (size_t)ctx->gauss_floats_cap * B));
+    CU(dalloc(&s.d_mask, (size_t)ctx->mask_words_cap * B));
+    CU(dalloc(&s.d_rows, (size_t)ctx->rows_cap * B));
+    CU(dalloc(&s.d_rowoff, (size_t)ctx->rows_cap * B));
+    CU(dalloc(&s.d_counts, 4 * B + 1));
+    CU(cudaHostAlloc((void**)&s.h_counts, (4 * B + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+    CU(dalloc(&s.d_keys, cap * B));
+    CU(dalloc(&s.d_refined, cap * B));
+    CU(dalloc(&s.d_nori, cap * B));
+    CU(dalloc(&s.d_angles, cap * B * MAX_ORI));
+    CU(dalloc(&s.d_kpoff, cap * B));
+    CU(dalloc(&s.d_kps, cap * B));
+    CU(dalloc(&s.d_sort, 4 * cap * B));
+    CU(dalloc(&s.d_order, cap * B));
+    CU(dalloc(&s.d_out_kps, cap * B));
+    CU(dalloc(&s.d_out_desc, cap * B * DESC_SIZE));
+    return SB200_OK;
+}
+
+void free_slot(Slot& s) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.ev_counts) cudaEventDestroy(s.ev_counts);
+    cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
+    cudaFree(s.d_rowoff); cudaFree(s.d_counts); cudaFreeHost(s.h_counts); cudaFree(s.d_keys);
+    cudaFree(s.d_refined); cudaFree(s.d_nori); cudaFree(s.d_angles); cudaFree(s.d_kpoff); cudaFree(s.d_kps);
+    cudaFree(s.d_sort); cudaFree(s.d_order); cudaFree(s.d_out_kps); cudaFree(s.d_out_desc);
+    s = Slot{};
+}
+
+int ensure_result_capacity(sb200_ctx* ctx, uint64_t need_kp, uint64_t need_imgs) {
+    if (need_imgs + 1 > ctx->offsets_cap) {
+        size_t ncap = std::max<size_t>(need_imgs + 1, ctx->offsets_cap * 2 + 16);
+        uint64_t* p = nullptr;
+        CU(cudaHostAlloc((void**)&p, ncap * sizeof(uint64_t), cudaHostAllocDefault));
+        if (ctx->h_offsets) {
+            memcpy(p, ctx->h_offsets, ctx->offsets_cap * sizeof(uint64_t));
+            cudaFreeHost(ctx->h_offsets);
+        }
+        ctx->h_offsets = p;
+        ctx->offsets_cap = ncap;
+    }
+    if (need_kp > ctx->res_cap) {
+        // pending async copies into the old buffers must land before they move
+        for (auto& s : ctx->slot) if (s.stream) CU(cudaStreamSynchronize(s.stream));
+        size_t ncap = std::max<size_t>(need_kp, ctx->res_cap * 2 + 4096);
+        sb200_keypoint* k = nullptr;
+        uint8_t* d = nullptr;
+        CU(cudaHostAlloc((void**)&k, ncap * sizeof(sb200_keypoint), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&d, ncap * SB200_DESC_SIZE, cudaHostAllocDefault));
+        if (ctx->h_kps) {
+            memcpy(k, ctx->h_kps, ctx->res_n * sizeof(sb200_keypoint));
+            memcpy(d, ctx->h_desc, ctx->res_n * SB200_DESC_SIZE);
+            cudaFreeHost(ctx->h_kps);
+            cudaFreeHost(ctx->h_desc);
+        }
+        ctx->h_kps = k;
+        ctx->h_desc = d;
+        ctx->res_cap = ncap;
+    }
+    return SB200_OK;
+}
+
+int set_image_size(sb200_ctx* ctx, uint32_t w, uint32_t h) {
+    if (w == 0 || h == 0) return fail(ctx, SB200_E_INVALID, "empty image (%ux%u)", w, h);
+    if (w > ctx->max_w || h > ctx->max_h)
+        return fail(ctx, SB200_E_INVALID, "image %ux%u larger than the context's %ux%u", w, h, ctx->max_w, ctx->max_h);
+    if (w != ctx->cur_w || h != ctx->cur_h) {
+        PyrLayout L = make_layout(w, h);
+        if (L.img_floats > ctx->gauss_floats_cap || L.img_mask_words > ctx->mask_words_cap || L.img_rows > ctx->rows_cap)
+            return fail(ctx, SB200_E_INVALID, "internal: layout of %ux%u exceeds the arena", w, h);
+        ctx->L = L;
+        ctx->cur_w = w;
+        ctx->cur_h = h;
+        ctx->have_pyramid = ctx->have_single = false;
+    }
+    return SB200_OK;
+}
+
+// ---- launches -----------------------------------------------------------------
+template <int LI, bool SEED, bool DEC>
+int set_blur_attr(sb200_ctx* ctx) {
+    CU(cudaFuncSetAttribute(k_blur<LI, SEED, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)BlurCfg<LI>::SMEM));
+    return SB200_OK;
+}
+
+template <int LI, bool SEED, bool DEC>
+void launch_blur(cudaStream_t st, const BlurParams& p, uint32_t n) {
+    using C = BlurCfg<LI>;
+    dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + C::TH - 1) / C::TH, n);
+    k_blur<LI, SEED, DEC><<<grid, C::THREADS, C::SMEM, st>>>(p);
+}
+
+// Gaussian scale space + DoG/extrema masks for the n images staged in slot.d_in
+int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, uint32_t in_stride,
+                    uint64_t in_img_stride, const uint8_t* d_in) {
+    const PyrLayout& L = ctx->L;
+    cudaStream_t st = s.stream;
+    CU(cudaMemsetAsync(s.d_rows, 0, (size_t)L.img_rows * n * sizeof(uint32_t), st));
+    {
+        StageScope sc(ctx, st, SB200_STAGE_SEED);
+        BlurParams p{};
+        p.dst = s.d_gauss + L.o[0].off;
+        p.img_stride = L.img_floats;
+        p.w = L.o[0].w; p.h = L.o[0].h; p.pitch = L.o[0].pitch;
+        p.in = d_in; p.in_img_stride = (long long)in_img_stride;
+        p.in_w = (int)w; p.in_h = (int)h; p.in_stride = (int)in_stride;
+        launch_blur<0, true, false>(st, p, n);
+        count_launch(ctx, SB200_STAGE_SEED);
+    }
+    for (int o = 0; o < L.n_oct; o++) {
+        const OctLayout& ol = L.o[o];
+        if (ol.w < 1 || ol.h < 1) continue;
+        {
+            StageScope sc(ctx, st, SB200_STAGE_BLUR);
+            for (int l = 1; l < N_LAYERS; l++) {
+                BlurParams p{};
+                p.src = s.d_gauss + ol.off + (long long)(l - 1) * ol.layer_stride;
+                p.dst = s.d_gauss + ol.off + (long long)l * ol.layer_stride;
+                p.img_stride = L.img_floats;
+                p.w = ol.w; p.h = ol.h; p.pitch = ol.pitch;
+                const bool dec = (l == 3) && (o + 1 < L.n_oct) && L.o[o + 1].w >= 1 && L.o[o + 1].h >= 1;
+                if (dec) {
+                    p.dec = s.d_gauss + L.o[o + 1].off;
+                    p.dec_w = L.o[o + 1].w; p.dec_h = L.o[o + 1].h; p.dec_pitch = L.o[o + 1].pitch;
+                }
+                switch (l) {
+                    case 1: launch_blur<1, false, false>(st, p, n); break;
+                    case 2: launch_blur<2, false, false>(st, p, n); break;
+                    case 3:
+                        if (dec) launch_blur<3, false, true>(st, p, n);
+                        else launch_blur<3, false, false>(st, p, n);
+                        break;
+                    case 4: launch_blur<4, false, false>(st, p, n); break;
+                    default: launch_blur<5, false, false>(st, p, n); break;
+                }
+                count_launch(ctx, SB200_STAGE_BLUR);
+            }
+        }
+        if (ol.scanned) {
+            StageScope sc(ctx, st, SB200_STAGE_EXTREMA);
+            ExtremaParams e{};
+            e.gauss = s.d_gauss + ol.off;
+            e.img_stride = L.img_floats;
+            e.layer_stride = ol.layer_stride;
+            e.w = ol.w; e.h = ol.h; e.pitch = ol.pitch;
+            e.mask = s.d_mask + ol.mask_off;
+            e.mask_img_stride = L.img_mask_words;
+            e.mask_pitch = ol.mask_pitch;
+            e.rows = s.d_rows + ol.row_base;
+            e.rows_img_stride = L.img_rows;
+            dim3 grid(ol.mask_pitch, (ol.h + EX_ROWS * EX_WARPS - 1) / (EX_ROWS * EX_WARPS), n);
+            k_extrema<<<grid, 32 * EX_WARPS, 0, st>>>(e);
+            count_launch(ctx, SB200_STAGE_EXTREMA);
+        }
+    }
+    CU(cudaGetLastError());
+    return SB200_OK;
+}
+
+KpParams make_kp_params(sb200_ctx* ctx, Slot& s) {
+    KpParams P{};
+    P.L = ctx->L;
+    P.gauss = s.d_gauss;
+    P.keys = s.d_keys;
+    P.cand_count = s.d_counts;
+    P.cap = ctx->cap;
+    P.refined = s.d_refined;
+    P.n_ori = s.d_nori;
+    P.angles = s.d_angles;
+    P.kp_off = s.d_kpoff;
+    P.kp_count = s.d_counts + ctx->max_batch;
+    P.kps = s.d_kps;
+    P.kcap = ctx->cap;
+    return P;
+}
+
+// candidates -> keypoints -> descriptors for the n pyramids resident in the slot
+int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
+    const PyrLayout& L = ctx->L;
+    cudaStream_t st = s.stream;
+    const uint32_t B = ctx->max_batch;
+    uint32_t* cand_count = s.d_counts;
+    uint32_t* kp_count = s.d_counts + B;
+    uint32_t* out_count = s.d_counts + 2 * B;
+    uint32_t* out_off = s.d_counts + 3 * B;
+    KpParams P = make_kp_params(ctx, s);
+    const int gx = std::max(1, std::min(4 * ctx->sm_count, (int)(8 * ctx->sm_count / std::max(1u, n)) + 1));
+    {
+        StageScope sc(ctx, st, SB200_STAGE_EXTREMA);
+        k_rowscan<<<n, 1024, 0, st>>>(s.d_rows, s.d_rowoff, L.img_rows, cand_count);
+        dim3 grid((L.img_rows + 7) / 8, n);
+        k_compact<<<grid, 256, 0, st>>>(L, s.d_mask, s.d_rows, s.d_rowoff, s.d_keys, ctx->cap);
+        count_launch(ctx, SB200_STAGE_EXTREMA, 2);
+    }
+    {
+        StageScope sc(ctx, st, SB200_STAGE_REFINE);
+        k_refine<<<dim3(gx, n), 128, 0, st>>>(P);
+        count_launch(ctx, SB200_STAGE_REFINE);
+    }
+    {
+        StageScope sc(ctx, st, SB200_STAGE_ORIENT);
+        k_orient<<<dim3(gx, n), 32 * ORI_WARPS, 0, st>>>(P);
+        k_kpscan<<<n, 1024, 0, st>>>(P);
+        k_emit<<<dim3(gx, n), 256, 0, st>>>(P);
+        count_launch(ctx, SB200_STAGE_ORIENT, 3);
+    }
+    {
+        StageScope sc(ctx, st, SB200_STAGE_DESCRIPTOR);
+        if (limit >= 0) {
+            k_sort_response<<<n, 1024, 0, st>>>(s.d_kps, kp_count, ctx->cap, s.d_sort, s.d_order);
+            count_launch(ctx, SB200_STAGE_DESCRIPTOR);
+        }
+        k_out_offsets<<<1, 1024, 0, st>>>(kp_count, ctx->cap, (long long)limit, (int)n, out_count, out_off);
+        DescParams D{};
+        D.L = L;
+        D.gauss = s.d_gauss;
+        D.kps = s.d_kps;
+        D.kp_count = kp_count;
+        D.order = s.d_order;
+        D.kcap = ctx->cap;
+        D.limit = limit;
+        D.out_count = out_count;
+        D.out_off = out_off;
+        D.out_kps = s.d_out_kps;
+        D.out_desc = s.d_out_desc;
+        k_descriptor<<<dim3(gx, n), 32 * DESC_WARPS, 0, st>>>(D);
+        count_launch(ctx, SB200_STAGE_DESCRIPTOR, 2);
+    }
+    CU(cudaGetLastError());
+    return SB200_OK;
+}
+
+bool is_device_accessible_host(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// upload + full pipeline + async read-back of the counts for one group
+int launch_group(sb200_ctx* ctx, Slot& s, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                 uint64_t image_stride, int64_t limit, uint64_t first_img) {
+    cudaStream_t st = s.stream;
+    const bool contiguous = (image_stride == (uint64_t)stride * h);
+    if (is_device_accessible_host(gray)) {
+        if (contiguous) {
+            CU(cudaMemcpy2DAsync(s.d_in, w, gray, stride, w, (size_t)h * n, cudaMemcpyHostToDevice, st));
+        } else {
+            for (uint32_t i = 0; i < n; i++)
+                CU(cudaMemcpy2DAsync(s.d_in + (size_t)i * w * h, w, gray + i * image_stride, stride, w, h,
+                                     cudaMemcpyHostToDevice, st));
+        }
+    } else {
+        // pageable memory: pack into the pinned staging buffer, then one async copy
+        CU(cudaStreamSynchronize(st));  // staging buffer may still feed the previous upload
+        for (uint32_t i = 0; i < n; i++) {
+            const uint8_t* src = gray + i * image_stride;
+            uint8_t* dst = s.h_in + (size_t)i * w * h;
+            if (stride == w) memcpy(dst, src, (size_t)w * h);
+            else for (uint32_t y = 0; y < h; y++) memcpy(dst + (size_t)y * w, src + (size_t)y * stride, w);
+        }
+        CU(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)w * h * n, cudaMemcpyHostToDevice, st));
+    }
+    int rc = enqueue_pyramid(ctx, s, n, w, h, w, (uint64_t)w * h, s.d_in);
+    if (rc) return rc;
+    rc = enqueue_detect(ctx, s, n, limit);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s.h_counts, s.d_counts, (4 * (size_t)ctx->max_batch + 1) * sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(s.ev_counts, st));
+    s.n_imgs = n;
+    s.first_img = first_img;
+    s.busy = true;
+    return SB200_OK;
+}
+
+// waits for the group's counts, appends its results to the context's result arrays
+int collect_group(sb200_ctx* ctx, Slot& s) {
+    if (!s.busy) return SB200_OK;
+    CU(cudaEventSynchronize(s.ev_counts));
+    s.busy = false;
+    const uint32_t B = ctx->max_batch, n = s.n_imgs;
+    const uint32_t* cand = s.h_counts;
+    const uint32_t* kpc = s.h_counts + B;
+    const uint32_t* outoff = s.h_counts + 3 * B;
+    for (uint32_t i = 0; i < n; i++) {
+        if (cand[i] > ctx->cap || kpc[i] > ctx->cap)
+            return fail(ctx, SB200_E_CAPACITY,
+                        "image %llu: %u candidates / %u keypoints exceed the context capacity %u",
+                        (unsigned long long)(s.first_img + i), cand[i], kpc[i], ctx->cap);
+    }
+    const uint64_t total = outoff[n];
+    int rc = ensure_result_capacity(ctx, ctx->res_n + total, s.first_img + n);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++) ctx->h_offsets[s.first_img + i] = ctx->res_n + outoff[i];
+    ctx->h_offsets[s.first_img + n] = ctx->res_n + total;
+    if (total) {
+        CU(cudaMemcpyAsync(ctx->h_kps + ctx->res_n, s.d_out_kps, total * sizeof(sb200_keypoint),
+                           cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(ctx->h_desc + ctx->res_n * SB200_DESC_SIZE, s.d_out_desc, total * SB200_DESC_SIZE,
+                           cudaMemcpyDeviceToHost, s.stream));
+    }
+    ctx->res_n += total;
+    return SB200_OK;
+}
+
+void fill_result(sb200_ctx* ctx, uint32_t n_images, sb200_result* out) {
+    out->n = ctx->res_n;
+    out->n_images = n_images;
+    out->offsets = ctx->h_offsets;
+    out->keypoints = ctx->h_kps;
+    out->descriptors = ctx->h_desc;
+}
+
+int finish_all(sb200_ctx* ctx) {
+    for (auto& s : ctx->slot) CU(cudaStreamSynchronize(s.stream));
+    if (ctx->profiling) drain_stage_events(ctx);
+    return SB200_OK;
+}
+
+}  // namespace
+
+// ============================================================================
+// C ABI
+// ============================================================================
+extern "C" {
+
+const char* sb200_status_string(int status) {
+    switch (status) {
+        case SB200_OK: return "ok";
+        case SB200_E_INVALID: return "invalid argument";
+        case SB200_E_CUDA: return "CUDA error";
+        case SB200_E_CAPACITY: return "capacity exceeded";
+        case SB200_E_STATE: return "invalid state";
+        default: return "unknown status";
+    }
+}
+
+const char* sb200_last_error(const sb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+const char* sb200_stage_name(uint32_t stage) { return stage < SB200_STAGE_COUNT ? kStageNames[stage] : "?"; }
+
+int sb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return -SB200_E_CUDA;
+    }
+    return n;
+}
+
+int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, uint32_t max_kp, sb200_ctx** out) {
+    if (!out) return SB200_E_INVALID;
+    *out = nullptr;
+    if (max_w == 0 || max_h == 0 || max_batch == 0 || max_w > SB200_MAX_DIM || max_h > SB200_MAX_DIM ||
+        max_batch > 65535)
+        return SB200_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return SB200_E_CUDA;
+    }
+    sb200_ctx* ctx = new sb200_ctx();
+    ctx->device = device;
+    ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
+    ctx->cap = max_kp ? max_kp : std::max<uint32_t>(16384u, (uint32_t)((uint64_t)max_w * max_h / 8));
+    auto bail = [&](int rc) {
+        std::string e = ctx->err;
+        fprintf(stderr, "sb200_create: %s\n", e.c_str());
+        sb200_destroy(ctx);
+        return rc;
+    };
+    int rc = SB200_OK;
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop{};
+        CU(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        // arenas sized for the largest image; a smaller image can have at most as many of everything
+        PyrLayout L = make_layout(max_w, max_h);
+        ctx->gauss_floats_cap = L.img_floats;
+        ctx->mask_words_cap = L.img_mask_words;
+        ctx->rows_cap = L.img_rows;
+        // Gaussian taps -> constant memory
+        float taps[N_LAYERS][32];
+        memset(taps, 0, sizeof taps);
+        for (int l = 0; l < N_LAYERS; l++) {
+            int ks = 0;
+            gaussian_taps(l == 0 ? seed_sigma() : octave_sigma(l), taps[l], ks);
+            if (ks != 2 * blur_radius(l) + 1)
+                return fail(ctx, SB200_E_INVALID, "internal: tap count %d of kernel %d", ks, l);
+        }
+        CU(cudaMemcpyToSymbol(c_taps, taps, sizeof taps));
+        int r;
+        if ((r = set_blur_attr<0, true, false>(ctx))) return r;
+        if ((r = set_blur_attr<1, false, false>(ctx))) return r;
+        if ((r = set_blur_attr<2, false, false>(ctx))) return r;
+        if ((r = set_blur_attr<3, false, false>(ctx))) return r;
+        if ((r = set_blur_attr<3, false, true>(ctx))) return r;
+        if ((r = set_blur_attr<4, false, false>(ctx))) return r;
+        if ((r = set_blur_attr<5, false, false>(ctx))) return r;
+        for (auto& s : ctx->slot)
+            if ((r = alloc_slot(ctx, s))) return r;
+        CU(cudaEventCreate(&ctx->t0));
+        CU(cudaEventCreate(&ctx->t1));
+        return SB200_OK;
+    };
+    rc = body();
+    if (rc) return bail(rc);
+    *out = ctx;
+    return SB200_OK;
+}
+
+void sb200_destroy(sb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& s : ctx->slot) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        free_slot(s);
+    }
+    for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    cudaFreeHost(ctx->h_offsets); cudaFreeHost(ctx->h_kps); cudaFreeHost(ctx->h_desc);
+    cudaFree(ctx->d_dimg); cudaFree(ctx->d_dkps); cudaFree(ctx->d_ddesc); cudaFree(ctx->d_flush);
+    delete ctx;
+}
+
+int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                        uint64_t image_stride, int64_t features_limit, sb200_result* out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!gray || !out || n == 0 || stride < w) return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch");
+    CU(cudaSetDevice(ctx->device));
+    int rc = set_image_size(ctx, w, h);
+    if (rc) return rc;
+    for (auto& s : ctx->slot) CU(cudaStreamSynchronize(s.stream));  // results of the previous call are released
+    ctx->res_n = 0;
+    ctx->have_pyramid = false;
+    rc = ensure_result_capacity(ctx, 0, n);
+    if (rc) return rc;
+    const uint32_t B = ctx->max_batch;
+    uint32_t g = 0;
+    for (uint64_t first = 0; first < n; first += B, g++) {
+        Slot& s = ctx->slot[g & 1];
+        // groups complete in order: the slot's previous group (g-2) was collected before group g-1 launched
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(B, n - first);
+        rc = launch_group(ctx, s, gray + first * image_stride, cnt, w, h, stride, image_stride, features_limit, first);
+        if (rc) return rc;
+        if (g >= 1) {
+            rc = collect_group(ctx, ctx->slot[(g - 1) & 1]);
+            if (rc) return rc;
+        }
+    }
+    rc = collect_group(ctx, ctx->slot[(g - 1) & 1]);
+    if (rc) return rc;
+    rc = finish_all(ctx);
+    if (rc) return rc;
+    ctx->have_single = (n == 1);
+    ctx->have_pyramid = (n == 1);
+    ctx->last_limit = features_limit;
+    fill_result(ctx, n, out);
+    return SB200_OK;
+}
+
+int sb200_extract(sb200_ctx* ctx, const uint8_t* gray, uint32_t w, uint32_t h, uint32_t stride, int64_t features_limit,
+                  sb200_result* out) {
+    return sb200_extract_batch(ctx, gray, 1, w, h, stride, (uint64_t)stride * h, features_limit, out);
+}
+
+int sb200_extract_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n, uint32_t w, uint32_t h,
+                               uint32_t stride, uint64_t image_stride, int64_t features_limit) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!d_gray || n == 0 || n > ctx->max_batch || stride < w)
+        return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch_device");
+    CU(cudaSetDevice(ctx->device));
+    int rc = set_image_size(ctx, w, h);
+    if (rc) return rc;
+    Slot& s = ctx->slot[0];
+    rc = enqueue_pyramid(ctx, s, n, w, h, stride, image_stride, d_gray);
+    if (rc) return rc;
+    rc = enqueue_detect(ctx, s, n, features_limit);
+    if (rc) return rc;
+    s.n_imgs = n;
+    ctx->have_single = ctx->have_pyramid = (n == 1);
+    ctx->last_limit = features_limit;
+    return SB200_OK;
+}
+
+int sb200_device_result(sb200_ctx* ctx, uint32_t* counts, uint32_t n, const sb200_keypoint** d_keypoints,
+                        const uint8_t** d_descriptors, uint32_t* capacity_per_image) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    if (n > ctx->max_batch) return fail(ctx, SB200_E_INVALID, "n exceeds max_batch");
+    CU(cudaStreamSynchronize(s.stream));
+    if (counts && n)
+        CU(cudaMemcpy(counts, s.d_counts + 2 * ctx->max_batch, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (d_keypoints) *d_keypoints = reinterpret_cast<const sb200_keypoint*>(s.d_out_kps);
+    if (d_descriptors) *d_descriptors = s.d_out_desc;
+    if (capacity_per_image) *capacity_per_image = ctx->cap;
+    return SB200_OK;
+}
+
+int sb200_sync(sb200_ctx* ctx) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    return finish_all(ctx);
+}
+
+int sb200_precompute(sb200_ctx* ctx, const uint8_t* gray, uint32_t w, uint32_t h, uint32_t stride) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!gray || stride < w) return fail(ctx, SB200_E_INVALID, "bad arguments to precompute");
+    CU(cudaSetDevice(ctx->device));
+    int rc = set_image_size(ctx, w, h);
+    if (rc) return rc;
+    Slot& s = ctx->slot[0];
+    for (auto& sl : ctx->slot) CU(cudaStreamSynchronize(sl.stream));
+    for (uint32_t y = 0; y < h; y++) memcpy(s.h_in + (size_t)y * w, gray + (size_t)y * stride, w);
+    CU(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)w * h, cudaMemcpyHostToDevice, s.stream));
+    rc = enqueue_pyramid(ctx, s, 1, w, h, w, (uint64_t)w * h, s.d_in);
+    if (rc) return rc;
+    rc = finish_all(ctx);
+    if (rc) return rc;
+    ctx->have_pyramid = true;
+    ctx->have_single = false;
+    return SB200_OK;
+}
+
+int sb200_extract_precomputed(sb200_ctx* ctx, int64_t features_limit, sb200_result* out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!out) return fail(ctx, SB200_E_INVALID, "null result");
+    if (!ctx->have_pyramid) return fail(ctx, SB200_E_STATE, "no pyramid resident: call sb200_precompute first");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    for (auto& sl : ctx->slot) CU(cudaStreamSynchronize(sl.stream));
+    ctx->res_n = 0;
+    int rc = ensure_result_capacity(ctx, 0, 1);
+    if (rc) return rc;
+    // the masks and row counters of the resident pyramid are intact: rerun detection only
+    rc = enqueue_detect(ctx, s, 1, features_limit);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s.h_counts, s.d_counts, (4 * (size_t)ctx->max_batch + 1) * sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaEventRecord(s.ev_counts, s.stream));
+    s.n_imgs = 1; s.first_img = 0; s.busy = true;
+    rc = collect_group(ctx, s);
+    if (rc) return rc;
+    rc = finish_all(ctx);
+    if (rc) return rc;
+    ctx->have_single = true;
+    ctx->last_limit = features_limit;
+    fill_result(ctx, 1, out);
+    return SB200_OK;
+}
+
+int sb200_pyramid_info(sb200_ctx* ctx, uint32_t* n_octaves, uint32_t* widths, uint32_t* heights, uint32_t cap) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!ctx->have_pyramid) return fail(ctx, SB200_E_STATE, "no pyramid resident");
+    if (n_octaves) *n_octaves = (uint32_t)ctx->L.n_oct;
+    for (uint32_t o = 0; o < cap && o < (uint32_t)ctx->L.n_oct; o++) {
+        if (widths) widths[o] = (uint32_t)ctx->L.o[o].w;
+        if (heights) heights[o] = (uint32_t)ctx->L.o[o].h;
+    }
+    return SB200_OK;
+}
+
+int sb200_pyramid_layer(sb200_ctx* ctx, uint32_t octave, uint32_t layer, float* out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!ctx->have_pyramid) return fail(ctx, SB200_E_STATE, "no pyramid resident");
+    if (!out || octave >= (uint32_t)ctx->L.n_oct || layer >= N_LAYERS) return fail(ctx, SB200_E_INVALID, "bad layer");
+    CU(cudaSetDevice(ctx->device));
+    const OctLayout& ol = ctx->L.o[octave];
+    if (ol.w < 1 || ol.h < 1) return SB200_OK;
+    Slot& s = ctx->slot[0];
+    CU(cudaMemcpy2DAsync(out, (size_t)ol.w * 4, s.d_gauss + ol.off + (long long)layer * ol.layer_stride,
+                         (size_t)ol.pitch * 4, (size_t)ol.w * 4, ol.h, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return SB200_OK;
+}
+
+int sb200_pyramid_dog(sb200_ctx* ctx, uint32_t octave, uint32_t layer, float* out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!ctx->have_pyramid) return fail(ctx, SB200_E_STATE, "no pyramid resident");
+    if (!out || octave >= (uint32_t)ctx->L.n_oct || layer >= N_DOG) return fail(ctx, SB200_E_INVALID, "bad layer");
+    CU(cudaSetDevice(ctx->device));
+    const OctLayout& ol = ctx->L.o[octave];
+    if (ol.w < 1 || ol.h < 1) return SB200_OK;
+    Slot& s = ctx->slot[0];
+    float* tmp = nullptr;
+    CU(cudaMalloc((void**)&tmp, (size_t)ol.w * ol.h * 4));
+    const float* a = s.d_gauss + ol.off + (long long)layer * ol.layer_stride;
+    k_dog_layer<<<dim3((ol.w + 127) / 128, ol.h), 128, 0, s.stream>>>(a, a + ol.layer_stride, tmp, ol.w, ol.h, ol.pitch);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)ol.w * ol.h * 4, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ctx, SB200_E_CUDA, "dog download: %s", cudaGetErrorString(e));
+    return SB200_OK;
+}
+
+int sb200_last_candidates(sb200_ctx* ctx, sb200_candidate* out, uint64_t cap, uint64_t* n) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!ctx->have_single) return fail(ctx, SB200_E_STATE, "no single-image run resident");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    CU(cudaStreamSynchronize(s.stream));
+    uint32_t cnt = 0;
+    CU(cudaMemcpy(&cnt, s.d_counts, 4, cudaMemcpyDeviceToHost));
+    if (n) *n = cnt;
+    const uint32_t m = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(cnt, ctx->cap), cap);
+    if (out && m) {
+        std::vector<uint32_t> keys(m);
+        CU(cudaMemcpy(keys.data(), s.d_keys, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < m; i++) {
+            int o, sc, y, x;
+            unpack_key(keys[i], o, sc, y, x);
+            out[i] = {o, sc, y, x};
+        }
+    }
+    return SB200_OK;
+}
+
+int sb200_last_sift_keypoints(sb200_ctx* ctx, sb200_sift_keypoint* out, uint64_t cap, uint64_t* n) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!ctx->have_single) return fail(ctx, SB200_E_STATE, "no single-image run resident");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    CU(cudaStreamSynchronize(s.stream));
+    uint32_t cnt = 0;
+    CU(cudaMemcpy(&cnt, s.d_counts + ctx->max_batch, 4, cudaMemcpyDeviceToHost));
+    if (n) *n = cnt;
+    const uint32_t m = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(cnt, ctx->cap), cap);
+    if (out && m) {
+        std::vector<DevKeyPoint> k(m);
+        CU(cudaMemcpy(k.data(), s.d_kps, (size_t)m * sizeof(DevKeyPoint), cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < m; i++)
+            out[i] = {k[i].x, k[i].y, k[i].size, k[i].angle, k[i].response, k[i].octave, k[i].scale};
+    }
+    return SB200_OK;
+}
+
+int sb200_compute_descriptors_device(sb200_ctx* ctx, const float* d_img, uint32_t w, uint32_t h, uint32_t stride,
+                                     const sb200_desc_in* d_kps, uint64_t n, uint8_t* d_out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!d_img || w < 3 || h < 3 || stride < w || (n && (!d_kps || !d_out)))
+        return fail(ctx, SB200_E_INVALID, "bad arguments to compute_descriptors");
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return SB200_OK;
+    cudaStream_t st = ctx->slot[0].stream;
+    StageScope sc(ctx, st, SB200_STAGE_DESCRIPTOR);
+    const int grid = (int)std::min<uint64_t>((n + DESC_WARPS - 1) / DESC_WARPS, (uint64_t)ctx->sm_count * 16);
+    k_descriptor_list<<<grid, 32 * DESC_WARPS, 0, st>>>(d_img, (int)w, (int)h, (int)stride,
+                                                        reinterpret_cast<const DescIn*>(d_kps), n, d_out);
+    count_launch(ctx, SB200_STAGE_DESCRIPTOR);
+    CU(cudaGetLastError());
+    return SB200_OK;
+}
+
+int sb200_compute_descriptors(sb200_ctx* ctx, const float* img, uint32_t w, uint32_t h, uint32_t stride,
+                              const sb200_desc_in* kps, uint64_t n, uint8_t* out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!img || w < 3 || h < 3 || stride < w || (n && (!kps || !out)))
+        return fail(ctx, SB200_E_INVALID, "bad arguments to compute_descriptors");
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return SB200_OK;
+    cudaStream_t st = ctx->slot[0].stream;
+    const size_t px = (size_t)w * h;
+    if (px > ctx->dimg_cap) {
+        cudaFree(ctx->d_dimg);
+        ctx->d_dimg = nullptr;
+        ctx->dimg_cap = 0;
+        CU(dalloc(&ctx->d_dimg, px));
+        ctx->dimg_cap = px;
+    }
+    if (n > ctx->dkps_cap) {
+        cudaFree(ctx->d_dkps); cudaFree(ctx->d_ddesc);
+        ctx->d_dkps = nullptr; ctx->d_ddesc = nullptr;
+        ctx->dkps_cap = 0;
+        CU(dalloc(&ctx->d_dkps, n));
+        CU(dalloc(&ctx->d_ddesc, n * DESC_SIZE));
+        ctx->dkps_cap = n;
+    }
+    CU(cudaMemcpy2DAsync(ctx->d_dimg, (size_t)w * 4, img, (size_t)stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_dkps, kps, n * sizeof(sb200_desc_in), cudaMemcpyHostToDevice, st));
+    int rc = sb200_compute_descriptors_device(ctx, ctx->d_dimg, w, h, w, reinterpret_cast<const sb200_desc_in*>(ctx->d_dkps),
+                                              n, ctx->d_ddesc);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, ctx->d_ddesc, n * DESC_SIZE, cudaMemcpyDeviceToHost, st));
+    return finish_all(ctx);
+}
+
+int sb200_extract_batch_multi(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* gray, uint32_t n, uint32_t w,
+                              uint32_t h, uint32_t stride, uint64_t image_stride, int64_t features_limit,
+                              sb200_result* out) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return SB200_E_INVALID;
+    sb200_ctx* ctx = ctxs[0];
+    if (!gray || !out || n == 0) return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch_multi");
+    if (n_ctx == 1) return sb200_extract_batch(ctx, gray, n, w, h, stride, image_stride, features_limit, out);
+    // contiguous shards of ceil(n / n_ctx) images, one host thread per context
+    const uint32_t per = (n + n_ctx - 1) / n_ctx;
+    std::vector<int> rcs(n_ctx, SB200_OK);
+    std::vector<sb200_result> parts(n_ctx);
+    std::vector<std::thread> th;
+    for (uint32_t d = 0; d < n_ctx; d++) {
+        const uint64_t first = (uint64_t)d * per;
+        if (first >= n) { parts[d] = sb200_result{0, 0, nullptr, nullptr, nullptr}; continue; }
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(per, n - first);
+        th.emplace_back([=, &rcs, &parts]() {
+            rcs[d] = sb200_extract_batch(ctxs[d], gray + first * image_stride, cnt, w, h, stride, image_stride,
+                                         features_limit, &parts[d]);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (uint32_t d = 0; d < n_ctx; d++)
+        if (rcs[d]) return fail(ctx, rcs[d], "device %u: %s", d, sb200_last_error(ctxs[d]));
+    // host-side gather in image order into ctxs[0]'s result arrays
+    uint64_t total = 0;
+    for (auto& p : parts) total += p.n;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_result_capacity(ctx, total, n);
+    if (rc) return rc;
+    // ctxs[0]'s own part already sits at the front of its arrays (ensure_result_capacity preserves it)
+    uint64_t pos = parts[0].n, img = parts[0].n_images;
+    for (uint32_t d = 1; d < n_ctx; d++) {
+        const sb200_result& p = parts[d];
+        if (p.n_images == 0) continue;
+        memcpy(ctx->h_kps + pos, p.keypoints, p.n * sizeof(sb200_keypoint));
+        memcpy(ctx->h_desc + pos * SB200_DESC_SIZE, p.descriptors, p.n * SB200_DESC_SIZE);
+        for (uint32_t i = 0; i < p.n_images; i++) ctx->h_offsets[img + i] = pos + p.offsets[i];
+        pos += p.n;
+        img += p.n_images;
+    }
+    ctx->h_offsets[img] = pos;
+    ctx->res_n = pos;
+    fill_result(ctx, n, out);
+    return SB200_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------
+int sb200_set_profiling(sb200_ctx* ctx, int on) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = finish_all(ctx);
+    ctx->profiling = on != 0;
+    return rc;
+}
+
+int sb200_stage_stats(sb200_ctx* ctx, double* ms, uint64_t* launches, uint32_t cap) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = finish_all(ctx);
+    if (rc) return rc;
+    drain_stage_events(ctx);
+    for (uint32_t i = 0; i < cap && i < SB200_STAGE_COUNT; i++) {
+        if (ms) ms[i] = ctx->stage_ms[i];
+        if (launches) launches[i] = ctx->stage_launches[i];
+    }
+    return SB200_OK;
+}
+
+int sb200_reset_stats(sb200_ctx* ctx) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = finish_all(ctx);
+    drain_stage_events(ctx);
+    for (int i = 0; i < SB200_STAGE_COUNT; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
+    return rc;
+}
+
+uint64_t sb200_launch_count(const sb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t sb200_algorithmic_bytes(uint32_t w, uint32_t h, uint64_t* out, uint32_t cap) {
+    // A(W,H) = W*H + 4*S  +  P*5*8 + P1*8  +  P_act*24
+    PyrLayout L = make_layout(w, h);
+    uint64_t S = (uint64_t)L.o[0].w * L.o[0].h, P = 0, Pact = 0;
+    for (int o = 0; o < L.n_oct; o++) {
+        const uint64_t px = (uint64_t)std::max(L.o[o].w, 0) * std::max(L.o[o].h, 0);
+        P += px;
+        if (L.o[o].scanned) Pact += px;
+    }
+    const uint64_t seed = (uint64_t)w * h + 4 * S;
+    const uint64_t blur = P * 5 * 8 + (P - S) * 8;
+    const uint64_t ext = Pact * 24;
+    if (out && cap > 0) out[0] = seed;
+    if (out && cap > 1) out[1] = blur;
+    if (out && cap > 2) out[2] = ext;
+    return seed + blur + ext;
+}
+
+int sb200_timer_start(sb200_ctx* ctx) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    // the timer lives on slot 0's stream; slot 1 is ordered behind it through a dependency event
+    CU(cudaEventRecord(ctx->t0, ctx->slot[0].stream));
+    CU(cudaStreamWaitEvent(ctx->slot[1].stream, ctx->t0, 0));
+    return SB200_OK;
+}
+
+int sb200_timer_stop(sb200_ctx* ctx) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaEvent_t j = get_event(ctx);
+    CU(cudaEventRecord(j, ctx->slot[1].stream));
+    CU(cudaStreamWaitEvent(ctx->slot[0].stream, j, 0));
+    ctx->ev_pool.push_back(j);
+    CU(cudaEventRecord(ctx->t1, ctx->slot[0].stream));
+    return SB200_OK;
+}
+
+int sb200_timer_elapsed_ms(sb200_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->t1));
+    CU(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return SB200_OK;
+}
+
+int sb200_host_alloc(size_t bytes, void** out) {
+    if (!out) return SB200_E_INVALID;
+    return cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? SB200_OK : SB200_E_CUDA;
+}
+int sb200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? SB200_OK : SB200_E_CUDA; }
+
+int sb200_device_alloc(sb200_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(out, std::max<size_t>(bytes, 1)));
+    return SB200_OK;
+}
+int sb200_device_free(sb200_ctx* ctx, void* p) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(p));
+    return SB200_OK;
+}
+int sb200_memcpy_h2d(sb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->slot[0].stream));
+    CU(cudaStreamSynchronize(ctx->slot[0].stream));
+    return SB200_OK;
+}
+int sb200_memcpy_d2h(sb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->slot[0].stream));
+    CU(cudaStreamSynchronize(ctx->slot[0].stream));
+    return SB200_OK;
+}
+
+int sb200_flush_l2(sb200_ctx* ctx) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_flush) {
+        ctx->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+        CU(cudaMalloc(&ctx->d_flush, ctx->flush_bytes));
+    }
+    CU(cudaMemsetAsync(ctx->d_flush, 0x5a, ctx->flush_bytes, ctx->slot[0].stream));
+    return SB200_OK;
+}
+
+}  // extern "C"
