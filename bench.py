@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the SIFT extraction hot path on B200 (BASELINE.json metric:
+"1080p images/sec at 1/2/4/8 B200; descriptors/sec; % of HBM roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k|vga|desc] [--impl b200|reference]
+
+One "step" = one pass of the whole hot path (seed, pyramid, DoG/extrema, refinement, orientation,
+descriptors) over one batch of synthetic gray images per GPU.  Prints ONE JSON line on rank 0.
+
+  value     images/s over all GPUs with the inputs already resident in HBM (results stay on the device),
+            timed with CUDA events on the launching streams, max over ranks.
+  e2e       the same metric through the public host API (sb200_extract_batch): pinned host inputs,
+            host->device and device->host copies inside the timed region.
+  roofline  algorithmic bytes of the blur stage / its measured duration vs the
+            measured HBM copy peak (MEASURED_PEAKS.json).
+  cpu_baseline  the in-repo oracle (a C port of the crate; the crate itself is Rust and cannot be built in
+            this image) timed on a bounded sample on the host, N=1 only.
+
+--impl reference times that same CPU port on all host cores (the reference's own CPU path stand-in).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, images per group (= context max_batch), groups per step)
+    "1080p": (1920, 1080, 8, 2),   # BASELINE.json configs[1] shape, batched
+    "4k": (3840, 2160, 2, 2),      # configs[2]
+    "vga": (640, 480, 64, 2),      # configs[3] shape (8192 images = 64 such steps)
+}
+
+
+def synth_images(n, w, h, seed):
+    """i.i.d. uniform u8 noise, a distinct stream per image."""
+    out = np.empty((n, h, w), np.uint8)
+    for i in range(n):
+        out[i] = np.random.default_rng([seed, i]).integers(0, 256, (h, w), dtype=np.uint8)
+    return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.t = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class Dist:
+    """torch.distributed plumbing for the N>1 contract (barrier + max over ranks); no data-path collective."""
+
+    def __init__(self, rank, local_rank, world, cuda=True):
+        self.rank, self.world, self.torch = rank, world, None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29511")
+            self.cuda = cuda and torch.cuda.is_available()
+            if self.cuda:
+                torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl" if self.cuda else "gloo", rank=rank, world_size=world)
+            self.torch, self.dist = torch, dist
+
+    def barrier(self):
+        if self.world > 1:
+            if self.cuda:
+                self.torch.cuda.synchronize()
+            self.dist.barrier()
+
+    def reduce(self, value, op="max"):
+        if self.world == 1:
+            return float(value)
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device="cuda" if self.cuda else "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def oracle_images_per_s(imgs, threads):
+    """Times the CPU port (oracle) on `imgs` with `threads` host threads; returns (images/s, keypoints)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.lib()
+    t0 = time.perf_counter()
+    if threads <= 1:
+        counts = [len(O.sift(im)[0]) for im in imgs]
+    else:
+        with ThreadPoolExecutor(threads) as ex:   # ctypes releases the GIL: real parallelism
+            counts = list(ex.map(lambda im: len(O.sift(im)[0]), imgs))
+    dt = time.perf_counter() - t0
+    return len(imgs) / dt, int(sum(counts))
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The crate is Rust
+    and cannot be compiled here (no rustc/cargo), so this is the oracle port (kind "port")."""
+    if rank != 0:
+        return
+    w, h, B, G = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    per_step = max(1, min(cores, 16 if args.workload != "4k" else 4))
+    imgs = synth_images(per_step, w, h, 1234)
+    for _ in range(min(args.warmup, 1)):
+        oracle_images_per_s(imgs[: max(1, per_step // 4)], cores)
+    t0 = time.perf_counter()
+    kps = 0
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        _, k = oracle_images_per_s(imgs, cores)
+        kps += k
+    dt = time.perf_counter() - t0
+    val = steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": f"{args.workload} images/sec", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} {w}x{h} gray u8 uniform noise, full SIFT extraction",
+                   "images_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} x {per_step} images on {cores} threads (oracle C port of src/lib.rs; "
+                                   "the Rust crate cannot be built in this image)"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "keypoints_per_s": kps / dt,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import sift_features_b200 as sf
+    from sift_features_b200 import _ffi
+    lib = _ffi.load()
+    dist = Dist(rank, local_rank, world)
+    w, h, B, G = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    per_step = B * G
+    ex = sf.Extractor(w, h, B, device=local_rank)
+    H = ex.handle
+
+    def chk(st):
+        if st:
+            raise RuntimeError(lib.sb200_last_error(H).decode())
+
+    # distinct input sets, rotated so that consecutive steps never reuse L2-resident inputs
+    set_bytes = per_step * w * h
+    n_sets = int(min(max(2, (160 << 20) // set_bytes + 2), 24))
+    sets_h, sets_d = [], []
+    for s in range(n_sets):
+        p = C.c_void_p()
+        chk(lib.sb200_host_alloc(set_bytes, C.byref(p)))
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(per_step, h, w))
+        arr[...] = synth_images(per_step, w, h, 1234 + 1000 * rank + s)
+        d = C.c_void_p()
+        chk(lib.sb200_device_alloc(H, set_bytes, C.byref(d)))
+        chk(lib.sb200_memcpy_h2d(H, d, p, set_bytes))
+        sets_h.append((p, arr)); sets_d.append(d)
+
+    def device_step(i):
+        d = sets_d[i % n_sets].value
+        for g in range(G):
+            chk(lib.sb200_extract_batch_device(H, d + g * B * w * h, B, w, h, w, w * h, -1))
+
+    res = _ffi.Result()
+
+    def host_step(i):
+        p, _ = sets_h[i % n_sets]
+        chk(lib.sb200_extract_batch(H, p, per_step, w, h, w, w * h, -1, C.byref(res)))
+        return int(res.n)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # ---- warm-up -------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        device_step(i)
+    chk(lib.sb200_sync(H))
+    counts = (C.c_uint32 * B)()
+    chk(lib.sb200_device_result(H, counts, B, None, None, None))
+    kp_per_group = int(sum(counts))
+    # ---- timed region: device-resident inputs, CUDA events on the launching streams --------------
+    chk(lib.sb200_set_profiling(H, 1 if args.profile_stages else 0))
+    chk(lib.sb200_reset_stats(H))
+    dist.barrier()
+    l0 = ex.launch_count
+    t_wall0 = time.perf_counter()
+    chk(lib.sb200_timer_start(H))
+    for i in range(args.steps):
+        device_step(args.warmup + i)
+    chk(lib.sb200_timer_stop(H))
+    ms = C.c_float()
+    chk(lib.sb200_timer_elapsed_ms(H, C.byref(ms)))
+    chk(lib.sb200_sync(H))
+    t_wall1 = time.perf_counter()
+    dist.barrier()
+    launches = ex.launch_count - l0
+    dev_ms = dist.reduce(ms.value, "max")
+    stats = ex.stage_stats()
+    chk(lib.sb200_set_profiling(H, 0))
+    # ---- e2e: host buffers through the public API, wall clock around synchronous calls --------------
+    for i in range(min(args.warmup, 2)):
+        host_step(i)
+    dist.barrier()
+    t0 = time.perf_counter()
+    kp_total = 0
+    for i in range(args.steps):
+        kp_total += host_step(args.warmup + i)
+    t_e2e = time.perf_counter() - t0
+    t_e2e = dist.reduce(t_e2e, "max")
+    kp_all = dist.reduce(kp_total, "sum")
+    d2h = kp_total / max(1, args.steps) * (20 + 128) + (per_step + 1) * 8
+    # clocks: the timed regions are short; keep the GPU under the same load until the sampler has >= 5 samples
+    clocks = None
+    if sampler:
+        t_load0 = t_wall0
+        extra_t0 = time.perf_counter()
+        i = 0
+        while time.perf_counter() - extra_t0 < 1.0:
+            device_step(i); i += 1
+            if i % 8 == 0:
+                chk(lib.sb200_sync(H))
+        chk(lib.sb200_sync(H))
+        t_load1 = time.perf_counter()
+        sampler.stop()
+        clocks = sampler.summary(t_load0, t_load1)
+        clocks["window"] = "timed region + e2e region + 1 s repeat of the timed loop"
+    if world > 1:
+        dist.barrier()
+
+    total_images = args.steps * per_step * world
+    value = total_images / (dev_ms * 1e-3)
+    e2e = total_images / t_e2e
+    line = {
+        "metric": f"{args.workload} images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {w}x{h} gray u8 i.i.d. uniform noise, full SIFT extraction "
+                        f"(pyramid + DoG/extrema + refinement + orientation + descriptors), {per_step} images per "
+                        f"step per GPU in {G} groups of {B}",
+            "images_per_step_per_gpu": per_step, "parallelism": f"independent image shards x{world}, no collective",
+            "l2": f"per-step working set ({per_step} pyramids) and {n_sets} rotating input sets exceed the 126 MB L2",
+        },
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": set_bytes, "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "keypoints_per_s": kp_per_group * G * args.steps * world / (dev_ms * 1e-3),
+        "keypoints_per_image": kp_per_group / B,
+        "e2e_keypoints_per_s": kp_all / t_e2e,
+        "clocks": clocks,
+    }
+    if rank == 0:
+        peak, peak_src = peaks()
+        tot, a_seed, a_blur, a_ext = sf.algorithmic_bytes(w, h)
+        imgs_rank = args.steps * per_step
+        if args.profile_stages:
+            blur_ms = stats["blur"]["ms"]
+            ach = a_blur * imgs_rank / (blur_ms * 1e-3) / 1e9 if blur_ms > 0 else None
+            pyr_ms = stats["seed"]["ms"] + stats["blur"]["ms"] + stats["extrema"]["ms"]
+            line["roofline"] = {
+                "bound": "hbm", "kernel": "k_blur (five separable Gaussian blurs per octave + fused decimation)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_image": a_blur,
+                "avg_launch_us": 1e3 * blur_ms / max(1, stats["blur"]["launches"]),
+                "pyramid_dog": {"algorithmic_bytes_per_image": tot, "ms_per_image": pyr_ms / imgs_rank,
+                                "achieved": tot * imgs_rank / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else None,
+                                "frac": tot * imgs_rank / (pyr_ms * 1e-3) / 1e9 / peak if pyr_ms > 0 else None},
+            }
+            line["stages_ms_per_image"] = {k: v["ms"] / imgs_rank for k, v in stats.items()}
+            line["whole_path_frac_of_hbm_roofline"] = tot * value / world / 1e9 / peak
+        if world == 1 and not args.no_cpu:
+            n_cpu = {"1080p": 3, "4k": 1, "vga": 24}[args.workload]
+            v, _ = oracle_images_per_s(list(sets_h[0][1][:n_cpu]), 1)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": 1, "kind": "port",
+                                    "sample": f"{n_cpu} of the step's images, single thread (the crate is "
+                                              "single-threaded); oracle C port of src/lib.rs"}
+        print(json.dumps(line), flush=True)
+    ex.close()
+    dist.close()
+
+
+def run_desc(args, rank, local_rank, world):
+    """BASELINE.json configs[4]: descriptor-only, 200k precomputed keypoints, benches/descriptor.rs shape."""
+    import sift_features_b200 as sf
+    from sift_features_b200 import _ffi
+    lib = _ffi.load()
+    dist = Dist(rank, local_rank, world)
+    w, h, n = 1920, 1080, 200_000
+    ex = sf.Extractor(w, h, 1, device=local_rank)
+    H = ex.handle
+
+    def chk(st):
+        if st:
+            raise RuntimeError(lib.sb200_last_error(H).decode())
+    img = synth_images(1, w, h, 1234 + rank)[0].astype(np.float32) / np.float32(255)
+    rng = np.random.default_rng(99 + rank)
+    k = np.empty((n, 4), np.float32)
+    k[:, 0] = rng.uniform(0, w, n); k[:, 1] = rng.uniform(0, h, n); k[:, 2] = 2.1; k[:, 3] = 123.0
+    d_img, d_k, d_out = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    chk(lib.sb200_device_alloc(H, img.nbytes, C.byref(d_img)))
+    chk(lib.sb200_device_alloc(H, k.nbytes, C.byref(d_k)))
+    chk(lib.sb200_device_alloc(H, n * 128, C.byref(d_out)))
+    chk(lib.sb200_memcpy_h2d(H, d_img, img.ctypes.data, img.nbytes))
+    chk(lib.sb200_memcpy_h2d(H, d_k, k.ctypes.data, k.nbytes))
+    for _ in range(args.warmup):
+        chk(lib.sb200_compute_descriptors_device(H, d_img, w, h, w, d_k, n, d_out))
+    chk(lib.sb200_sync(H))
+    dist.barrier()
+    l0 = ex.launch_count
+    chk(lib.sb200_timer_start(H))
+    for _ in range(args.steps):
+        chk(lib.sb200_compute_descriptors_device(H, d_img, w, h, w, d_k, n, d_out))
+    chk(lib.sb200_timer_stop(H))
+    ms = C.c_float()
+    chk(lib.sb200_timer_elapsed_ms(H, C.byref(ms)))
+    dev_ms = dist.reduce(ms.value, "max")
+    launches = ex.launch_count - l0
+    out = np.zeros((n, 128), np.uint8)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chk(lib.sb200_compute_descriptors(H, img.ctypes.data, w, h, w, k.ctypes.data, n, out.ctypes.data))
+    t_e2e = dist.reduce(time.perf_counter() - t0, "max")
+    if rank == 0:
+        peak, peak_src = peaks()
+        bytes_kp = 45 * 45 * 4 + 128 + 16
+        val = args.steps * n * world / (dev_ms * 1e-3)
+        line = {"metric": "descriptors/sec", "value": val, "unit": "keypoints/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "descriptor-only: 200k keypoints (scale 2.1, 123 deg, benches/descriptor.rs "
+                                       "shape) on one 1920x1080 f32 noise image"},
+                "e2e": {"value": args.steps * n * world / t_e2e, "unit": "keypoints/s",
+                        "h2d_bytes_per_step": int(img.nbytes + k.nbytes), "d2h_bytes_per_step": n * 128},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "k_descriptor_list", "achieved": bytes_kp * val / world / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": bytes_kp * val / world / 1e9 / peak,
+                             "traffic": None, "peak_source": peak_src,
+                             "note": "SFU / shared-atomic bound on L2-resident patches; HBM fraction is low by nature"}}
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as O
+            m = 2000
+            t0 = time.perf_counter()
+            for r in k[:m]:
+                O.compute_descriptor(img, *map(float, r))
+            line["cpu_baseline"] = {"value": m / (time.perf_counter() - t0), "unit": "keypoints/s", "cores": 1,
+                                    "kind": "port", "sample": f"first {m} of the 200k keypoints, single thread"}
+        print(json.dumps(line), flush=True)
+    ex.close()
+    dist.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS) + ["desc"])
+    ap.add_argument("--batch", type=int, default=0, help="images per group (context max_batch)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-profile-stages", dest="profile_stages", action="store_false",
+                    help="do not bracket stages with CUDA events during the timed region")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        if args.workload == "desc":
+            args.workload = "1080p"
+        return run_reference(args, rank, world)
+    if args.workload == "desc":
+        return run_desc(args, rank, local_rank, world)
+    return run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,32 @@ class Extractor:
             raise SiftError(st, f"sb200_create(device={device}, {max_width}x{max_height}, batch={max_batch}) failed: "
                             + self._lib.sb200_status_string(st).decode())
         self.device, self.max_width, self.max_height, self.max_batch = device, max_width, max_height, max_batch
+        self.max_keypoints_per_image = max_keypoints_per_image or max(16384, max_width * max_height // 8)
+        self.auto_grow = max_keypoints_per_image == 0   # an explicit capacity is a hard limit
+
+    def _grow(self) -> bool:
+        """Rebuilds the context with 4x the per-image candidate/keypoint capacity (bounded by the number of
+        (pixel, scale) positions the detector scans).  The crate has no such limit; this keeps the drop-in
+        from failing on images that are far denser than the default sizing assumes."""
+        worst = 16 * self.max_width * self.max_height
+        if not self.auto_grow or self.max_keypoints_per_image >= worst:
+            return False
+        cap = min(self.max_keypoints_per_image * 4, worst)
+        self._lib.sb200_destroy(self._h)
+        self._h = C.c_void_p()
+        st = self._lib.sb200_create(self.device, self.max_width, self.max_height, self.max_batch, cap, C.byref(self._h))
+        if st != _ffi.OK:
+            raise SiftError(st, "re-creating the context with a larger capacity failed")
+        self.max_keypoints_per_image = cap
+        return True
+
+    def _retry_capacity(self, call):
+        while True:
+            st = call()
+            if st == _ffi.E_CAPACITY and self._grow():
+                continue
+            self._check(st)
+            return
 
     # -- plumbing ---------------------------------------------------------
     @property
@@ -163,8 +189,9 @@ class Extractor:
         """sift / sift_with_processing::<OpenCVProcessing> (src/lib.rs:71-81)."""
         a = _as_gray(img)
         res = _ffi.Result()
-        self._check(self._lib.sb200_extract(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0],
-                                            -1 if features_limit is None else int(features_limit), C.byref(res)))
+        self._retry_capacity(lambda: self._lib.sb200_extract(
+            self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0],
+            -1 if features_limit is None else int(features_limit), C.byref(res)))
         _, kp, de = self._take(res)
         return SiftResult(kp, de)
 
@@ -176,10 +203,9 @@ class Extractor:
         if a.strides[2] != 1 or a.strides[1] < a.shape[2]:
             a = np.ascontiguousarray(a)
         res = _ffi.Result()
-        self._check(self._lib.sb200_extract_batch(self._h, a.ctypes.data, a.shape[0], a.shape[2], a.shape[1],
-                                                  a.strides[1], a.strides[0],
-                                                  -1 if features_limit is None else int(features_limit),
-                                                  C.byref(res)))
+        self._retry_capacity(lambda: self._lib.sb200_extract_batch(
+            self._h, a.ctypes.data, a.shape[0], a.shape[2], a.shape[1], a.strides[1], a.strides[0],
+            -1 if features_limit is None else int(features_limit), C.byref(res)))
         return self._take(res)
 
     def precompute_images(self, img) -> "PrecomputedImages":

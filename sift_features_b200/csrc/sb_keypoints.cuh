@@ -418,10 +418,24 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 
 // ---------------------------------------------------------------------------
 // compute_descriptor (src/lib.rs:785-990) + output pack (src/lib.rs:164-174).
-// One warp per keypoint; the (6,6,8) histogram lives in shared memory.
+// One warp per keypoint.
+//   * Only the inner 4x4 cells of the reference's (6,6,8) histogram survive the crop at :951, so
+//     only those 128 bins are accumulated.
+//   * No atomics: the warp keeps DESC_COPIES lane-private copies of the 128 bins in shared memory,
+//     copy k at word bin*DESC_COPIES + k, so a half-warp's read-modify-writes always hit 16 distinct
+//     banks; lanes l and l+16 share a copy and update it in two phases.  The copies are summed
+//     at the end (f32 sums in a different order than the reference's raster order: the +-1 byte
+//     tolerance of the north star covers it; everything up to the accumulation is the reference's
+//     arithmetic).
+//   * Window samples that fall outside the rotated 4x4 grid (about half) are filtered by a cheap
+//     pass and the survivors queued, so the expensive gradient / exp / atan2 / trilinear part
+//     always runs with 32 active lanes.
 // ---------------------------------------------------------------------------
 constexpr int DESC_WARPS = 8;
-constexpr int DESC_HIST = 6 * 6 * 8;
+constexpr int DESC_COPIES = 16;
+constexpr int DESC_QCAP = 64;
+constexpr int DESC_SMEM_WORDS = DESC_SIZE * DESC_COPIES + DESC_QCAP;  // per warp
+constexpr size_t DESC_SMEM_BYTES = 256 + (size_t)DESC_WARPS * DESC_SMEM_WORDS * sizeof(float);
 
 struct DescTarget {
     const float* img;  // layer base
@@ -429,82 +443,142 @@ struct DescTarget {
     float x, y, scale, orientation;  // arguments of compute_descriptor
 };
 
-__device__ __forceinline__ void descriptor_warp(const DescTarget t, float* hist /* smem [288] */, int lane,
+struct DescGeom {
+    const float* img;
+    int w, h, pitch, x, y, radius;
+    float sin_s, cos_s, orientation;
+};
+
+// one queued sample per active lane: gradient, weight, angle, trilinear split, accumulation
+__device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint32_t packed, const bool active,
+                                                  float* hist, const int lane, const uint64_t* s_tab) {
+    float cv[8];
+    int cb[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { cv[k] = 0.f; cb[k] = -1; }
+    if (active) {
+        const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
+        const float col_rot = (float)xw * G.cos_s - (float)yw * G.sin_s;
+        const float row_rot = (float)xw * G.sin_s + (float)yw * G.cos_s;
+        const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
+        const float* c = G.img + (long long)(G.y + yw) * G.pitch + (G.x + xw);
+        const float dx = __ldg(c + 1) - __ldg(c - 1);
+        const float dy = __ldg(c - G.pitch) - __ldg(c + G.pitch);
+        const float wgt = col_rot * col_rot + row_rot * row_rot;
+        const float weight = sbm::expf_glibc(s_tab, wgt * -0.125f);  // -2 / 4^2, :859
+        // ((atan2_f64(dy,dx).to_degrees() + 360) % 360) as f32 - orientation, :871
+        float deg = atan2f(dy, dx) * 57.29577951308232f;
+        if (deg < 0.f) deg += 360.0f;
+        if (deg >= 360.0f) deg -= 360.0f;
+        const float orient = deg - G.orientation;
+        float mag = sqrtf(dx * dx + dy * dy);
+        const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
+        mag = mag * weight;
+        const float obin = orient * (8.0f / 360.0f);
+        const float row_floor = floorf(rb), col_floor = floorf(cbn), ori_floor = floorf(obin);
+        const float row_frac = rb - row_floor, col_frac = cbn - col_floor, ori_frac = obin - ori_floor;
+        const float c1 = mag * row_frac, c0 = mag - c1;
+        const float c11 = c1 * col_frac, c10 = c1 - c11;
+        const float c01 = c0 * col_frac, c00 = c0 - c01;
+        cv[7] = c11 * ori_frac; cv[6] = c11 - cv[7];   // c111, c110
+        cv[5] = c10 * ori_frac; cv[4] = c10 - cv[5];   // c101, c100
+        cv[3] = c01 * ori_frac; cv[2] = c01 - cv[3];   // c011, c010
+        cv[1] = c00 * ori_frac; cv[0] = c00 - cv[1];   // c001, c000
+        // reference cells are (row_floor+1 .. +2, col_floor+1 .. +2) of the 6x6 grid; inner cells are 1..4
+        const int r1 = (int)row_floor, q1 = (int)col_floor;  // inner-grid index of the first cell (-1..3)
+        float of = ori_floor;
+        if (of < 0.f) of += 8.f;
+        else if (of >= 8.f) of -= 8.f;
+        const int o0 = min(max((int)of, 0), 7);
+        const int o1 = (o0 + 1) & 7;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int rr = r1 + (k >> 2), qq = q1 + ((k >> 1) & 1);
+            const bool in = (rr >= 0) && (rr < 4) && (qq >= 0) && (qq < 4);
+            cb[k] = in ? ((rr * 4 + qq) * 8 + ((k & 1) ? o1 : o0)) : -1;
+        }
+    }
+    float* mine = hist + (lane & (DESC_COPIES - 1));
+#pragma unroll
+    for (int phase = 0; phase < 32 / DESC_COPIES; phase++) {
+        if ((lane / DESC_COPIES) == phase) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (cb[k] >= 0) mine[cb[k] * DESC_COPIES] += cv[k];
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /* smem [DESC_SMEM_WORDS] */, int lane,
                                                 const uint64_t* s_tab, uint8_t* out /* 128 B */) {
-    for (int k = lane; k < DESC_HIST; k += 32) hist[k] = 0.f;
+    float* hist = wsm;
+    uint32_t* queue = reinterpret_cast<uint32_t*>(wsm + DESC_SIZE * DESC_COPIES);
+    {
+        float4* h4 = reinterpret_cast<float4*>(hist);
+        for (int k = lane; k < DESC_SIZE * DESC_COPIES / 4; k += 32) h4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    DescGeom G;
+    G.img = t.img; G.w = t.w; G.h = t.h; G.pitch = t.pitch; G.orientation = t.orientation;
     // `x.round() as usize` (src/lib.rs:796-797): saturating, negative -> 0
     const float xr = roundf(t.x), yr = roundf(t.y);
-    const int x = xr > 0.f ? (int)fminf(xr, 1e9f) : 0;
-    const int y = yr > 0.f ? (int)fminf(yr, 1e9f) : 0;
-    const float BIN_ANGLE_STEP = 8.0f / 360.0f;
+    G.x = xr > 0.f ? (int)fminf(xr, 1e9f) : 0;
+    G.y = yr > 0.f ? (int)fminf(yr, 1e9f) : 0;
     const float hist_width = 3.0f * t.scale;
-    const int radius = (int)roundf(3.0f * t.scale * sqrtf(2.0f) * 5.0f * 0.5f);  // :800
-    const float rad = t.orientation * (3.14159265358979323846f / 180.0f);          // f32::to_radians
+    G.radius = min((int)roundf(3.0f * t.scale * sqrtf(2.0f) * 5.0f * 0.5f), 127);  // :800 (<= 38 on this path)
+    const float rad = t.orientation * (3.14159265358979323846f / 180.0f);            // f32::to_radians
     double sd, cd;
     sincos((double)rad, &sd, &cd);  // libm sinf/cosf are (nearly always) correctly rounded: round once from f64
-    const float sin_s = (float)sd / hist_width, cos_s = (float)cd / hist_width;
-    const int side = 2 * radius + 1, total = side * side;
-    const int w = t.w, h = t.h, pitch = t.pitch;
+    G.sin_s = (float)sd / hist_width;
+    G.cos_s = (float)cd / hist_width;
+    const int side = 2 * G.radius + 1;
     __syncwarp();
-    for (int base = 0; base < total; base += 32) {
-        const int idx = base + lane;
-        if (idx < total) {
-            const int yq = idx / side;
-            const int yw = yq - radius, xw = idx - yq * side - radius;
-            const float col_rot = (float)xw * cos_s - (float)yw * sin_s;
-            const float row_rot = (float)xw * sin_s + (float)yw * cos_s;
+    uint32_t qhead = 0, qtail = 0;  // warp-uniform
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int yq = 0; yq < side; yq++) {
+        const int yw = yq - G.radius;
+        const int ay = G.y + yw;
+        if (ay <= 0 || ay >= G.h - 1) continue;  // warp-uniform
+        const float ys = (float)yw * G.sin_s, yc = (float)yw * G.cos_s;
+        for (int xb = 0; xb < side; xb += 32) {
+            const int xq = xb + lane;
+            const int xw = xq - G.radius;
+            const float col_rot = (float)xw * G.cos_s - ys;
+            const float row_rot = (float)xw * G.sin_s + yc;
             const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
-            const int ay = y + yw, ax = x + xw;
-            if (row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f && ay > 0 && ay < h - 1 &&
-                ax > 0 && ax < w - 1) {
-                const float* c = t.img + (long long)ay * pitch + ax;
-                const float dx = __ldg(c + 1) - __ldg(c - 1);
-                const float dy = __ldg(c - pitch) - __ldg(c + pitch);
-                const float wgt = col_rot * col_rot + row_rot * row_rot;
-                const float weight = sbm::expf_glibc(s_tab, wgt * -0.125f);  // -2 / 4^2, :859
-                // ((atan2_f64(dy,dx).to_degrees() + 360) % 360) as f32 - orientation, :871
-                float deg = atan2f(dy, dx) * 57.29577951308232f;
-                if (deg < 0.f) deg += 360.0f;
-                if (deg >= 360.0f) deg -= 360.0f;
-                const float orient = deg - t.orientation;
-                float mag = sqrtf(dx * dx + dy * dy);
-                const float rb = row_bin - 0.5f, cb = col_bin - 0.5f;
-                mag = mag * weight;
-                const float obin = orient * BIN_ANGLE_STEP;
-                const float row_floor = floorf(rb), col_floor = floorf(cb), ori_floor = floorf(obin);
-                const float row_frac = rb - row_floor, col_frac = cb - col_floor, ori_frac = obin - ori_floor;
-                const float c1 = mag * row_frac, c0 = mag - c1;
-                const float c11 = c1 * col_frac, c10 = c1 - c11;
-                const float c01 = c0 * col_frac, c00 = c0 - c01;
-                const float c111 = c11 * ori_frac, c110 = c11 - c111;
-                const float c101 = c10 * ori_frac, c100 = c10 - c101;
-                const float c011 = c01 * ori_frac, c010 = c01 - c011;
-                const float c001 = c00 * ori_frac, c000 = c00 - c001;
-                const int r1 = (int)(row_floor + 1.f), q1 = (int)(col_floor + 1.f);
-                float of = ori_floor;
-                if (of < 0.f) of += 8.f;
-                else if (of >= 8.f) of -= 8.f;
-                int o0 = (int)of;
-                o0 = min(max(o0, 0), 7);
-                const int o1 = (o0 + 1 >= 8) ? 0 : o0 + 1;
-                float* h0 = hist + (r1 * 6 + q1) * 8;
-                atomicAdd(h0 + o0, c000);
-                atomicAdd(h0 + o1, c001);
-                atomicAdd(h0 + 8 + o0, c010);
-                atomicAdd(h0 + 8 + o1, c011);
-                atomicAdd(h0 + 48 + o0, c100);
-                atomicAdd(h0 + 48 + o1, c101);
-                atomicAdd(h0 + 56 + o0, c110);
-                atomicAdd(h0 + 56 + o1, c111);
+            const int ax = G.x + xw;
+            const bool valid = xq < side && row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f &&
+                               ax > 0 && ax < G.w - 1;
+            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            if (vm == 0) continue;
+            if (valid) queue[(qtail + __popc(vm & lt)) & (DESC_QCAP - 1)] = ((uint32_t)yq << 8) | (uint32_t)xq;
+            qtail += __popc(vm);
+            __syncwarp();
+            if (qtail - qhead >= 32) {
+                const uint32_t e = queue[(qhead + lane) & (DESC_QCAP - 1)];
+                qhead += 32;
+                descriptor_sample(G, e, true, hist, lane, s_tab);
             }
         }
     }
+    {
+        const uint32_t n = qtail - qhead;  // < 32
+        if (n) {
+            const uint32_t e = queue[(qhead + lane) & (DESC_QCAP - 1)];
+            descriptor_sample(G, e, lane < n, hist, lane, s_tab);
+        }
+    }
     __syncwarp();
-    // hist[1..5, 1..5, :] flattened (src/lib.rs:951): lane owns flat[4*lane .. 4*lane+3]
-    const int fr = lane >> 3, fc = (lane >> 1) & 3, fo = (lane & 1) * 4;
+    // sum the private copies: lane owns flat[4*lane .. 4*lane+3]; rotated start => conflict-free reads
     float f[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) f[k] = hist[((fr + 1) * 6 + fc + 1) * 8 + fo + k];
+    for (int k = 0; k < 4; k++) {
+        const float* hb = hist + (4 * lane + k) * DESC_COPIES;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < DESC_COPIES; c++) acc += hb[(c + lane) & (DESC_COPIES - 1)];
+        f[k] = acc;
+    }
     // l2 norm in chunks of four, chunks added in order (src/lib.rs:957-962)
     float s = 0.f;
 #pragma unroll
@@ -599,8 +673,9 @@ __global__ void __launch_bounds__(1024) k_out_offsets(const uint32_t* __restrict
 // compute_descriptors (src/lib.rs:759-782) over the keypoint list of each image and
 // the final KeyPoint records (src/lib.rs:164-174).
 __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams P) {
-    __shared__ uint64_t s_tab[32];
-    __shared__ float s_hist[DESC_WARPS][DESC_HIST];
+    extern __shared__ __align__(16) unsigned char desc_smem[];  // DESC_SMEM_BYTES, dynamic (> 48 KB)
+    uint64_t* s_tab = reinterpret_cast<uint64_t*>(desc_smem);
+    float (*s_hist)[DESC_SMEM_WORDS] = reinterpret_cast<float (*)[DESC_SMEM_WORDS]>(desc_smem + 256);
     if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -637,8 +712,9 @@ struct DescIn { float x, y, scale, orientation; };
 __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor_list(const float* __restrict__ img, int w, int h,
                                                                       int pitch, const DescIn* __restrict__ kps,
                                                                       unsigned long long n, uint8_t* __restrict__ out) {
-    __shared__ uint64_t s_tab[32];
-    __shared__ float s_hist[DESC_WARPS][DESC_HIST];
+    extern __shared__ __align__(16) unsigned char desc_smem[];  // DESC_SMEM_BYTES, dynamic (> 48 KB)
+    uint64_t* s_tab = reinterpret_cast<uint64_t*>(desc_smem);
+    float (*s_hist)[DESC_SMEM_WORDS] = reinterpret_cast<float (*)[DESC_SMEM_WORDS]>(desc_smem + 256);
     if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

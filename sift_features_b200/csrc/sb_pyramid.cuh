@@ -12,6 +12,8 @@
 //   * DoG (src/lib.rs:271-279): G[l+1] - G[l], recomputed on the fly (never stored).
 // The translation unit is compiled with --fmad=false: every FMA below is explicit.
 #pragma once
+#include <cuda.h>
+
 #include "sb_common.cuh"
 
 namespace sb {
@@ -55,7 +57,7 @@ struct BlurCfg {
     static constexpr int IN_H = 40, IN_W = 72;   // seed only: staged input tile (aliases `inter`)
     static constexpr size_t SMEM = (size_t)SH * (SPITCH + IPITCH) * sizeof(float);
     static_assert(120 + 4 * NV4 <= SPITCH, "row-pass window overruns the stage pitch");
-    static_assert(IN_H * IN_W <= SH * IPITCH, "input tile does not fit the aliased buffer");
+    static_assert(IN_H * (IN_W + SW) <= SH * IPITCH, "input tile + horizontal buffer do not fit the aliased buffer");
     static_assert(L != 0 || ((TH + 2 * R) / 2 + 2 <= IN_H && (TW + 2 * R) / 2 + 2 <= IN_W), "input tile too small");
 };
 
@@ -105,24 +107,37 @@ __global__ void __launch_bounds__(256, 2) k_blur(const BlurParams p) {
             in_tile[r * C::IN_W + c] = v / 255.0f;
         }
         __syncthreads();
-        for (int idx = tid; idx < C::SH * C::SW; idx += C::THREADS) {
-            int row = idx / C::SW, col = idx - row * C::SW;
-            float v = 0.0f;
-            if (row < rows_needed && col < cols_needed) {
-                int y = reflect101(ty0 - R + row, h);
-                int x = reflect101(tx0 - R + col, w);
-                int ay, by, ax, bx;
-                float fy, fx;
-                lerp2x(y, p.in_h, ay, by, fy);
+        // horizontal lerp of every staged input row (OpenCV resize: horizontal pass first):
+        // hbuf[r][col] = fma(I[r][bx] - I[r][ax], fx, I[r][ax]) for the SW staged columns
+        float* hbuf = in_tile + C::IN_H * C::IN_W;  // IN_H x SW, also inside `inter`
+        for (int col = tid & 127; col < C::SW; col += 128) {
+            if (col < cols_needed) {
+                const int x = reflect101(tx0 - R + col, w);
+                int ax, bx;
+                float fx;
                 lerp2x(x, p.in_w, ax, bx, fx);
-                const float* r0 = in_tile + (ay - iy0) * C::IN_W - ix0;
-                const float* r1 = in_tile + (by - iy0) * C::IN_W - ix0;
-                float p00 = r0[ax], p01 = r0[bx], p10 = r1[ax], p11 = r1[bx];
-                float h0 = fmaf(p01 - p00, fx, p00);
-                float h1 = fmaf(p11 - p10, fx, p10);
-                v = fmaf(h1 - h0, fy, h0);
+                for (int r = tid >> 7; r < ih; r += C::THREADS / 128) {
+                    const float a = in_tile[r * C::IN_W + ax - ix0], b = in_tile[r * C::IN_W + bx - ix0];
+                    hbuf[r * C::SW + col] = fmaf(b - a, fx, a);
+                }
             }
-            stage[row * C::SPITCH + col] = v;
+        }
+        __syncthreads();
+        // vertical lerp into the stage: U[y][x] = fma(H[by][x] - H[ay][x], fy, H[ay][x])
+        for (int col = tid & 127; col < C::SW; col += 128) {
+            const bool col_ok = col < cols_needed;
+            for (int row = tid >> 7; row < C::SH; row += C::THREADS / 128) {
+                float v = 0.0f;
+                if (col_ok && row < rows_needed) {
+                    const int y = reflect101(ty0 - R + row, h);
+                    int ay, by;
+                    float fy;
+                    lerp2x(y, p.in_h, ay, by, fy);
+                    const float a = hbuf[(ay - iy0) * C::SW + col], b = hbuf[(by - iy0) * C::SW + col];
+                    v = fmaf(b - a, fy, a);
+                }
+                stage[row * C::SPITCH + col] = v;
+            }
         }
     } else {
         const float* src = p.src + img * p.img_stride;
@@ -202,6 +217,215 @@ __global__ void __launch_bounds__(256, 2) k_blur(const BlurParams p) {
 }
 
 // ---------------------------------------------------------------------------
+// u8 -> f32 / 255 -> 2x bilinear upsample (first half of create_seed_image, src/lib.rs:196-205) as an
+// elementwise kernel for octave sizes that take the TMA blur; the seed blur then runs as k_blur_tma<0>.
+// A thread owns the 2 x 4 output block rows {2y+1, 2y+2}, columns {4k .. 4k+3}: both rows interpolate
+// between input rows y and y+1, the columns between input columns 2k-1 .. 2k+2 (clamped at the border,
+// where the lerp degenerates to fma(0, t, a) = a exactly as the clamped reference index does).
+// ---------------------------------------------------------------------------
+struct UpsampleParams {
+    const uint8_t* in;
+    long long in_img_stride;
+    int in_w, in_h, in_stride;
+    float* dst;              // 2W x 2H f32, image 0
+    long long img_stride;
+    int pitch;
+};
+
+__global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;      // output columns 4k .. 4k+3
+    const int y = (int)blockIdx.y - 1;                        // input row pair (y, y+1); y = -1 yields output row 0
+    const long long img = blockIdx.z;
+    const int W = p.in_w, H = p.in_h;
+    if (4 * k >= 2 * W) return;
+    const uint8_t* in = p.in + img * p.in_img_stride;
+    const int y0 = max(y, 0), y1 = min(y + 1, H - 1);
+    float a[2][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int x = min(max(2 * k - 1 + c, 0), W - 1);
+        a[0][c] = (float)in[(long long)y0 * p.in_stride + x] / 255.0f;
+        a[1][c] = (float)in[(long long)y1 * p.in_stride + x] / 255.0f;
+    }
+    // horizontal pass: out col 4k = lerp(c0, c1, .75), 4k+1 = lerp(c1, c2, .25), 4k+2 = lerp(c1, c2, .75), 4k+3 = lerp(c2, c3, .25)
+    float hrow[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        hrow[r][0] = fmaf(a[r][1] - a[r][0], 0.75f, a[r][0]);
+        hrow[r][1] = fmaf(a[r][2] - a[r][1], 0.25f, a[r][1]);
+        hrow[r][2] = fmaf(a[r][2] - a[r][1], 0.75f, a[r][1]);
+        hrow[r][3] = fmaf(a[r][3] - a[r][2], 0.25f, a[r][2]);
+    }
+    // the reference clamps the source index and zeroes the weight at the borders (column 0 and 2W-1)
+    if (k == 0) { hrow[0][0] = a[0][1]; hrow[1][0] = a[1][1]; }   // 2k-1 < 0: both taps are column 0
+    float* dst = p.dst + img * p.img_stride;
+    const bool full = (4 * k + 3) < 2 * W;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int Y = 2 * y + 1 + r;
+        if (Y < 0 || Y >= 2 * H) continue;
+        const float f = r ? 0.75f : 0.25f;
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) o[c] = fmaf(hrow[1][c] - hrow[0][c], f, hrow[0][c]);
+        float* q = dst + (long long)Y * p.pitch + 4 * k;
+        if (full) *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
+        else for (int c = 0; c < 4 && 4 * k + c < 2 * W; c++) q[c] = o[c];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA variant of the blur for octaves of at least TMA_MIN_DIM pixels per side: the
+// (TH+2R) x BW input box (halo included) is fetched by ONE cp.async.bulk.tensor
+// (UTMALDG) issued by an elected thread and completed on an mbarrier, instead of
+// ~54 dependent global loads per thread.  Out-of-image box elements arrive as
+// zeros; tiles on the image border then patch their halo with BORDER_REFLECT_101
+// copies taken from the box itself.  Same row/column arithmetic as k_blur.
+// The tensor map is 4-D: (x, y, layer, image) over one octave of the slot's arena.
+// ---------------------------------------------------------------------------
+constexpr int TMA_MIN_DIM = 32;
+
+template <int L>
+struct TmaCfg {
+    static constexpr int R = blur_radius(L);
+    static constexpr int RA = (R + 3) / 4 * 4;   // left halo of the box: the box's first column must be 16-byte aligned
+    static constexpr int XO = RA - R;            // box column of the first element the filter needs
+    static constexpr int TW = 128, TH = 64;
+    static constexpr int SH = TH + 2 * R;
+    static constexpr int SW = TW + 2 * R;
+    static constexpr int WIN = XO + 8 + 2 * R;   // box floats read for 8 consecutive row-pass outputs (aligned start)
+    static constexpr int NV4 = (WIN + 3) / 4;
+    // box width: multiple of 4 floats (16 B) with BW/4 odd, so that 8 consecutive rows start in 8
+    // distinct 4-bank groups (conflict-free LDS.128 with lanes <-> rows)
+    static constexpr int BW = (R <= 8) ? 148 : (R == 10) ? 156 : 164;
+    static constexpr int IPITCH = 132;
+    static constexpr int PY = 16;
+    static constexpr int THREADS = 256;
+    static constexpr uint32_t BOX_BYTES = (uint32_t)SH * BW * sizeof(float);
+    static constexpr size_t SMEM = (size_t)SH * (BW + IPITCH) * sizeof(float);
+    static_assert(BW >= XO + SW && (BW / 4) % 2 == 1 && 120 + 4 * NV4 <= BW, "box width");
+    static_assert(BOX_BYTES % 16 == 0 && BW <= 256 && SH <= 256, "TMA box limits");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int L, bool DECIMATE>
+__global__ void __launch_bounds__(256, 2) k_blur_tma(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
+                                                      const int src_layer) {
+    using C = TmaCfg<L>;
+    constexpr int R = C::R;
+    extern __shared__ __align__(1024) float smem_tma[];  // own symbol: `smem` above is declared 16-byte aligned
+    __shared__ __align__(8) uint64_t bar;
+    float* stage = smem_tma;                     // SH x BW, dense (TMA box layout)
+    float* inter = smem_tma + C::SH * C::BW;     // SH x IPITCH
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * C::TW, ty0 = blockIdx.y * C::TH;
+    const int img = blockIdx.z;
+    const int w = p.w, h = p.h;
+    const int rows_needed = min(C::TH, h - ty0) + 2 * R;
+    const int cols_needed = min(C::TW, w - tx0) + 2 * R;
+    const uint32_t bar_a = smem_u32(&bar);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(C::BOX_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(stage)), "l"(&tmap), "r"(tx0 - C::RA), "r"(ty0 - R), "r"(src_layer), "r"(img), "r"(bar_a)
+            : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
+        }
+    }
+    // BORDER_REFLECT_101 for tiles that stick out of the image (block-uniform branch).
+    // Box element (row, XO + col) holds image pixel (ty0 - R + row, tx0 - R + col).
+    if (tx0 - R < 0 || ty0 - R < 0 || tx0 + C::TW + R > w || ty0 + C::TH + R > h) {
+        for (int idx = tid; idx < C::SH * C::SW; idx += C::THREADS) {
+            const int row = idx / C::SW, col = idx - row * C::SW;
+            if (row < rows_needed && col < cols_needed) {
+                const int gy = ty0 - R + row, gx = tx0 - R + col;
+                if (gy < 0 || gy >= h || gx < 0 || gx >= w) {
+                    const int ry = reflect101(gy, h) - (ty0 - R), rx = reflect101(gx, w) - (tx0 - R);
+                    // the source pixel is inside the image, hence inside the box
+                    stage[row * C::BW + C::XO + col] = stage[ry * C::BW + C::XO + rx];
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- row pass: warp = 32 staged rows x one 8-pixel segment ----
+    {
+        constexpr int NGROUPS = (C::SH + 31) / 32;
+        constexpr int NSEG = C::TW / 8;
+        for (int task = warp; task < NGROUPS * NSEG; task += C::THREADS / 32) {
+            const int g = task / NSEG, seg = task - g * NSEG;
+            const int row = g * 32 + lane;
+            if (row < rows_needed && row < C::SH) {
+                float win[4 * C::NV4];
+                const float4* sp = reinterpret_cast<const float4*>(stage + row * C::BW + seg * 8);
+#pragma unroll
+                for (int v = 0; v < C::NV4; v++) {
+                    float4 q = sp[v];
+                    win[4 * v + 0] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
+                }
+                float out[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float acc = win[C::XO + j] * c_taps[L][0];
+#pragma unroll
+                    for (int i = 1; i <= 2 * R; i++) acc = fmaf(win[C::XO + j + i], c_taps[L][i], acc);
+                    out[j] = acc;
+                }
+                float4* ip = reinterpret_cast<float4*>(inter + row * C::IPITCH + seg * 8);
+                ip[0] = make_float4(out[0], out[1], out[2], out[3]);
+                ip[1] = make_float4(out[4], out[5], out[6], out[7]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- column pass: thread = one column x PY consecutive rows ----
+    {
+        float* dst = p.dst + (long long)img * p.img_stride;
+        float* dec = DECIMATE ? p.dec + (long long)img * p.img_stride : nullptr;
+        constexpr int NCH = C::TH / C::PY;
+        for (int task = tid; task < C::TW * NCH; task += C::THREADS) {
+            const int cy = task / C::TW, x = task - cy * C::TW;
+            const int y0 = cy * C::PY;
+            const int gx = tx0 + x;
+            if (ty0 + y0 >= h) continue;
+            float c[C::PY + 2 * R];
+#pragma unroll
+            for (int j = 0; j < C::PY + 2 * R; j++) c[j] = inter[(y0 + j) * C::IPITCH + x];
+#pragma unroll
+            for (int j = 0; j < C::PY; j++) {
+                float acc = c[j + R] * c_taps[L][R];
+#pragma unroll
+                for (int i = 1; i <= R; i++) acc = fmaf(c[j + R + i] + c[j + R - i], c_taps[L][R + i], acc);
+                const int gy = ty0 + y0 + j;
+                if (gy < h && gx < w) {
+                    dst[(long long)gy * p.pitch + gx] = acc;
+                    if (DECIMATE && !(gy & 1) && !(gx & 1)) {
+                        const int dy = gy >> 1, dx = gx >> 1;
+                        if (dy < p.dec_h && dx < p.dec_w) dec[(long long)dy * p.dec_pitch + dx] = acc;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // DoG + 3x3x3 extrema (build_dog + point_is_local_extremum, src/lib.rs:271-279,
 // 437-506) for the three scales of one octave in one pass over its six Gaussian
 // layers.  A warp owns 32 consecutive columns (one mask word) and walks down
@@ -212,6 +436,7 @@ __global__ void __launch_bounds__(256, 2) k_blur(const BlurParams p) {
 // ---------------------------------------------------------------------------
 constexpr int EX_ROWS = 16;
 constexpr int EX_WARPS = 4;
+constexpr int EX_COLS = 32;  // columns per warp == one mask word
 
 struct ExtremaParams {
     const float* gauss;       // octave base (layer 0), image 0
@@ -225,79 +450,125 @@ struct ExtremaParams {
     int rows_img_stride;
 };
 
+// sm_100 three-input min/max (FMNMX3)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// rolling three-row state of one warp: per DoG layer the horizontal 3-max / 3-min of rows
+// (c-1, c, c+1) and the centre-column DoG values, one column per lane
+struct ExState {
+    float hx[3][N_DOG], hn[3][N_DOG], v[3][N_DOG];
+};
+
+struct ExWarp {
+    const float* g;       // layer 0, row 0, this lane's (clamped) column
+    uint32_t* mask;
+    uint32_t* rows;
+    long long layer_stride;
+    int h, pitch, mask_pitch, strip, lane, y0;
+    bool x_ok;
+};
+
+// Row r of the six Gaussian layers at columns x-1, x, x+1 (the shifted loads hit the L1 lines the
+// centre load just brought in): no shuffles, no edge lanes, three immediate offsets per layer pointer.
+__device__ __forceinline__ void ex_load(const ExWarp& W, const int r, float (*gv)[3]) {
+    const int rc = min(max(r, 0), W.h - 1);
+    const float* row = W.g + (long long)rc * W.pitch;
+#pragma unroll
+    for (int l = 0; l < N_LAYERS; l++) {
+        const float* q = row + l * W.layer_stride;
+        gv[l][0] = __ldg(q - 1);
+        gv[l][1] = __ldg(q);
+        gv[l][2] = __ldg(q + 1);
+    }
+}
+
+// Processes image row r (already in gv) into slot K (K = (r - (y0-1)) mod 3, a compile-time constant
+// thanks to the 3x unrolled caller, so the state never moves between registers), issues the loads of
+// row r+1 as soon as gv is consumed, and once three rows are in evaluates the centre row r-1.
+template <int K, bool KEEP_FLAT>
+__device__ __forceinline__ void ex_step(const ExWarp& W, ExState& S, const int r, const int r_last, float (*gv)[3]) {
+    constexpr int A = (K + 1) % 3, B = (K + 2) % 3;  // rows r-2 and r-1
+#pragma unroll
+    for (int l = 0; l < N_DOG; l++) {
+        const float dl = gv[l + 1][0] - gv[l][0];
+        const float dc = gv[l + 1][1] - gv[l][1];
+        const float dr = gv[l + 1][2] - gv[l][2];
+        S.v[K][l] = dc;
+        S.hx[K][l] = fmax3(dl, dc, dr);
+        S.hn[K][l] = fmin3(dl, dc, dr);
+    }
+    if (r < r_last) ex_load(W, r + 1, gv);  // in flight while this row is evaluated
+    if (r < W.y0 + 1) return;               // warp-uniform: fewer than three rows so far
+    const int c = r - 1;
+    float M[N_DOG], m[N_DOG];
+#pragma unroll
+    for (int l = 0; l < N_DOG; l++) {
+        M[l] = fmax3(S.hx[A][l], S.hx[B][l], S.hx[K][l]);
+        m[l] = fmin3(S.hn[A][l], S.hn[B][l], S.hn[K][l]);
+    }
+    const bool ok = W.x_ok && (c >= IMAGE_BORDER) && (c < W.h - IMAGE_BORDER);
+    bool flat[N_DOG];
+#pragma unroll
+    for (int l = 0; l < N_DOG; l++) flat[l] = (M[l] == m[l]);
+    uint32_t mine = 0;  // lane s-1 keeps the ballot of scale s
+#pragma unroll
+    for (int s = 1; s <= SCALES_PER_OCTAVE; s++) {
+        const float v = S.v[B][s];
+        // the 27-neighbourhood max / min include v itself
+        const float Mx = fmax3(M[s - 1], M[s], M[s + 1]);
+        const float mn = fmin3(m[s - 1], m[s], m[s + 1]);
+        bool ext = ok && ((v > 0.0f && v >= Mx) || (v < 0.0f && v <= mn));
+        // A candidate whose three DoG layers are each spatially constant over its 3x3 window has zero
+        // spatial derivatives (h12 = h13 = h22 = h33 = h23 = 0, g2 = g3 = 0), so interpolate_extremum
+        // computes det = 0, every cofactor quotient is 0/0 = NaN, the NaN offsets never pass `abs() < 0.5`,
+        // round(NaN) as isize = 0 keeps the point in place, and after MAX_INTERPOLATION_STEPS it returns
+        // None (src/lib.rs:545-602).  Such points can never become keypoints, and saturated / constant
+        // image regions produce them for every pixel, so the pipeline drops them here.  KEEP_FLAT = true
+        // reproduces the reference's full candidate list for the parity view (sb200_last_candidates).
+        if (!KEEP_FLAT) ext = ext && !(flat[s - 1] && flat[s] && flat[s + 1]);
+        const uint32_t bits = __ballot_sync(0xffffffffu, ext);
+        if (W.lane == s - 1) mine = bits;
+    }
+    if (W.lane < SCALES_PER_OCTAVE) {
+        const long long ri = (long long)W.lane * W.h + c;
+        W.mask[ri * W.mask_pitch + W.strip] = mine;
+        if (mine) atomicAdd(W.rows + ri, (uint32_t)__popc(mine));
+    }
+}
+
+template <bool KEEP_FLAT>
 __global__ void __launch_bounds__(32 * EX_WARPS) k_extrema(const ExtremaParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x;
-    const int y0 = (blockIdx.y * EX_WARPS + warp) * EX_ROWS;
     const long long img = blockIdx.z;
-    const int w = p.w, h = p.h;
-    if (y0 >= h) return;
-    const float* g = p.gauss + img * p.img_stride;
-    uint32_t* mask = p.mask + img * p.mask_img_stride;
-    uint32_t* rows = p.rows + img * p.rows_img_stride;
-
-    const int x = strip * 32 + lane;
-    const int xc = min(x, w - 1);
-    // lane 0 fetches the column left of the strip, lane 31 the column right of it
-    const int xe = (lane == 0) ? max(strip * 32 - 1, 0) : min(strip * 32 + 32, w - 1);
-    const bool edge_lane = (lane == 0) || (lane == 31);
-    const bool x_ok = (x >= IMAGE_BORDER) && (x < w - IMAGE_BORDER);
-
-    float hmaxA[N_DOG], hmaxB[N_DOG], hminA[N_DOG], hminB[N_DOG], vB[N_DOG];
-#pragma unroll
-    for (int l = 0; l < N_DOG; l++) { hmaxA[l] = hmaxB[l] = hminA[l] = hminB[l] = vB[l] = 0.0f; }
-
-    const int r_end = min(y0 + EX_ROWS, h);  // centre rows [y0, r_end)
-    for (int r = y0 - 1; r <= r_end; r++) {
-        const int rc = min(max(r, 0), h - 1);
-        const float* row = g + (long long)rc * p.pitch;
-        float gv[N_LAYERS], ge[N_LAYERS];
-#pragma unroll
-        for (int l = 0; l < N_LAYERS; l++) {
-            gv[l] = __ldg(row + l * p.layer_stride + xc);
-            ge[l] = edge_lane ? __ldg(row + l * p.layer_stride + xe) : 0.0f;
-        }
-        float d[N_DOG], hmx[N_DOG], hmn[N_DOG];
-#pragma unroll
-        for (int l = 0; l < N_DOG; l++) {
-            d[l] = gv[l + 1] - gv[l];
-            float e = ge[l + 1] - ge[l];
-            float left = __shfl_up_sync(0xffffffffu, d[l], 1);
-            float right = __shfl_down_sync(0xffffffffu, d[l], 1);
-            if (lane == 0) left = e;
-            if (lane == 31) right = e;
-            hmx[l] = fmaxf(fmaxf(left, d[l]), right);
-            hmn[l] = fminf(fminf(left, d[l]), right);
-        }
-        if (r >= y0 + 1) {
-            const int c = r - 1;  // centre row: A = c-1, B = c, new = c+1
-            float M[N_DOG], m[N_DOG];
-#pragma unroll
-            for (int l = 0; l < N_DOG; l++) {
-                M[l] = fmaxf(fmaxf(hmaxA[l], hmaxB[l]), hmx[l]);
-                m[l] = fminf(fminf(hminA[l], hminB[l]), hmn[l]);
-            }
-            const bool ok = x_ok && (c >= IMAGE_BORDER) && (c < h - IMAGE_BORDER);
-#pragma unroll
-            for (int s = 1; s <= SCALES_PER_OCTAVE; s++) {
-                const float v = vB[s];
-                const float Mx = fmaxf(fmaxf(M[s - 1], M[s]), M[s + 1]);
-                const float mn = fminf(fminf(m[s - 1], m[s]), m[s + 1]);
-                const bool ext = ok && ((v > 0.0f && v >= Mx) || (v < 0.0f && v <= mn));
-                const uint32_t bits = __ballot_sync(0xffffffffu, ext);
-                if (lane == 0) {
-                    const long long ri = (long long)(s - 1) * h + c;
-                    mask[ri * p.mask_pitch + strip] = bits;
-                    if (bits) atomicAdd(rows + ri, (uint32_t)__popc(bits));
-                }
-            }
-        }
-#pragma unroll
-        for (int l = 0; l < N_DOG; l++) {
-            hmaxA[l] = hmaxB[l]; hmaxB[l] = hmx[l];
-            hminA[l] = hminB[l]; hminB[l] = hmn[l];
-            vB[l] = d[l];
-        }
+    ExWarp W;
+    W.strip = blockIdx.x;
+    W.y0 = (blockIdx.y * EX_WARPS + warp) * EX_ROWS;
+    W.h = p.h; W.pitch = p.pitch; W.mask_pitch = p.mask_pitch; W.lane = lane;
+    W.layer_stride = p.layer_stride;
+    if (W.y0 >= W.h) return;
+    const int x = W.strip * 32 + lane;
+    // columns outside [1, pitch-2] load a clamped column instead: they can never be candidates
+    // (x < 5 or x >= w - 5) and, since every lane loads its own neighbours, nobody reads their values
+    W.g = p.gauss + img * p.img_stride + min(max(x, 1), p.pitch - 2);
+    W.mask = p.mask + img * p.mask_img_stride;
+    W.rows = p.rows + img * p.rows_img_stride;
+    W.x_ok = (x >= IMAGE_BORDER) && (x < p.w - IMAGE_BORDER);
+    ExState S;
+    const int r_end = min(W.y0 + EX_ROWS, W.h);  // centre rows [y0, r_end): image rows y0-1 .. r_end
+    float gv[N_LAYERS][3];
+    ex_load(W, W.y0 - 1, gv);
+    for (int r = W.y0 - 1; r <= r_end; r += 3) {
+        ex_step<0, KEEP_FLAT>(W, S, r, r_end, gv);
+        if (r + 1 <= r_end) ex_step<1, KEEP_FLAT>(W, S, r + 1, r_end, gv);
+        if (r + 2 <= r_end) ex_step<2, KEEP_FLAT>(W, S, r + 2, r_end, gv);
     }
 }
 

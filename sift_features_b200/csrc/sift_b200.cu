@@ -7,12 +7,14 @@
 // synchronisation per group is the read of the per-image keypoint counts.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --fmad=false -shared ...
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -33,6 +35,7 @@ namespace {
 const char* kStageNames[SB200_STAGE_COUNT] = {"seed", "blur", "extrema", "refine", "orient", "descriptor"};
 
 struct Slot {
+    int index = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_counts = nullptr;
     // input
@@ -78,6 +81,10 @@ struct sb200_ctx {
     // layout of the current image size
     PyrLayout L{};
     uint32_t cur_w = 0, cur_h = 0;
+    // TMA descriptors of the Gaussian arenas: [slot][octave][destination layer 1..5]
+    CUtensorMap tmap[2][MAX_OCT][N_LAYERS];
+    bool tmap_ok[MAX_OCT] = {false};
+    void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
     // capacities the arenas were sized for
     long long gauss_floats_cap = 0, mask_words_cap = 0;
     int rows_cap = 0;
@@ -92,6 +99,8 @@ struct sb200_ctx {
     bool have_pyramid = false;
     bool have_single = false;  // slot[0] holds the intermediates of a single-image run
     int64_t last_limit = -1;
+    int dev_rr = 0;     // slot used by the next sb200_extract_batch_device
+    int last_slot = 0;  // slot holding the most recent run (debug / device-result views)
     // descriptor-only scratch
     float* d_dimg = nullptr;
     size_t dimg_cap = 0;
@@ -328,6 +337,44 @@ int ensure_result_capacity(sb200_ctx* ctx, uint64_t need_kp, uint64_t need_imgs)
     return SB200_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int LI>
+int encode_one(sb200_ctx* ctx, int slot, int o) {
+    using C = TmaCfg<LI>;
+    const OctLayout& ol = ctx->L.o[o];
+    const cuuint64_t gdim[4] = {(cuuint64_t)ol.w, (cuuint64_t)ol.h, (cuuint64_t)N_LAYERS, (cuuint64_t)ctx->max_batch};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ol.pitch * 4, (cuuint64_t)ol.layer_stride * 4,
+                                (cuuint64_t)ctx->L.img_floats * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)C::BW, (cuuint32_t)C::SH, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode_fn)(&ctx->tmap[slot][o][LI], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                                 ctx->slot[slot].d_gauss + ol.off, gdim, gstr, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SB200_E_CUDA, "cuTensorMapEncodeTiled failed (%d) octave %d layer %d", (int)r, o, LI);
+    return SB200_OK;
+}
+
+int build_tensor_maps(sb200_ctx* ctx) {
+    for (int o = 0; o < MAX_OCT; o++) ctx->tmap_ok[o] = false;
+    if (!ctx->encode_fn || getenv("SB200_NO_TMA")) return SB200_OK;  // env switch: debugging aid only
+    for (int o = 0; o < ctx->L.n_oct; o++) {
+        const OctLayout& ol = ctx->L.o[o];
+        if (ol.w < TMA_MIN_DIM || ol.h < TMA_MIN_DIM) continue;
+        for (int sl = 0; sl < 2; sl++) {
+            int r;
+            if ((o == 0 && (r = encode_one<0>(ctx, sl, o))) || (r = encode_one<1>(ctx, sl, o)) || (r = encode_one<2>(ctx, sl, o)) || (r = encode_one<3>(ctx, sl, o)) ||
+                (r = encode_one<4>(ctx, sl, o)) || (r = encode_one<5>(ctx, sl, o)))
+                return r;
+        }
+        ctx->tmap_ok[o] = true;
+    }
+    return SB200_OK;
+}
+
 int set_image_size(sb200_ctx* ctx, uint32_t w, uint32_t h) {
     if (w == 0 || h == 0) return fail(ctx, SB200_E_INVALID, "empty image (%ux%u)", w, h);
     if (w > ctx->max_w || h > ctx->max_h)
@@ -340,6 +387,8 @@ int set_image_size(sb200_ctx* ctx, uint32_t w, uint32_t h) {
         ctx->cur_w = w;
         ctx->cur_h = h;
         ctx->have_pyramid = ctx->have_single = false;
+        int rc = build_tensor_maps(ctx);
+        if (rc) return rc;
     }
     return SB200_OK;
 }
@@ -359,6 +408,20 @@ void launch_blur(cudaStream_t st, const BlurParams& p, uint32_t n) {
     k_blur<LI, SEED, DEC><<<grid, C::THREADS, C::SMEM, st>>>(p);
 }
 
+template <int LI, bool DEC>
+int set_tma_attr(sb200_ctx* ctx) {
+    CU(cudaFuncSetAttribute(k_blur_tma<LI, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaCfg<LI>::SMEM));
+    CU(cudaFuncSetAttribute(k_blur_tma<LI, DEC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    return SB200_OK;
+}
+
+template <int LI, bool DEC>
+void launch_blur_tma(cudaStream_t st, const CUtensorMap& tm, const BlurParams& p, uint32_t n, int src_layer) {
+    using C = TmaCfg<LI>;
+    dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + C::TH - 1) / C::TH, n);
+    k_blur_tma<LI, DEC><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer);
+}
+
 // Gaussian scale space + DoG/extrema masks for the n images staged in slot.d_in
 int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, uint32_t in_stride,
                     uint64_t in_img_stride, const uint8_t* d_in) {
@@ -373,8 +436,22 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
         p.w = L.o[0].w; p.h = L.o[0].h; p.pitch = L.o[0].pitch;
         p.in = d_in; p.in_img_stride = (long long)in_img_stride;
         p.in_w = (int)w; p.in_h = (int)h; p.in_stride = (int)in_stride;
-        launch_blur<0, true, false>(st, p, n);
-        count_launch(ctx, SB200_STAGE_SEED);
+        if (ctx->tmap_ok[0]) {
+            // upsample into layer 5 of octave 0 (free until the last blur of the octave overwrites it),
+            // then the seed blur as a TMA blur from layer 5 into layer 0
+            UpsampleParams u{};
+            u.in = d_in; u.in_img_stride = (long long)in_img_stride;
+            u.in_w = (int)w; u.in_h = (int)h; u.in_stride = (int)in_stride;
+            u.dst = s.d_gauss + L.o[0].off + 5 * L.o[0].layer_stride;
+            u.img_stride = L.img_floats; u.pitch = L.o[0].pitch;
+            dim3 grid((((int)w + 1) / 2 + 255) / 256, h + 1, n);
+            k_upsample2x<<<grid, 256, 0, st>>>(u);
+            launch_blur_tma<0, false>(st, ctx->tmap[s.index][0][0], p, n, 5);
+            count_launch(ctx, SB200_STAGE_SEED, 2);
+        } else {
+            launch_blur<0, true, false>(st, p, n);
+            count_launch(ctx, SB200_STAGE_SEED);
+        }
     }
     for (int o = 0; o < L.n_oct; o++) {
         const OctLayout& ol = L.o[o];
@@ -392,15 +469,29 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
                     p.dec = s.d_gauss + L.o[o + 1].off;
                     p.dec_w = L.o[o + 1].w; p.dec_h = L.o[o + 1].h; p.dec_pitch = L.o[o + 1].pitch;
                 }
-                switch (l) {
-                    case 1: launch_blur<1, false, false>(st, p, n); break;
-                    case 2: launch_blur<2, false, false>(st, p, n); break;
-                    case 3:
-                        if (dec) launch_blur<3, false, true>(st, p, n);
-                        else launch_blur<3, false, false>(st, p, n);
-                        break;
-                    case 4: launch_blur<4, false, false>(st, p, n); break;
-                    default: launch_blur<5, false, false>(st, p, n); break;
+                if (ctx->tmap_ok[o]) {
+                    const CUtensorMap& tm = ctx->tmap[s.index][o][l];
+                    switch (l) {
+                        case 1: launch_blur_tma<1, false>(st, tm, p, n, 0); break;
+                        case 2: launch_blur_tma<2, false>(st, tm, p, n, 1); break;
+                        case 3:
+                            if (dec) launch_blur_tma<3, true>(st, tm, p, n, 2);
+                            else launch_blur_tma<3, false>(st, tm, p, n, 2);
+                            break;
+                        case 4: launch_blur_tma<4, false>(st, tm, p, n, 3); break;
+                        default: launch_blur_tma<5, false>(st, tm, p, n, 4); break;
+                    }
+                } else {
+                    switch (l) {
+                        case 1: launch_blur<1, false, false>(st, p, n); break;
+                        case 2: launch_blur<2, false, false>(st, p, n); break;
+                        case 3:
+                            if (dec) launch_blur<3, false, true>(st, p, n);
+                            else launch_blur<3, false, false>(st, p, n);
+                            break;
+                        case 4: launch_blur<4, false, false>(st, p, n); break;
+                        default: launch_blur<5, false, false>(st, p, n); break;
+                    }
                 }
                 count_launch(ctx, SB200_STAGE_BLUR);
             }
@@ -417,8 +508,8 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             e.mask_pitch = ol.mask_pitch;
             e.rows = s.d_rows + ol.row_base;
             e.rows_img_stride = L.img_rows;
-            dim3 grid(ol.mask_pitch, (ol.h + EX_ROWS * EX_WARPS - 1) / (EX_ROWS * EX_WARPS), n);
-            k_extrema<<<grid, 32 * EX_WARPS, 0, st>>>(e);
+            dim3 grid((ol.w + EX_COLS - 1) / EX_COLS, (ol.h + EX_ROWS * EX_WARPS - 1) / (EX_ROWS * EX_WARPS), n);
+            k_extrema<false><<<grid, 32 * EX_WARPS, 0, st>>>(e);
             count_launch(ctx, SB200_STAGE_EXTREMA);
         }
     }
@@ -492,7 +583,7 @@ int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
         D.out_off = out_off;
         D.out_kps = s.d_out_kps;
         D.out_desc = s.d_out_desc;
-        k_descriptor<<<dim3(gx, n), 32 * DESC_WARPS, 0, st>>>(D);
+        k_descriptor<<<dim3(gx, n), 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(D);
         count_launch(ctx, SB200_STAGE_DESCRIPTOR, 2);
     }
     CU(cudaGetLastError());
@@ -670,8 +761,24 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         if ((r = set_blur_attr<3, false, true>(ctx))) return r;
         if ((r = set_blur_attr<4, false, false>(ctx))) return r;
         if ((r = set_blur_attr<5, false, false>(ctx))) return r;
-        for (auto& s : ctx->slot)
-            if ((r = alloc_slot(ctx, s))) return r;
+        if ((r = set_tma_attr<0, false>(ctx)) || (r = set_tma_attr<1, false>(ctx)) || (r = set_tma_attr<2, false>(ctx)) || (r = set_tma_attr<3, false>(ctx)) ||
+            (r = set_tma_attr<3, true>(ctx)) || (r = set_tma_attr<4, false>(ctx)) || (r = set_tma_attr<5, false>(ctx)))
+            return r;
+        CU(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DESC_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_descriptor_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DESC_SMEM_BYTES));
+        {
+            cudaDriverEntryPointQueryResult q;
+            void* fn = nullptr;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                ctx->encode_fn = fn;
+            else
+                return fail(ctx, SB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        }
+        for (int i = 0; i < 2; i++) {
+            ctx->slot[i].index = i;
+            if ((r = alloc_slot(ctx, ctx->slot[i]))) return r;
+        }
         CU(cudaEventCreate(&ctx->t0));
         CU(cudaEventCreate(&ctx->t1));
         return SB200_OK;
@@ -729,6 +836,7 @@ int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_
     if (rc) return rc;
     ctx->have_single = (n == 1);
     ctx->have_pyramid = (n == 1);
+    ctx->last_slot = 0;
     ctx->last_limit = features_limit;
     fill_result(ctx, n, out);
     return SB200_OK;
@@ -747,7 +855,11 @@ int sb200_extract_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n
     CU(cudaSetDevice(ctx->device));
     int rc = set_image_size(ctx, w, h);
     if (rc) return rc;
-    Slot& s = ctx->slot[0];
+    // consecutive calls alternate between the two slots so that the tail of one batch
+    // (small octaves, keypoint kernels) overlaps the head of the next
+    Slot& s = ctx->slot[ctx->dev_rr];
+    ctx->last_slot = ctx->dev_rr;
+    ctx->dev_rr ^= 1;
     rc = enqueue_pyramid(ctx, s, n, w, h, stride, image_stride, d_gray);
     if (rc) return rc;
     rc = enqueue_detect(ctx, s, n, features_limit);
@@ -762,7 +874,7 @@ int sb200_device_result(sb200_ctx* ctx, uint32_t* counts, uint32_t n, const sb20
                         const uint8_t** d_descriptors, uint32_t* capacity_per_image) {
     if (!ctx) return SB200_E_INVALID;
     CU(cudaSetDevice(ctx->device));
-    Slot& s = ctx->slot[0];
+    Slot& s = ctx->slot[ctx->last_slot];
     if (n > ctx->max_batch) return fail(ctx, SB200_E_INVALID, "n exceeds max_batch");
     CU(cudaStreamSynchronize(s.stream));
     if (counts && n)
@@ -795,6 +907,7 @@ int sb200_precompute(sb200_ctx* ctx, const uint8_t* gray, uint32_t w, uint32_t h
     if (rc) return rc;
     ctx->have_pyramid = true;
     ctx->have_single = false;
+    ctx->last_slot = 0;
     return SB200_OK;
 }
 
@@ -803,7 +916,7 @@ int sb200_extract_precomputed(sb200_ctx* ctx, int64_t features_limit, sb200_resu
     if (!out) return fail(ctx, SB200_E_INVALID, "null result");
     if (!ctx->have_pyramid) return fail(ctx, SB200_E_STATE, "no pyramid resident: call sb200_precompute first");
     CU(cudaSetDevice(ctx->device));
-    Slot& s = ctx->slot[0];
+    Slot& s = ctx->slot[ctx->last_slot];
     for (auto& sl : ctx->slot) CU(cudaStreamSynchronize(sl.stream));
     ctx->res_n = 0;
     int rc = ensure_result_capacity(ctx, 0, 1);
@@ -843,7 +956,7 @@ int sb200_pyramid_layer(sb200_ctx* ctx, uint32_t octave, uint32_t layer, float* 
     CU(cudaSetDevice(ctx->device));
     const OctLayout& ol = ctx->L.o[octave];
     if (ol.w < 1 || ol.h < 1) return SB200_OK;
-    Slot& s = ctx->slot[0];
+    Slot& s = ctx->slot[ctx->last_slot];
     CU(cudaMemcpy2DAsync(out, (size_t)ol.w * 4, s.d_gauss + ol.off + (long long)layer * ol.layer_stride,
                          (size_t)ol.pitch * 4, (size_t)ol.w * 4, ol.h, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaStreamSynchronize(s.stream));
@@ -857,7 +970,7 @@ int sb200_pyramid_dog(sb200_ctx* ctx, uint32_t octave, uint32_t layer, float* ou
     CU(cudaSetDevice(ctx->device));
     const OctLayout& ol = ctx->L.o[octave];
     if (ol.w < 1 || ol.h < 1) return SB200_OK;
-    Slot& s = ctx->slot[0];
+    Slot& s = ctx->slot[ctx->last_slot];
     float* tmp = nullptr;
     CU(cudaMalloc((void**)&tmp, (size_t)ol.w * ol.h * 4));
     const float* a = s.d_gauss + ol.off + (long long)layer * ol.layer_stride;
@@ -871,32 +984,69 @@ int sb200_pyramid_dog(sb200_ctx* ctx, uint32_t octave, uint32_t layer, float* ou
 }
 
 int sb200_last_candidates(sb200_ctx* ctx, sb200_candidate* out, uint64_t cap, uint64_t* n) {
+    // Parity view: the reference's complete candidate list (src/lib.rs:324-332), including the exactly-flat
+    // neighbourhoods the pipeline drops early.  Recomputed from the resident pyramid into temporary buffers.
     if (!ctx) return SB200_E_INVALID;
-    if (!ctx->have_single) return fail(ctx, SB200_E_STATE, "no single-image run resident");
+    if (!ctx->have_single && !ctx->have_pyramid) return fail(ctx, SB200_E_STATE, "no single-image run resident");
     CU(cudaSetDevice(ctx->device));
-    Slot& s = ctx->slot[0];
-    CU(cudaStreamSynchronize(s.stream));
-    uint32_t cnt = 0;
-    CU(cudaMemcpy(&cnt, s.d_counts, 4, cudaMemcpyDeviceToHost));
-    if (n) *n = cnt;
-    const uint32_t m = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(cnt, ctx->cap), cap);
-    if (out && m) {
-        std::vector<uint32_t> keys(m);
-        CU(cudaMemcpy(keys.data(), s.d_keys, (size_t)m * 4, cudaMemcpyDeviceToHost));
-        for (uint32_t i = 0; i < m; i++) {
-            int o, sc, y, x;
-            unpack_key(keys[i], o, sc, y, x);
-            out[i] = {o, sc, y, x};
+    Slot& s = ctx->slot[ctx->last_slot];
+    const PyrLayout& L = ctx->L;
+    cudaStream_t st = s.stream;
+    CU(cudaStreamSynchronize(st));
+    uint32_t *d_mask = nullptr, *d_rows = nullptr, *d_rowoff = nullptr, *d_cnt = nullptr, *d_keys = nullptr;
+    int rc = SB200_OK;
+    auto cleanup = [&]() { cudaFree(d_mask); cudaFree(d_rows); cudaFree(d_rowoff); cudaFree(d_cnt); cudaFree(d_keys); };
+    auto body = [&]() -> int {
+        CU(dalloc(&d_mask, (size_t)L.img_mask_words));
+        CU(dalloc(&d_rows, (size_t)L.img_rows));
+        CU(dalloc(&d_rowoff, (size_t)L.img_rows));
+        CU(dalloc(&d_cnt, 1));
+        CU(cudaMemsetAsync(d_rows, 0, (size_t)L.img_rows * 4, st));
+        for (int o = 0; o < L.n_oct; o++) {
+            const OctLayout& ol = L.o[o];
+            if (!ol.scanned) continue;
+            ExtremaParams e{};
+            e.gauss = s.d_gauss + ol.off; e.img_stride = L.img_floats; e.layer_stride = ol.layer_stride;
+            e.w = ol.w; e.h = ol.h; e.pitch = ol.pitch;
+            e.mask = d_mask + ol.mask_off; e.mask_img_stride = L.img_mask_words; e.mask_pitch = ol.mask_pitch;
+            e.rows = d_rows + ol.row_base; e.rows_img_stride = L.img_rows;
+            dim3 grid((ol.w + EX_COLS - 1) / EX_COLS, (ol.h + EX_ROWS * EX_WARPS - 1) / (EX_ROWS * EX_WARPS), 1);
+            k_extrema<true><<<grid, 32 * EX_WARPS, 0, st>>>(e);
+            ctx->launches++;
         }
-    }
-    return SB200_OK;
+        k_rowscan<<<1, 1024, 0, st>>>(d_rows, d_rowoff, L.img_rows, d_cnt);
+        ctx->launches++;
+        uint32_t cnt = 0;
+        CU(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (n) *n = cnt;
+        const uint32_t m = (uint32_t)std::min<uint64_t>(cnt, cap);
+        if (out && m) {
+            CU(dalloc(&d_keys, (size_t)cnt));
+            dim3 grid((L.img_rows + 7) / 8, 1);
+            k_compact<<<grid, 256, 0, st>>>(L, d_mask, d_rows, d_rowoff, d_keys, cnt);
+            ctx->launches++;
+            std::vector<uint32_t> keys(m);
+            CU(cudaMemcpyAsync(keys.data(), d_keys, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < m; i++) {
+                int o, sc, y, x;
+                unpack_key(keys[i], o, sc, y, x);
+                out[i] = {o, sc, y, x};
+            }
+        }
+        return SB200_OK;
+    };
+    rc = body();
+    cleanup();
+    return rc;
 }
 
 int sb200_last_sift_keypoints(sb200_ctx* ctx, sb200_sift_keypoint* out, uint64_t cap, uint64_t* n) {
     if (!ctx) return SB200_E_INVALID;
     if (!ctx->have_single) return fail(ctx, SB200_E_STATE, "no single-image run resident");
     CU(cudaSetDevice(ctx->device));
-    Slot& s = ctx->slot[0];
+    Slot& s = ctx->slot[ctx->last_slot];
     CU(cudaStreamSynchronize(s.stream));
     uint32_t cnt = 0;
     CU(cudaMemcpy(&cnt, s.d_counts + ctx->max_batch, 4, cudaMemcpyDeviceToHost));
@@ -921,7 +1071,7 @@ int sb200_compute_descriptors_device(sb200_ctx* ctx, const float* d_img, uint32_
     cudaStream_t st = ctx->slot[0].stream;
     StageScope sc(ctx, st, SB200_STAGE_DESCRIPTOR);
     const int grid = (int)std::min<uint64_t>((n + DESC_WARPS - 1) / DESC_WARPS, (uint64_t)ctx->sm_count * 16);
-    k_descriptor_list<<<grid, 32 * DESC_WARPS, 0, st>>>(d_img, (int)w, (int)h, (int)stride,
+    k_descriptor_list<<<grid, 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(d_img, (int)w, (int)h, (int)stride,
                                                         reinterpret_cast<const DescIn*>(d_kps), n, d_out);
     count_launch(ctx, SB200_STAGE_DESCRIPTOR);
     CU(cudaGetLastError());
