@@ -1,0 +1,113 @@
+// sift_features.hpp -- header-only C++ mirror of the crate's public interface over the C ABI
+// (include/sift_b200.h).  Same names, argument meaning and result types as src/lib.rs:39-81,124-177,785;
+// the crate panics on failure, this mirror throws sift_features::Error.
+#pragma once
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sift_b200.h"
+
+namespace sift_features {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int st, const std::string& what) : std::runtime_error(what), status(st) {}
+};
+
+// src/lib.rs:48-56
+struct KeyPoint {
+    float x, y, size, angle, response;
+    bool operator==(const KeyPoint& o) const {
+        return x == o.x && y == o.y && size == o.size && angle == o.angle && response == o.response;
+    }
+};
+static_assert(sizeof(KeyPoint) == sizeof(sb200_keypoint), "layout");
+
+// src/lib.rs:39-46: descriptors is (keypoints.size(), 128) row-major
+struct SiftResult {
+    std::vector<KeyPoint> keypoints;
+    std::vector<uint8_t> descriptors;
+};
+
+// image::GrayImage (src/lib.rs:71): borrowed, row-major, `stride` bytes per row
+struct GrayImageView {
+    const uint8_t* data;
+    uint32_t width, height, stride;
+};
+
+// One context per (thread, device); owns the device arenas.  Not re-entrant.
+class Extractor {
+public:
+    Extractor(uint32_t max_w, uint32_t max_h, uint32_t max_batch = 1, int device = 0) {
+        int st = sb200_create(device, max_w, max_h, max_batch, 0, &ctx_);
+        if (st) throw Error(st, std::string("sb200_create: ") + sb200_status_string(st));
+    }
+    ~Extractor() { sb200_destroy(ctx_); }
+    Extractor(const Extractor&) = delete;
+    Extractor& operator=(const Extractor&) = delete;
+
+    // sift / sift_with_processing::<OpenCVProcessing>, src/lib.rs:71-81
+    SiftResult sift(const GrayImageView& img, std::optional<size_t> features_limit = std::nullopt) {
+        sb200_result r{};
+        check(sb200_extract(ctx_, img.data, img.width, img.height, img.stride,
+                            features_limit ? (int64_t)*features_limit : -1, &r));
+        return take(r, 0);
+    }
+    // n images of identical size -> one SiftResult per image
+    std::vector<SiftResult> sift_batch(const uint8_t* data, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                                       uint64_t image_stride, std::optional<size_t> features_limit = std::nullopt) {
+        sb200_result r{};
+        check(sb200_extract_batch(ctx_, data, n, w, h, stride, image_stride,
+                                  features_limit ? (int64_t)*features_limit : -1, &r));
+        std::vector<SiftResult> out;
+        for (uint32_t i = 0; i < n; i++) out.push_back(take(r, i));
+        return out;
+    }
+    // precompute_images, src/lib.rs:131-143 (the pyramid stays on the device)
+    void precompute_images(const GrayImageView& img) {
+        check(sb200_precompute(ctx_, img.data, img.width, img.height, img.stride));
+    }
+    // sift_with_precomputed, src/lib.rs:147-177
+    SiftResult sift_with_precomputed(std::optional<size_t> features_limit = std::nullopt) {
+        sb200_result r{};
+        check(sb200_extract_precomputed(ctx_, features_limit ? (int64_t)*features_limit : -1, &r));
+        return take(r, 0);
+    }
+    // compute_descriptor, src/lib.rs:785-990
+    std::vector<uint8_t> compute_descriptor(const float* img, uint32_t w, uint32_t h, float x, float y, float scale,
+                                            float orientation) {
+        sb200_desc_in k{x, y, scale, orientation};
+        std::vector<uint8_t> out(SB200_DESC_SIZE);
+        check(sb200_compute_descriptors(ctx_, img, w, h, w, &k, 1, out.data()));
+        return out;
+    }
+    sb200_ctx* handle() { return ctx_; }
+
+private:
+    void check(int st) {
+        if (st) throw Error(st, sb200_last_error(ctx_));
+    }
+    static SiftResult take(const sb200_result& r, uint32_t i) {
+        SiftResult s;
+        const uint64_t a = r.offsets[i], b = r.offsets[i + 1];
+        s.keypoints.resize(b - a);
+        for (uint64_t k = a; k < b; k++) {
+            const sb200_keypoint& q = r.keypoints[k];
+            s.keypoints[k - a] = KeyPoint{q.x, q.y, q.size, q.angle, q.response};
+        }
+        s.descriptors.assign(r.descriptors + a * SB200_DESC_SIZE, r.descriptors + b * SB200_DESC_SIZE);
+        return s;
+    }
+    sb200_ctx* ctx_ = nullptr;
+};
+
+// src/lib.rs:71 as a free function (creates a context sized for this image)
+inline SiftResult sift(const GrayImageView& img, std::optional<size_t> features_limit = std::nullopt) {
+    Extractor ex(img.width, img.height);
+    return ex.sift(img, features_limit);
+}
+
+}  // namespace sift_features

@@ -1,0 +1,133 @@
+//! Drop-in for the extraction path of `sift-features` on NVIDIA B200: the same public items as the
+//! crate's `src/lib.rs:39-81,124-177,785` (`sift`, `sift_with_processing`, `precompute_images`,
+//! `sift_with_precomputed`, `compute_descriptor`, `SiftResult`, `KeyPoint`), implemented by calls into
+//! `libsift_b200.so` (C ABI: include/sift_b200.h).  NOT compiled in the build image (no rustc); kept as
+//! the reference-side binding described in INTEGRATION.md.
+use image::GrayImage;
+use ndarray::{Array2, ArrayView2};
+use std::os::raw::{c_char, c_int};
+
+#[repr(C)]
+#[derive(Debug, Clone, Copy, PartialEq, PartialOrd)]
+pub struct KeyPoint {
+    pub x: f32,
+    pub y: f32,
+    pub size: f32,
+    pub angle: f32,
+    pub response: f32,
+}
+
+#[derive(Debug, Clone, PartialEq)]
+pub struct SiftResult {
+    pub keypoints: Vec<KeyPoint>,
+    /// `(keypoints.len(), 128)`, same order as `keypoints`
+    pub descriptors: Array2<u8>,
+}
+
+#[repr(C)]
+struct Sb200Ctx {
+    _private: [u8; 0],
+}
+#[repr(C)]
+struct Sb200Result {
+    n: u64,
+    n_images: u32,
+    offsets: *const u64,
+    keypoints: *const KeyPoint,
+    descriptors: *const u8,
+}
+#[repr(C)]
+struct Sb200DescIn {
+    x: f32,
+    y: f32,
+    scale: f32,
+    orientation: f32,
+}
+
+extern "C" {
+    fn sb200_create(device: c_int, max_w: u32, max_h: u32, max_batch: u32, max_kp: u32, out: *mut *mut Sb200Ctx) -> c_int;
+    fn sb200_destroy(ctx: *mut Sb200Ctx);
+    fn sb200_last_error(ctx: *const Sb200Ctx) -> *const c_char;
+    fn sb200_extract(ctx: *mut Sb200Ctx, gray: *const u8, w: u32, h: u32, stride: u32, limit: i64, out: *mut Sb200Result) -> c_int;
+    fn sb200_precompute(ctx: *mut Sb200Ctx, gray: *const u8, w: u32, h: u32, stride: u32) -> c_int;
+    fn sb200_extract_precomputed(ctx: *mut Sb200Ctx, limit: i64, out: *mut Sb200Result) -> c_int;
+    fn sb200_compute_descriptors(ctx: *mut Sb200Ctx, img: *const f32, w: u32, h: u32, stride: u32,
+                                 kps: *const Sb200DescIn, n: u64, out: *mut u8) -> c_int;
+}
+
+/// One context per (thread, device); owns the device arenas.
+pub struct Context(*mut Sb200Ctx);
+
+impl Context {
+    pub fn new(max_w: u32, max_h: u32) -> Self {
+        let mut p = std::ptr::null_mut();
+        let st = unsafe { sb200_create(0, max_w, max_h, 1, 0, &mut p) };
+        assert!(st == 0, "sb200_create failed with status {st} (no CUDA device? there is no CPU fallback)");
+        Context(p)
+    }
+    fn check(&self, st: c_int) {
+        if st != 0 {
+            let msg = unsafe { std::ffi::CStr::from_ptr(sb200_last_error(self.0)) };
+            panic!("sift_b200 status {st}: {}", msg.to_string_lossy()); // the crate panics on errors too
+        }
+    }
+    fn take(r: &Sb200Result) -> SiftResult {
+        let n = r.n as usize;
+        let kps = if n == 0 { Vec::new() } else { unsafe { std::slice::from_raw_parts(r.keypoints, n) }.to_vec() };
+        let desc = if n == 0 { Vec::new() } else { unsafe { std::slice::from_raw_parts(r.descriptors, n * 128) }.to_vec() };
+        SiftResult { keypoints: kps, descriptors: Array2::from_shape_vec((n, 128), desc).unwrap() }
+    }
+    pub fn sift(&mut self, img: &GrayImage, features_limit: Option<usize>) -> SiftResult {
+        let mut r = std::mem::MaybeUninit::<Sb200Result>::zeroed();
+        let st = unsafe {
+            sb200_extract(self.0, img.as_raw().as_ptr(), img.width(), img.height(), img.width(),
+                          features_limit.map_or(-1, |l| l as i64), r.as_mut_ptr())
+        };
+        self.check(st);
+        Self::take(unsafe { &r.assume_init() })
+    }
+}
+
+impl Drop for Context {
+    fn drop(&mut self) {
+        unsafe { sb200_destroy(self.0) }
+    }
+}
+
+/// Device-resident pyramid of the last `precompute_images` (src/lib.rs:124-128).
+pub struct PrecomputedImages {
+    ctx: Context,
+}
+
+/// src/lib.rs:71 (OpenCVProcessing flavour: the one the crate's test and snapshots pin).
+pub fn sift(img: &GrayImage, features_limit: Option<usize>) -> SiftResult {
+    Context::new(img.width(), img.height()).sift(img, features_limit)
+}
+
+/// src/lib.rs:131
+pub fn precompute_images(img: &GrayImage) -> PrecomputedImages {
+    let ctx = Context::new(img.width(), img.height());
+    let st = unsafe { sb200_precompute(ctx.0, img.as_raw().as_ptr(), img.width(), img.height(), img.width()) };
+    ctx.check(st);
+    PrecomputedImages { ctx }
+}
+
+/// src/lib.rs:147
+pub fn sift_with_precomputed(pre: &PrecomputedImages, features_limit: Option<usize>) -> SiftResult {
+    let mut r = std::mem::MaybeUninit::<Sb200Result>::zeroed();
+    let st = unsafe { sb200_extract_precomputed(pre.ctx.0, features_limit.map_or(-1, |l| l as i64), r.as_mut_ptr()) };
+    pre.ctx.check(st);
+    Context::take(unsafe { &r.assume_init() })
+}
+
+/// src/lib.rs:785
+pub fn compute_descriptor(img: &ArrayView2<f32>, x: f32, y: f32, scale: f32, orientation: f32) -> impl IntoIterator<Item = u8> {
+    let (h, w) = img.dim();
+    let data = img.as_standard_layout();
+    let ctx = Context::new(w as u32, h as u32);
+    let k = Sb200DescIn { x, y, scale, orientation };
+    let mut out = vec![0u8; 128];
+    let st = unsafe { sb200_compute_descriptors(ctx.0, data.as_ptr(), w as u32, h as u32, w as u32, &k, 1, out.as_mut_ptr()) };
+    ctx.check(st);
+    out
+}
