@@ -449,34 +449,56 @@ struct DescGeom {
     float sin_s, cos_s, orientation;
 };
 
+// atan2(y, x) in degrees, [0, 360): minimax polynomial of atan on [0,1] (|error| < 3.3e-7 rad) plus octant
+// folding.  The reference's f64 atan2 only feeds the trilinear orientation weights here (continuous in the
+// angle), so a 2e-5 degree error is far below the u8 quantisation step of the descriptor.
+__device__ __forceinline__ float fast_atan2_deg(const float y, const float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+    const float s = a * a;
+    float p = 0x1.be6ae0p-8f;
+    p = fmaf(p, s, -0x1.134924p-5f);
+    p = fmaf(p, s, 0x1.462378p-4f);
+    p = fmaf(p, s, -0x1.0f04d4p-3f);
+    p = fmaf(p, s, 0x1.95aa00p-3f);
+    p = fmaf(p, s, -0x1.552b7cp-2f);
+    p = fmaf(p, s, 0x1.ffff7ep-1f);
+    float r = p * a;                                   // [0, pi/4]
+    if (ay > ax) r = 1.57079632679489661923f - r;      // [0, pi/2]
+    if (x < 0.f) r = 3.14159265358979323846f - r;      // [0, pi]
+    if (y < 0.f) r = 6.28318530717958647692f - r;      // (pi, 2pi]
+    float deg = r * 57.29577951308232f;
+    if (deg >= 360.0f) deg -= 360.0f;
+    return deg;
+}
+
 // one queued sample per active lane: gradient, weight, angle, trilinear split, accumulation
 __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint32_t packed, const bool active,
-                                                  float* hist, const int lane, const uint64_t* s_tab) {
+                                                  float* hist, const int lane) {
     float cv[8];
-    int cb[8];
+    bool ok[8];
+    int b0 = 0, b1 = 0;  // word offsets of the (first cell, o0) and (first cell, o1) bins
 #pragma unroll
-    for (int k = 0; k < 8; k++) { cv[k] = 0.f; cb[k] = -1; }
+    for (int k = 0; k < 8; k++) { cv[k] = 0.f; ok[k] = false; }
     if (active) {
+        // geometry: the reference's f32 operations, so cell indices and fractions are its values
         const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
         const float col_rot = (float)xw * G.cos_s - (float)yw * G.sin_s;
         const float row_rot = (float)xw * G.sin_s + (float)yw * G.cos_s;
-        const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
+        const float rb = (row_rot + 2.0f) - 0.5f, cbn = (col_rot + 2.0f) - 0.5f;
         const float* c = G.img + (long long)(G.y + yw) * G.pitch + (G.x + xw);
         const float dx = __ldg(c + 1) - __ldg(c - 1);
         const float dy = __ldg(c - G.pitch) - __ldg(c + G.pitch);
-        const float wgt = col_rot * col_rot + row_rot * row_rot;
-        const float weight = sbm::expf_glibc(s_tab, wgt * -0.125f);  // -2 / 4^2, :859
-        // ((atan2_f64(dy,dx).to_degrees() + 360) % 360) as f32 - orientation, :871
-        float deg = atan2f(dy, dx) * 57.29577951308232f;
-        if (deg < 0.f) deg += 360.0f;
-        if (deg >= 360.0f) deg -= 360.0f;
-        const float orient = deg - G.orientation;
-        float mag = sqrtf(dx * dx + dy * dy);
-        const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
-        mag = mag * weight;
+        // magnitude, Gaussian weight and angle: fast approximations (relative error ~1e-6), see header comment
+        const float d2 = fmaf(dx, dx, dy * dy);
+        const float wgt = fmaf(col_rot, col_rot, row_rot * row_rot);
+        const float mag = (d2 > 0.f ? d2 * rsqrtf(d2) : 0.f) * __expf(wgt * -0.125f);  // exp(-2/4^2 * wgt), :859
+        const float orient = fast_atan2_deg(dy, dx) - G.orientation;                   // :871
         const float obin = orient * (8.0f / 360.0f);
         const float row_floor = floorf(rb), col_floor = floorf(cbn), ori_floor = floorf(obin);
         const float row_frac = rb - row_floor, col_frac = cbn - col_floor, ori_frac = obin - ori_floor;
+        // trilinear split exactly as src/lib.rs:906-919
         const float c1 = mag * row_frac, c0 = mag - c1;
         const float c11 = c1 * col_frac, c10 = c1 - c11;
         const float c01 = c0 * col_frac, c00 = c0 - c01;
@@ -484,34 +506,42 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
         cv[5] = c10 * ori_frac; cv[4] = c10 - cv[5];   // c101, c100
         cv[3] = c01 * ori_frac; cv[2] = c01 - cv[3];   // c011, c010
         cv[1] = c00 * ori_frac; cv[0] = c00 - cv[1];   // c001, c000
-        // reference cells are (row_floor+1 .. +2, col_floor+1 .. +2) of the 6x6 grid; inner cells are 1..4
-        const int r1 = (int)row_floor, q1 = (int)col_floor;  // inner-grid index of the first cell (-1..3)
-        float of = ori_floor;
-        if (of < 0.f) of += 8.f;
-        else if (of >= 8.f) of -= 8.f;
-        const int o0 = min(max((int)of, 0), 7);
+        // the reference adds into cells (row_floor+1 .. +2, col_floor+1 .. +2) of its 6x6 grid and keeps
+        // cells 1..4 (:951): in inner-grid terms the first cell is (r1, q1) in -1..3
+        const int r1 = (int)row_floor, q1 = (int)col_floor;
+        const int o0 = ((int)ori_floor) & 7;           // ori_floor in [-16, 16): wrap like :926-938
         const int o1 = (o0 + 1) & 7;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int rr = r1 + (k >> 2), qq = q1 + ((k >> 1) & 1);
-            const bool in = (rr >= 0) && (rr < 4) && (qq >= 0) && (qq < 4);
-            cb[k] = in ? ((rr * 4 + qq) * 8 + ((k & 1) ? o1 : o0)) : -1;
-        }
+        const bool r0ok = r1 >= 0, r1ok = r1 <= 2, q0ok = q1 >= 0, q1ok = q1 <= 2;
+        ok[0] = ok[1] = r0ok && q0ok;
+        ok[2] = ok[3] = r0ok && q1ok;
+        ok[4] = ok[5] = r1ok && q0ok;
+        ok[6] = ok[7] = r1ok && q1ok;
+        const int base = (r1 * 4 + q1) * 8;
+        b0 = (base + o0) * DESC_COPIES;
+        b1 = (base + o1) * DESC_COPIES;
     }
     float* mine = hist + (lane & (DESC_COPIES - 1));
+    // word offsets of the 8 bins: +8 bins per column step, +32 bins per row step
 #pragma unroll
     for (int phase = 0; phase < 32 / DESC_COPIES; phase++) {
-        if ((lane / DESC_COPIES) == phase) {
+        const bool on = (lane / DESC_COPIES) == phase;
+        float old[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (cb[k] >= 0) mine[cb[k] * DESC_COPIES] += cv[k];
+        for (int k = 0; k < 8; k++) {
+            const int off = ((k & 1) ? b1 : b0) + (((k >> 1) & 1) * 8 + (k >> 2) * 32) * DESC_COPIES;
+            old[k] = (on && ok[k]) ? mine[off] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int off = ((k & 1) ? b1 : b0) + (((k >> 1) & 1) * 8 + (k >> 2) * 32) * DESC_COPIES;
+            if (on && ok[k]) mine[off] = old[k] + cv[k];
         }
         __syncwarp();
     }
 }
 
 __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /* smem [DESC_SMEM_WORDS] */, int lane,
-                                                const uint64_t* s_tab, uint8_t* out /* 128 B */) {
+                                                uint8_t* out /* 128 B */) {
     float* hist = wsm;
     uint32_t* queue = reinterpret_cast<uint32_t*>(wsm + DESC_SIZE * DESC_COPIES);
     {
@@ -531,33 +561,45 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     sincos((double)rad, &sd, &cd);  // libm sinf/cosf are (nearly always) correctly rounded: round once from f64
     G.sin_s = (float)sd / hist_width;
     G.cos_s = (float)cd / hist_width;
-    const int side = 2 * G.radius + 1;
+    // conservative per-row column range of the rotated 5x5-cell square: x*k + t in (-2.5, 2.5)
+    const float inv_s = fabsf(G.sin_s) > 1e-7f ? 1.0f / G.sin_s : 0.f;
+    const float inv_c = fabsf(G.cos_s) > 1e-7f ? 1.0f / G.cos_s : 0.f;
+    const int xw_min = max(-G.radius, 1 - G.x), xw_max = min(G.radius, G.w - 2 - G.x);
     __syncwarp();
     uint32_t qhead = 0, qtail = 0;  // warp-uniform
     const uint32_t lt = (1u << lane) - 1u;
-    for (int yq = 0; yq < side; yq++) {
-        const int yw = yq - G.radius;
+    for (int yw = -G.radius; yw <= G.radius; yw++) {
         const int ay = G.y + yw;
         if (ay <= 0 || ay >= G.h - 1) continue;  // warp-uniform
         const float ys = (float)yw * G.sin_s, yc = (float)yw * G.cos_s;
-        for (int xb = 0; xb < side; xb += 32) {
-            const int xq = xb + lane;
-            const int xw = xq - G.radius;
+        float lo = (float)xw_min, hi = (float)xw_max;
+        if (inv_s != 0.f) {  // row_rot = x*sin_s + yc
+            const float a = (-2.5f - yc) * inv_s, b = (2.5f - yc) * inv_s;
+            lo = fmaxf(lo, floorf(fminf(a, b)));
+            hi = fminf(hi, ceilf(fmaxf(a, b)));
+        }
+        if (inv_c != 0.f) {  // col_rot = x*cos_s - ys
+            const float a = (-2.5f + ys) * inv_c, b = (2.5f + ys) * inv_c;
+            lo = fmaxf(lo, floorf(fminf(a, b)));
+            hi = fminf(hi, ceilf(fmaxf(a, b)));
+        }
+        const int xlo = (int)lo, xhi = (int)hi;
+        const uint32_t yq = (uint32_t)(yw + G.radius);
+        for (int xb = xlo; xb <= xhi; xb += 32) {
+            const int xw = xb + lane;
             const float col_rot = (float)xw * G.cos_s - ys;
             const float row_rot = (float)xw * G.sin_s + yc;
             const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
-            const int ax = G.x + xw;
-            const bool valid = xq < side && row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f &&
-                               ax > 0 && ax < G.w - 1;
+            const bool valid = xw <= xhi && row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f;
             const uint32_t vm = __ballot_sync(0xffffffffu, valid);
             if (vm == 0) continue;
-            if (valid) queue[(qtail + __popc(vm & lt)) & (DESC_QCAP - 1)] = ((uint32_t)yq << 8) | (uint32_t)xq;
+            if (valid) queue[(qtail + __popc(vm & lt)) & (DESC_QCAP - 1)] = (yq << 8) | (uint32_t)(xw + G.radius);
             qtail += __popc(vm);
             __syncwarp();
             if (qtail - qhead >= 32) {
                 const uint32_t e = queue[(qhead + lane) & (DESC_QCAP - 1)];
                 qhead += 32;
-                descriptor_sample(G, e, true, hist, lane, s_tab);
+                descriptor_sample(G, e, true, hist, lane);
             }
         }
     }
@@ -565,7 +607,7 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
         const uint32_t n = qtail - qhead;  // < 32
         if (n) {
             const uint32_t e = queue[(qhead + lane) & (DESC_QCAP - 1)];
-            descriptor_sample(G, e, lane < n, hist, lane, s_tab);
+            descriptor_sample(G, e, lane < n, hist, lane);
         }
     }
     __syncwarp();
@@ -696,7 +738,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams
         const float f = pow2i(-kp.octave);  // 2_f32.powi(-octave), src/lib.rs:768
         t.x = kp.x * f; t.y = kp.y * f; t.scale = kp.size * f;
         t.orientation = 360.0f - kp.angle;   // :766
-        descriptor_warp(t, s_hist[warp], lane, s_tab, P.out_desc + (obase + j) * DESC_SIZE);
+        descriptor_warp(t, s_hist[warp], lane, P.out_desc + (obase + j) * DESC_SIZE);
         if (lane == 0) {
             OutKeyPoint o;  // DELTA_MIN = 0.5 undoes the seed upsampling, src/lib.rs:168-170
             o.x = kp.x * 0.5f; o.y = kp.y * 0.5f; o.size = kp.size * 0.5f;
@@ -724,7 +766,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor_list(const float
         DescTarget t;
         t.img = img; t.w = w; t.h = h; t.pitch = pitch;
         t.x = k.x; t.y = k.y; t.scale = k.scale; t.orientation = k.orientation;
-        descriptor_warp(t, s_hist[warp], lane, s_tab, out + j * DESC_SIZE);
+        descriptor_warp(t, s_hist[warp], lane, out + j * DESC_SIZE);
     }
 }
 
