@@ -196,3 +196,22 @@ def test_opencv_cross_match(sf):
     d = np.array([np.hypot(ka["x"][x.queryIdx] - ckp[x.trainIdx].pt[0], ka["y"][x.queryIdx] - ckp[x.trainIdx].pt[1])
                   for x in m])
     assert (d < 1.0).mean() >= 0.9
+
+
+def test_multi_device_shards(sf, oracle):
+    """sb200_extract_batch_multi: contiguous shards over several contexts, host-side gather in image order
+    (SURVEY.md section 8e).  Needs >= 2 devices; with one device the same entry point runs with one context."""
+    from sift_features_b200 import _ffi
+    ndev = _ffi.load().sb200_device_count()
+    devices = list(range(min(ndev, 4)))
+    n, w, h = 9, 160, 120
+    imgs = np.stack([noise_image(w, h, 300 + i) for i in range(n)])
+    res = sf.sift_batch(imgs, devices=devices, max_batch=2)
+    assert len(res) == n
+    for i in (0, 4, 8):
+        okp, odesc = oracle.sift(imgs[i])
+        assert len(res[i]) == len(okp)
+        assert np.array_equal(_bits(res[i].keypoint_array["x"]), _bits(okp["x"]))
+        assert np.abs(res[i].descriptors.astype(int) - odesc.astype(int)).max(initial=0) <= 1
+    if ndev < 2:
+        pytest.skip("single device: multi-context gather exercised with one context only")
