@@ -301,10 +301,15 @@ struct TmaCfg {
     static constexpr int IPITCH = 132;
     static constexpr int PY = 16;
     static constexpr int THREADS = 256;
-    static constexpr uint32_t BOX_BYTES = (uint32_t)SH * BW * sizeof(float);
-    static constexpr size_t SMEM = (size_t)SH * (BW + IPITCH) * sizeof(float);
+    // the box arrives as NBAND row bands of BAND rows, each on its own mbarrier, so the row pass of the first
+    // 32 staged rows starts while the rest of the box is still in flight
+    static constexpr int BAND = 32;
+    static constexpr int NBAND = (SH + BAND - 1) / BAND;
+    static constexpr int SHP = NBAND * BAND;       // staged rows incl. padding of the last band
+    static constexpr uint32_t BAND_BYTES = (uint32_t)BAND * BW * sizeof(float);
+    static constexpr size_t SMEM = ((size_t)SHP * BW + (size_t)SH * IPITCH) * sizeof(float);
     static_assert(BW >= XO + SW && (BW / 4) % 2 == 1 && 120 + 4 * NV4 <= BW, "box width");
-    static_assert(BOX_BYTES % 16 == 0 && BW <= 256 && SH <= 256, "TMA box limits");
+    static_assert(BAND_BYTES % 128 == 0 && BW <= 256, "TMA box limits / 128-byte aligned band destinations");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -315,40 +320,50 @@ __global__ void __launch_bounds__(256, 2) k_blur_tma(const __grid_constant__ CUt
     using C = TmaCfg<L>;
     constexpr int R = C::R;
     extern __shared__ __align__(1024) float smem_tma[];  // own symbol: `smem` above is declared 16-byte aligned
-    __shared__ __align__(8) uint64_t bar;
-    float* stage = smem_tma;                     // SH x BW, dense (TMA box layout)
-    float* inter = smem_tma + C::SH * C::BW;     // SH x IPITCH
+    __shared__ __align__(8) uint64_t bar[C::NBAND];
+    float* stage = smem_tma;                     // SHP x BW, dense (TMA box layout)
+    float* inter = smem_tma + C::SHP * C::BW;    // SH x IPITCH
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * C::TW, ty0 = blockIdx.y * C::TH;
     const int img = blockIdx.z;
     const int w = p.w, h = p.h;
     const int rows_needed = min(C::TH, h - ty0) + 2 * R;
     const int cols_needed = min(C::TW, w - tx0) + 2 * R;
-    const uint32_t bar_a = smem_u32(&bar);
-
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+#pragma unroll
+        for (int b = 0; b < C::NBAND; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[b])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(C::BOX_BYTES) : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-            ::"r"(smem_u32(stage)), "l"(&tmap), "r"(tx0 - C::RA), "r"(ty0 - R), "r"(src_layer), "r"(img), "r"(bar_a)
-            : "memory");
+#pragma unroll
+        for (int b = 0; b < C::NBAND; b++) {
+            const uint32_t bar_a = smem_u32(&bar[b]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(C::BAND_BYTES) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                ::"r"(smem_u32(stage + b * C::BAND * C::BW)), "l"(&tmap), "r"(tx0 - C::RA), "r"(ty0 - R + b * C::BAND),
+                  "r"(src_layer), "r"(img), "r"(bar_a)
+                : "memory");
+        }
     }
-    {
+    const bool border_tile = tx0 - R < 0 || ty0 - R < 0 || tx0 + C::TW + R > w || ty0 + C::TH + R > h;
+    auto wait_band = [&](int b) {
         uint32_t done = 0;
+        const uint32_t bar_a = smem_u32(&bar[b]);
         while (!done) {
             asm volatile(
                 "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                 : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
         }
+    };
+    if (border_tile) {  // the halo patch below reads across bands: wait for the whole box
+#pragma unroll
+        for (int b = 0; b < C::NBAND; b++) wait_band(b);
     }
     // BORDER_REFLECT_101 for tiles that stick out of the image (block-uniform branch).
     // Box element (row, XO + col) holds image pixel (ty0 - R + row, tx0 - R + col).
-    if (tx0 - R < 0 || ty0 - R < 0 || tx0 + C::TW + R > w || ty0 + C::TH + R > h) {
+    if (border_tile) {
         for (int idx = tid; idx < C::SH * C::SW; idx += C::THREADS) {
             const int row = idx / C::SW, col = idx - row * C::SW;
             if (row < rows_needed && col < cols_needed) {
@@ -370,6 +385,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_tma(const __grid_constant__ CUt
         for (int task = warp; task < NGROUPS * NSEG; task += C::THREADS / 32) {
             const int g = task / NSEG, seg = task - g * NSEG;
             const int row = g * 32 + lane;
+            if (!border_tile) wait_band(g);   // warp-uniform; a no-op once the band has landed
             if (row < rows_needed && row < C::SH) {
                 float win[4 * C::NV4];
                 const float4* sp = reinterpret_cast<const float4*>(stage + row * C::BW + seg * 8);

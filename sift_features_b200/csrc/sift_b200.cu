@@ -348,7 +348,7 @@ int encode_one(sb200_ctx* ctx, int slot, int o) {
     const cuuint64_t gdim[4] = {(cuuint64_t)ol.w, (cuuint64_t)ol.h, (cuuint64_t)N_LAYERS, (cuuint64_t)ctx->max_batch};
     const cuuint64_t gstr[3] = {(cuuint64_t)ol.pitch * 4, (cuuint64_t)ol.layer_stride * 4,
                                 (cuuint64_t)ctx->L.img_floats * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)C::BW, (cuuint32_t)C::SH, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)C::BW, (cuuint32_t)C::BAND, 1, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = ((EncodeTiledFn)ctx->encode_fn)(&ctx->tmap[slot][o][LI], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                                                  ctx->slot[slot].d_gauss + ol.off, gdim, gstr, box, estr,
