@@ -116,7 +116,8 @@ int sb200_extract_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n
                                int64_t features_limit);
 /* device-side view of the last sb200_extract_batch_device: per-image keypoint
  * counts are copied to `counts` (n entries, host); d_keypoints / d_descriptors
- * receive the device base pointers, image i's rows start at i*capacity. */
+ * receive the device base pointers of the dense, batch-wide result arrays (image
+ * i's keypoints start at the exclusive prefix sum of the counts). */
 int sb200_device_result(sb200_ctx* ctx, uint32_t* counts, uint32_t n, const sb200_keypoint** d_keypoints,
                         const uint8_t** d_descriptors, uint32_t* capacity_per_image);
 int sb200_sync(sb200_ctx* ctx);
@@ -163,7 +164,8 @@ int sb200_extract_batch_multi(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint
 #define SB200_STAGE_REFINE 3      /* refinement, contrast, edge              (:525-653) */
 #define SB200_STAGE_ORIENT 4      /* orientation histogram + peaks           (:657-757, 389-431) */
 #define SB200_STAGE_DESCRIPTOR 5  /* descriptors + output pack               (:759-990, 164-174) */
-#define SB200_STAGE_COUNT 6
+#define SB200_STAGE_TOP_BLUR 6    /* the single heaviest launch: 27-tap blur of octave 0 (also counted in BLUR) */
+#define SB200_STAGE_COUNT 7
 /* With profiling on, every stage of the next extract calls is bracketed by
  * CUDA events on the launching stream(s) (this serialises the stages). */
 int sb200_set_profiling(sb200_ctx* ctx, int on);

@@ -44,7 +44,7 @@ SIFT_KEYPOINT_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angl
                                 ("octave", "i4"), ("scale", "i4")])
 CANDIDATE_DTYPE = np.dtype([("octave", "i4"), ("scale", "i4"), ("y", "i4"), ("x", "i4")])
 DESC_IN_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("scale", "f4"), ("orientation", "f4")])
-STAGE_NAMES = ("seed", "blur", "extrema", "refine", "orient", "descriptor")
+STAGE_NAMES = ("seed", "blur", "extrema", "refine", "orient", "descriptor", "top_blur")
 
 
 class SiftError(RuntimeError):

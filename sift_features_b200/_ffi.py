@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsift_b200.so")
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_STATE = 0, 1, 2, 3, 4
 DESC_SIZE = 128
-STAGE_COUNT = 6
+STAGE_COUNT = 7
 
 # every symbol include/sift_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [

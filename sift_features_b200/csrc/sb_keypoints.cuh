@@ -27,6 +27,27 @@ struct KpParams {
 
 __device__ __forceinline__ float pow2i(int e) { return __int_as_float((127 + e) << 23); }
 
+// atan2(y, x) in (-pi, pi]: minimax polynomial of atan on [0,1] (|error| < 3.3e-7 rad) plus octant folding.
+// Used where the result only selects a bin (with an exact f64 re-evaluation near bin boundaries) or feeds a
+// continuous interpolation weight.
+__device__ __forceinline__ float fast_atan2_rad(const float y, const float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+    const float s = a * a;
+    float p = 0x1.be6ae0p-8f;
+    p = fmaf(p, s, -0x1.134924p-5f);
+    p = fmaf(p, s, 0x1.462378p-4f);
+    p = fmaf(p, s, -0x1.0f04d4p-3f);
+    p = fmaf(p, s, 0x1.95aa00p-3f);
+    p = fmaf(p, s, -0x1.552b7cp-2f);
+    p = fmaf(p, s, 0x1.ffff7ep-1f);
+    float r = p * a;                                   // [0, pi/4]
+    if (ay > ax) r = 1.57079632679489661923f - r;      // [0, pi/2]
+    if (x < 0.f) r = 3.14159265358979323846f - r;      // [0, pi]
+    return (y < 0.f) ? -r : r;
+}
+
 // DoG value (src/lib.rs:275): layer l of the octave whose Gaussian layer 0 is `g`
 struct DogView {
     const float* g;
@@ -198,7 +219,7 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P) {
                     // bin = round(36/(2pi) * (atan2_f64(dy,dx) as f32)), src/lib.rs:715-726.
                     // f32 atan2 decides unless the scaled angle is close to a rounding
                     // boundary; then the f64 evaluation the reference uses decides.
-                    float raw = bin_angle_step * atan2f(dy, dx);
+                    float raw = bin_angle_step * fast_atan2_rad(dy, dx);   // |error| < 4e-7 rad => < 3e-6 bins
                     if (fabsf(fabsf(raw - truncf(raw)) - 0.5f) < 1e-3f)
                         raw = bin_angle_step * (float)atan2((double)dy, (double)dx);
                     bin = (int)roundf(raw);
@@ -481,12 +502,14 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     int b0 = 0, b1 = 0;  // word offsets of the (first cell, o0) and (first cell, o1) bins
 #pragma unroll
     for (int k = 0; k < 8; k++) { cv[k] = 0.f; ok[k] = false; }
-    if (active) {
-        // geometry: the reference's f32 operations, so cell indices and fractions are its values
-        const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
-        const float col_rot = (float)xw * G.cos_s - (float)yw * G.sin_s;
-        const float row_rot = (float)xw * G.sin_s + (float)yw * G.cos_s;
-        const float rb = (row_rot + 2.0f) - 0.5f, cbn = (col_rot + 2.0f) - 0.5f;
+    // geometry: the reference's f32 operations, so the membership test, cell indices and fractions are its values
+    const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
+    const float col_rot = (float)xw * G.cos_s - (float)yw * G.sin_s;
+    const float row_rot = (float)xw * G.sin_s + (float)yw * G.cos_s;
+    const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
+    // src/lib.rs:834-837 (the image-bounds half of the test, :838-841, is enforced by the span construction)
+    if (active && row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f) {
+        const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
         const float* c = G.img + (long long)(G.y + yw) * G.pitch + (G.x + xw);
         const float dx = __ldg(c + 1) - __ldg(c - 1);
         const float dy = __ldg(c - G.pitch) - __ldg(c + G.pitch);
@@ -585,16 +608,13 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
         }
         const int xlo = (int)lo, xhi = (int)hi;
         const uint32_t yq = (uint32_t)(yw + G.radius);
+        // queue the whole conservative span (at most a couple of samples per row fail the exact test, which the
+        // sample step repeats); no floating-point work and no ballots in the scan
         for (int xb = xlo; xb <= xhi; xb += 32) {
             const int xw = xb + lane;
-            const float col_rot = (float)xw * G.cos_s - ys;
-            const float row_rot = (float)xw * G.sin_s + yc;
-            const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
-            const bool valid = xw <= xhi && row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f;
-            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-            if (vm == 0) continue;
-            if (valid) queue[(qtail + __popc(vm & lt)) & (DESC_QCAP - 1)] = (yq << 8) | (uint32_t)(xw + G.radius);
-            qtail += __popc(vm);
+            const int cnt = min(32, xhi - xb + 1);
+            if (lane < cnt) queue[(qtail + lane) & (DESC_QCAP - 1)] = (yq << 8) | (uint32_t)(xw + G.radius);
+            qtail += cnt;
             __syncwarp();
             if (qtail - qhead >= 32) {
                 const uint32_t e = queue[(qhead + lane) & (DESC_QCAP - 1)];

@@ -37,7 +37,7 @@ def test_status_strings_and_stage_names(sf):
     lib = _ffi.load()
     assert lib.sb200_status_string(0) == b"ok"
     assert lib.sb200_status_string(3) == b"capacity exceeded"
-    assert [lib.sb200_stage_name(i).decode() for i in range(6)] == list(sf.STAGE_NAMES)
+    assert [lib.sb200_stage_name(i).decode() for i in range(7)] == list(sf.STAGE_NAMES)
 
 
 def test_algorithmic_bytes_match_survey_table(sf):
