@@ -284,21 +284,26 @@ __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
 // The tensor map is 4-D: (x, y, layer, image) over one octave of the slot's arena.
 // ---------------------------------------------------------------------------
 constexpr int TMA_MIN_DIM = 32;
+// output tile width per tap set (measured on B200): the narrow taps run faster with 64-column tiles
+// (3 CTAs per SM), the 21- and 27-tap kernels with 128-column tiles (less horizontal halo per output)
+__host__ __device__ constexpr int blur_tile_w(int l) { return l <= 3 ? 64 : 128; }
 
 template <int L>
 struct TmaCfg {
     static constexpr int R = blur_radius(L);
     static constexpr int RA = (R + 3) / 4 * 4;   // left halo of the box: the box's first column must be 16-byte aligned
     static constexpr int XO = RA - R;            // box column of the first element the filter needs
-    static constexpr int TW = 128, TH = 64;
+    static constexpr int TW = blur_tile_w(L), TH = 64;
     static constexpr int SH = TH + 2 * R;
     static constexpr int SW = TW + 2 * R;
     static constexpr int WIN = XO + 8 + 2 * R;   // box floats read for 8 consecutive row-pass outputs (aligned start)
     static constexpr int NV4 = (WIN + 3) / 4;
     // box width: multiple of 4 floats (16 B) with BW/4 odd, so that 8 consecutive rows start in 8
     // distinct 4-bank groups (conflict-free LDS.128 with lanes <-> rows)
-    static constexpr int BW = (R <= 8) ? 148 : (R == 10) ? 156 : 164;
-    static constexpr int IPITCH = 132;
+    static constexpr int BW_MIN = (XO + SW > TW - 8 + 4 * NV4) ? XO + SW : TW - 8 + 4 * NV4;
+    static constexpr int BW4 = (BW_MIN + 3) / 4;
+    static constexpr int BW = 4 * ((BW4 % 2) ? BW4 : BW4 + 1);
+    static constexpr int IPITCH = TW + 4;        // == 4 (mod 32) for TW = 64, 128
     static constexpr int PY = 16;
     static constexpr int THREADS = 256;
     // the box arrives as NBAND row bands of BAND rows, each on its own mbarrier, so the row pass of the first
@@ -308,14 +313,16 @@ struct TmaCfg {
     static constexpr int SHP = NBAND * BAND;       // staged rows incl. padding of the last band
     static constexpr uint32_t BAND_BYTES = (uint32_t)BAND * BW * sizeof(float);
     static constexpr size_t SMEM = ((size_t)SHP * BW + (size_t)SH * IPITCH) * sizeof(float);
-    static_assert(BW >= XO + SW && (BW / 4) % 2 == 1 && 120 + 4 * NV4 <= BW, "box width");
+    static constexpr int CTAS_PER_SM = (TW == 64) ? 3 : 2;
+    static_assert(BW >= XO + SW && (BW / 4) % 2 == 1 && TW - 8 + 4 * NV4 <= BW, "box width");
     static_assert(BAND_BYTES % 128 == 0 && BW <= 256, "TMA box limits / 128-byte aligned band destinations");
+    static_assert(IPITCH % 32 == 4, "inter pitch");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int L, bool DECIMATE>
-__global__ void __launch_bounds__(256, 2) k_blur_tma(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
+__global__ void __launch_bounds__(256, TmaCfg<L>::CTAS_PER_SM) k_blur_tma(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
                                                       const int src_layer) {
     using C = TmaCfg<L>;
     constexpr int R = C::R;
