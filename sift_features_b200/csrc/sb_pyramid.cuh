@@ -20,6 +20,34 @@ namespace sb {
 
 // taps of the six Gaussian kernels, [kernel][0..2R]; filled by the host at context creation
 __constant__ float c_taps[N_LAYERS][32];
+// the same taps duplicated into both halves of a 64-bit operand for the packed f32x2 arithmetic
+__constant__ float2 c_taps2[N_LAYERS][32];
+
+// Blackwell packed single precision (SASS FFMA2 / FADD2 / FMUL2): two independent IEEE round-to-nearest
+// operations per instruction, i.e. the same bits as the scalar fmaf / + / * -- but half the issue slots,
+// which is what bounds the wide-tap blurs.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return d;
+}
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -304,7 +332,7 @@ struct TmaCfg {
     static constexpr int BW4 = (BW_MIN + 3) / 4;
     static constexpr int BW = 4 * ((BW4 % 2) ? BW4 : BW4 + 1);
     static constexpr int IPITCH = TW + 4;        // == 4 (mod 32) for TW = 64, 128
-    static constexpr int PY = 16;
+    static constexpr int PY = 8;                 // rows per column-pass thread (which owns two adjacent columns)
     static constexpr int THREADS = 256;
     // the box arrives as NBAND row bands of BAND rows, each on its own mbarrier, so the row pass of the first
     // 32 staged rows starts while the rest of the box is still in flight
@@ -401,46 +429,58 @@ __global__ void __launch_bounds__(256, TmaCfg<L>::CTAS_PER_SM) k_blur_tma(const 
                     float4 q = sp[v];
                     win[4 * v + 0] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
                 }
-                float out[8];
+                // packed arithmetic: outputs (2jp, 2jp+1) share one FFMA2 chain; the operand pair for tap i starts
+                // at window index XO + 2jp + i, which is an aligned register pair of `win` when even and comes
+                // from the one-float-shifted copy `sh` when odd
+                float2 sh[2 * C::NV4];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    float acc = win[C::XO + j] * c_taps[L][0];
+                for (int m = 0; 2 * m + 2 < 4 * C::NV4; m++) sh[m] = make_float2(win[2 * m + 1], win[2 * m + 2]);
+                float2 acc[4];
 #pragma unroll
-                    for (int i = 1; i <= 2 * R; i++) acc = fmaf(win[C::XO + j + i], c_taps[L][i], acc);
-                    out[j] = acc;
+                for (int jp = 0; jp < 4; jp++) {
+#pragma unroll
+                    for (int i = 0; i <= 2 * R; i++) {
+                        const int sidx = C::XO + 2 * jp + i;
+                        const float2 in = (sidx & 1) ? sh[sidx >> 1] : make_float2(win[sidx], win[sidx + 1]);
+                        acc[jp] = (i == 0) ? mul2(in, c_taps2[L][0]) : fma2(in, c_taps2[L][i], acc[jp]);
+                    }
                 }
                 float4* ip = reinterpret_cast<float4*>(inter + row * C::IPITCH + seg * 8);
-                ip[0] = make_float4(out[0], out[1], out[2], out[3]);
-                ip[1] = make_float4(out[4], out[5], out[6], out[7]);
+                ip[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+                ip[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
             }
         }
     }
     __syncthreads();
 
-    // ---- column pass: thread = one column x PY consecutive rows ----
+    // ---- column pass: thread = two adjacent columns x PY consecutive rows, packed f32x2 ----
     {
         float* dst = p.dst + (long long)img * p.img_stride;
         float* dec = DECIMATE ? p.dec + (long long)img * p.img_stride : nullptr;
         constexpr int NCH = C::TH / C::PY;
-        for (int task = tid; task < C::TW * NCH; task += C::THREADS) {
-            const int cy = task / C::TW, x = task - cy * C::TW;
+        constexpr int NXP = C::TW / 2;
+        for (int task = tid; task < NXP * NCH; task += C::THREADS) {
+            const int cy = task / NXP, xp = task - cy * NXP;
             const int y0 = cy * C::PY;
-            const int gx = tx0 + x;
-            if (ty0 + y0 >= h) continue;
-            float c[C::PY + 2 * R];
+            const int gx = tx0 + 2 * xp;
+            if (ty0 + y0 >= h) continue;  // whole chunk below the image (warp-uniform)
+            float2 c[C::PY + 2 * R];
 #pragma unroll
-            for (int j = 0; j < C::PY + 2 * R; j++) c[j] = inter[(y0 + j) * C::IPITCH + x];
+            for (int j = 0; j < C::PY + 2 * R; j++)
+                c[j] = *reinterpret_cast<const float2*>(inter + (y0 + j) * C::IPITCH + 2 * xp);
 #pragma unroll
             for (int j = 0; j < C::PY; j++) {
-                float acc = c[j + R] * c_taps[L][R];
+                float2 acc = mul2(c[j + R], c_taps2[L][R]);
 #pragma unroll
-                for (int i = 1; i <= R; i++) acc = fmaf(c[j + R + i] + c[j + R - i], c_taps[L][R + i], acc);
+                for (int i = 1; i <= R; i++) acc = fma2(add2(c[j + R + i], c[j + R - i]), c_taps2[L][R + i], acc);
                 const int gy = ty0 + y0 + j;
                 if (gy < h && gx < w) {
-                    dst[(long long)gy * p.pitch + gx] = acc;
-                    if (DECIMATE && !(gy & 1) && !(gx & 1)) {
+                    float* q = dst + (long long)gy * p.pitch + gx;
+                    if (gx + 1 < w) *reinterpret_cast<float2*>(q) = acc;
+                    else q[0] = acc.x;
+                    if (DECIMATE && !(gy & 1)) {   // gx is even
                         const int dy = gy >> 1, dx = gx >> 1;
-                        if (dy < p.dec_h && dx < p.dec_w) dec[(long long)dy * p.dec_pitch + dx] = acc;
+                        if (dy < p.dec_h && dx < p.dec_w) dec[(long long)dy * p.dec_pitch + dx] = acc.x;
                     }
                 }
             }

@@ -756,6 +756,12 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
                 return fail(ctx, SB200_E_INVALID, "internal: tap count %d of kernel %d", ks, l);
         }
         CU(cudaMemcpyToSymbol(c_taps, taps, sizeof taps));
+        {
+            float2 taps2[N_LAYERS][32];
+            for (int l = 0; l < N_LAYERS; l++)
+                for (int i = 0; i < 32; i++) taps2[l][i] = make_float2(taps[l][i], taps[l][i]);
+            CU(cudaMemcpyToSymbol(c_taps2, taps2, sizeof taps2));
+        }
         int r;
         if ((r = set_blur_attr<0, true, false>(ctx))) return r;
         if ((r = set_blur_attr<1, false, false>(ctx))) return r;
