@@ -24,7 +24,8 @@ constexpr int MAX_TAPS = 27;
 
 // One octave of one image inside the per-image arenas.
 //   Gaussian layer l:  gauss + off + l*layer_stride, row pitch `pitch` floats (multiple of 32)
-//   extrema mask:      mask + mask_off + ((s-1)*h + y)*mask_pitch words, bit x%32 of word x/32
+//   extrema mask:      mask + mask_off + ((s-1)*h + y)*mask_pitch words; strip j (60 columns) owns words
+//                      2j, 2j+1: bit l of word 2j+k <=> column 60j - 2 + 2l + k (sb_pyramid.cuh, k_extrema)
 //   row counters:      rows + row_base + (s-1)*h + y
 struct OctLayout {
     int w, h, pitch, mask_pitch;

@@ -491,15 +491,20 @@ __global__ void __launch_bounds__(256, TmaCfg<L>::CTAS_PER_SM) k_blur_tma(const 
 // ---------------------------------------------------------------------------
 // DoG + 3x3x3 extrema (build_dog + point_is_local_extremum, src/lib.rs:271-279,
 // 437-506) for the three scales of one octave in one pass over its six Gaussian
-// layers.  A warp owns 32 consecutive columns (one mask word) and walks down
-// EX_ROWS rows keeping, per DoG layer, the horizontal 3-max / 3-min of the two
-// previous rows in registers.  Output: one ballot word per (scale, row, 32
-// columns) -- a raster-ordered bit mask, so candidate order is deterministic --
-// plus a per-row population count.
+// layers.  A warp owns a strip of EX_SPAN = 60 output columns: lane l holds the
+// column pair 60*strip - 2 + 2l, +1 (one 8-byte load per layer and row), so the
+// lanes 1..30 find both horizontal neighbours of their columns in the adjacent
+// lanes (two shuffles per DoG layer, no edge cases) and lanes 0 / 31 only carry
+// the halo.  The warp walks down EX_ROWS rows keeping, per DoG layer, the
+// horizontal 3-max / 3-min of the two previous rows in registers.
+// Output per (scale, row, strip): two ballot words {B0, B1}, bit l of Bk <=> column
+// 60*strip - 2 + 2l + k -- a raster-ordered bit mask, so candidate order is
+// deterministic -- plus a per-row population count.
 // ---------------------------------------------------------------------------
-constexpr int EX_ROWS = 16;
+constexpr int EX_ROWS = 32;
 constexpr int EX_WARPS = 4;
-constexpr int EX_COLS = 32;  // columns per warp == one mask word
+constexpr int EX_SPAN = 60;  // output columns per warp
+__host__ __device__ constexpr int ex_strips(int w) { return (w + EX_SPAN - 1) / EX_SPAN; }
 
 struct ExtremaParams {
     const float* gauss;       // octave base (layer 0), image 0
@@ -508,7 +513,7 @@ struct ExtremaParams {
     int w, h, pitch;
     uint32_t* mask;           // octave mask base, image 0
     long long mask_img_stride;
-    int mask_pitch;
+    int mask_pitch;           // words per (scale, row): 2 * ex_strips(w)
     uint32_t* rows;           // octave row counters, image 0
     int rows_img_stride;
 };
@@ -524,71 +529,71 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-// rolling three-row state of one warp: per DoG layer the horizontal 3-max / 3-min of rows
-// (c-1, c, c+1) and the centre-column DoG values, one column per lane
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {   // FADD2 with a negated operand: a - b, both halves
+    float2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return d;
+}
+// rolling three-row state of one warp: the DoG values of rows (c-1, c, c+1) for the lane's two columns
 struct ExState {
-    float hx[3][N_DOG], hn[3][N_DOG], v[3][N_DOG];
+    float2 d[3][N_DOG];
 };
 
 struct ExWarp {
-    const float* g;       // layer 0, row 0, this lane's (clamped) column
-    uint32_t* mask;
-    uint32_t* rows;
-    long long layer_stride;
-    int h, pitch, mask_pitch, strip, lane, y0;
-    bool x_ok;
+    const float* g;            // layer 0, row 0 at this lane's (clamped) column pair
+    uint32_t* mask;            // lanes 0..2: word pair of (scale lane+1, row 0) of this strip
+    uint32_t* rows;            // lanes 0..2: row counter of (scale lane+1, row 0)
+    int ls;                    // layer stride in floats
+    int h, pitch, mask_pitch, lane;
+    uint32_t ok;               // bit k: the lane's column k can hold candidates (IMAGE_BORDER, halo lanes excluded)
 };
 
-// Row r of the six Gaussian layers at columns x-1, x, x+1 (the shifted loads hit the L1 lines the
-// centre load just brought in): no shuffles, no edge lanes, three immediate offsets per layer pointer.
-__device__ __forceinline__ void ex_load(const ExWarp& W, const int r, float (*gv)[3]) {
-    const int rc = min(max(r, 0), W.h - 1);
-    const float* row = W.g + (long long)rc * W.pitch;
-#pragma unroll
-    for (int l = 0; l < N_LAYERS; l++) {
-        const float* q = row + l * W.layer_stride;
-        gv[l][0] = __ldg(q - 1);
-        gv[l][1] = __ldg(q);
-        gv[l][2] = __ldg(q + 1);
-    }
+__device__ __forceinline__ const float2* ex_addr(const float* base, const int off) {
+    const float2* q;   // base + 4 * off as one IMAD.WIDE
+    asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(q) : "r"(off), "l"(base));
+    return q;
 }
 
-// Processes image row r (already in gv) into slot K (K = (r - (y0-1)) mod 3, a compile-time constant
-// thanks to the 3x unrolled caller, so the state never moves between registers), issues the loads of
-// row r+1 as soon as gv is consumed, and once three rows are in evaluates the centre row r-1.
+__device__ __forceinline__ void ex_load(const ExWarp& W, const int r, float2* gv) {
+    const int roff = min(max(r, 0), W.h - 1) * W.pitch;
+#pragma unroll
+    for (int l = 0; l < N_LAYERS; l++) gv[l] = __ldg(ex_addr(W.g, roff + l * W.ls));
+}
+
+// (v > 0 and v >= Mx) or (v < 0 and v <= mn), gated by `ok`, without short-circuit branches
+__device__ __forceinline__ bool ex_is_extremum(const bool ok, const float v, const float Mx, const float mn) {
+    return (ok & (v > 0.0f) & (v >= Mx)) | (ok & (v < 0.0f) & (v <= mn));
+}
+
+// Evaluates the centre row c = r-1 once rows r-2, r-1, r sit in slots A, B, K of the state (K a compile-time
+// constant thanks to the 3x unrolled callers, so the state never moves between registers): vertical
+// 3-max / 3-min per DoG layer, then across the three layers of each scale, then across the three columns
+// (neighbour lanes by shuffle) -- 44 three-input min/max and 12 shuffles per column pair.
 template <int K, bool KEEP_FLAT>
-__device__ __forceinline__ void ex_step(const ExWarp& W, ExState& S, const int r, const int r_last, float (*gv)[3]) {
-    constexpr int A = (K + 1) % 3, B = (K + 2) % 3;  // rows r-2 and r-1
+__device__ __forceinline__ void ex_eval(const ExWarp& W, const ExState& S, const int c) {
+    constexpr int A = (K + 1) % 3, B = (K + 2) % 3;  // rows c-1 and c
+    float2 VM[N_DOG], Vm[N_DOG];   // column-wise max / min over the three rows
 #pragma unroll
     for (int l = 0; l < N_DOG; l++) {
-        const float dl = gv[l + 1][0] - gv[l][0];
-        const float dc = gv[l + 1][1] - gv[l][1];
-        const float dr = gv[l + 1][2] - gv[l][2];
-        S.v[K][l] = dc;
-        S.hx[K][l] = fmax3(dl, dc, dr);
-        S.hn[K][l] = fmin3(dl, dc, dr);
+        VM[l] = make_float2(fmax3(S.d[A][l].x, S.d[B][l].x, S.d[K][l].x), fmax3(S.d[A][l].y, S.d[B][l].y, S.d[K][l].y));
+        Vm[l] = make_float2(fmin3(S.d[A][l].x, S.d[B][l].x, S.d[K][l].x), fmin3(S.d[A][l].y, S.d[B][l].y, S.d[K][l].y));
     }
-    if (r < r_last) ex_load(W, r + 1, gv);  // in flight while this row is evaluated
-    if (r < W.y0 + 1) return;               // warp-uniform: fewer than three rows so far
-    const int c = r - 1;
-    float M[N_DOG], m[N_DOG];
-#pragma unroll
-    for (int l = 0; l < N_DOG; l++) {
-        M[l] = fmax3(S.hx[A][l], S.hx[B][l], S.hx[K][l]);
-        m[l] = fmin3(S.hn[A][l], S.hn[B][l], S.hn[K][l]);
-    }
-    const bool ok = W.x_ok && (c >= IMAGE_BORDER) && (c < W.h - IMAGE_BORDER);
-    bool flat[N_DOG];
-#pragma unroll
-    for (int l = 0; l < N_DOG; l++) flat[l] = (M[l] == m[l]);
-    uint32_t mine = 0;  // lane s-1 keeps the ballot of scale s
+    const bool row_ok = (c >= IMAGE_BORDER) & (c < W.h - IMAGE_BORDER);  // warp-uniform
+    const bool ok0 = row_ok & ((W.ok & 1u) != 0), ok1 = row_ok & ((W.ok & 2u) != 0);
+    uint32_t mine0 = 0, mine1 = 0;  // lane s-1 keeps the ballots of scale s
 #pragma unroll
     for (int s = 1; s <= SCALES_PER_OCTAVE; s++) {
-        const float v = S.v[B][s];
-        // the 27-neighbourhood max / min include v itself
-        const float Mx = fmax3(M[s - 1], M[s], M[s + 1]);
-        const float mn = fmin3(m[s - 1], m[s], m[s + 1]);
-        bool ext = ok && ((v > 0.0f && v >= Mx) || (v < 0.0f && v <= mn));
+        const float2 v = S.d[B][s];
+        // max / min over rows and layers, per column; then over the three columns (v itself included)
+        const float2 XM = make_float2(fmax3(VM[s - 1].x, VM[s].x, VM[s + 1].x), fmax3(VM[s - 1].y, VM[s].y, VM[s + 1].y));
+        const float2 Xm = make_float2(fmin3(Vm[s - 1].x, Vm[s].x, Vm[s + 1].x), fmin3(Vm[s - 1].y, Vm[s].y, Vm[s + 1].y));
+        const float lM = __shfl_up_sync(0xffffffffu, XM.y, 1), rM = __shfl_down_sync(0xffffffffu, XM.x, 1);
+        const float lm = __shfl_up_sync(0xffffffffu, Xm.y, 1), rm = __shfl_down_sync(0xffffffffu, Xm.x, 1);
+        const bool e0 = ex_is_extremum(ok0, v.x, fmax3(lM, XM.x, XM.y), fmin3(lm, Xm.x, Xm.y));
+        const bool e1 = ex_is_extremum(ok1, v.y, fmax3(XM.x, XM.y, rM), fmin3(Xm.x, Xm.y, rm));
+        uint32_t b0 = __ballot_sync(0xffffffffu, e0), b1 = __ballot_sync(0xffffffffu, e1);
         // A candidate whose three DoG layers are each spatially constant over its 3x3 window has zero
         // spatial derivatives (h12 = h13 = h22 = h33 = h23 = 0, g2 = g3 = 0), so interpolate_extremum
         // computes det = 0, every cofactor quotient is 0/0 = NaN, the NaN offsets never pass `abs() < 0.5`,
@@ -596,42 +601,164 @@ __device__ __forceinline__ void ex_step(const ExWarp& W, ExState& S, const int r
         // None (src/lib.rs:545-602).  Such points can never become keypoints, and saturated / constant
         // image regions produce them for every pixel, so the pipeline drops them here.  KEEP_FLAT = true
         // reproduces the reference's full candidate list for the parity view (sb200_last_candidates).
-        if (!KEEP_FLAT) ext = ext && !(flat[s - 1] && flat[s] && flat[s + 1]);
-        const uint32_t bits = __ballot_sync(0xffffffffu, ext);
-        if (W.lane == s - 1) mine = bits;
+        if (!KEEP_FLAT && (b0 | b1)) {  // warp-uniform and rare: most rows of a strip hold no extremum
+            bool f0 = true, f1 = true;
+#pragma unroll
+            for (int l = s - 1; l <= s + 1; l++) {
+                // column k of the lane is vertically constant in layer l
+                const bool c0 = VM[l].x == Vm[l].x, c1 = VM[l].y == Vm[l].y;
+                const float lv = __shfl_up_sync(0xffffffffu, VM[l].y, 1), rv = __shfl_down_sync(0xffffffffu, VM[l].x, 1);
+                const bool lc = __shfl_up_sync(0xffffffffu, (int)c1, 1) != 0, rc = __shfl_down_sync(0xffffffffu, (int)c0, 1) != 0;
+                const bool mid = c0 & c1 & (VM[l].x == VM[l].y);
+                f0 &= mid & lc & (lv == VM[l].x);
+                f1 &= mid & rc & (rv == VM[l].y);
+            }
+            b0 = __ballot_sync(0xffffffffu, e0 & !f0);
+            b1 = __ballot_sync(0xffffffffu, e1 & !f1);
+        }
+        if (W.lane == s - 1) { mine0 = b0; mine1 = b1; }
     }
-    if (W.lane < SCALES_PER_OCTAVE) {
-        const long long ri = (long long)W.lane * W.h + c;
-        W.mask[ri * W.mask_pitch + W.strip] = mine;
-        if (mine) atomicAdd(W.rows + ri, (uint32_t)__popc(mine));
+    if (W.lane < SCALES_PER_OCTAVE && c < W.h) {
+        *reinterpret_cast<uint2*>(W.mask + (long long)c * W.mask_pitch) = make_uint2(mine0, mine1);
+        if (mine0 | mine1) atomicAdd(W.rows + c, (uint32_t)(__popc(mine0) + __popc(mine1)));
     }
 }
 
-template <bool KEEP_FLAT>
-__global__ void __launch_bounds__(32 * EX_WARPS) k_extrema(const ExtremaParams p) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long img = blockIdx.z;
-    ExWarp W;
-    W.strip = blockIdx.x;
-    W.y0 = (blockIdx.y * EX_WARPS + warp) * EX_ROWS;
+// Generic-load variant (octaves too small for a tensor map): processes image row r (already in gv) into
+// slot K, issues the loads of row r+1 as soon as gv is consumed, and (EVAL) evaluates the centre row r-1.
+template <int K, bool EVAL, bool KEEP_FLAT>
+__device__ __forceinline__ void ex_step(const ExWarp& W, ExState& S, const int r, float2* gv) {
+#pragma unroll
+    for (int l = 0; l < N_DOG; l++) S.d[K][l] = sub2(gv[l + 1], gv[l]);
+    ex_load(W, r + 1, gv);  // in flight while this row is evaluated (row index clamped: harmless past the end)
+    if (EVAL) ex_eval<K, KEEP_FLAT>(W, S, r - 1);
+}
+
+__device__ __forceinline__ void ex_setup(ExWarp& W, const ExtremaParams& p, const int strip, const int lane, const long long img) {
     W.h = p.h; W.pitch = p.pitch; W.mask_pitch = p.mask_pitch; W.lane = lane;
-    W.layer_stride = p.layer_stride;
-    if (W.y0 >= W.h) return;
-    const int x = W.strip * 32 + lane;
-    // columns outside [1, pitch-2] load a clamped column instead: they can never be candidates
-    // (x < 5 or x >= w - 5) and, since every lane loads its own neighbours, nobody reads their values
-    W.g = p.gauss + img * p.img_stride + min(max(x, 1), p.pitch - 2);
-    W.mask = p.mask + img * p.mask_img_stride;
-    W.rows = p.rows + img * p.rows_img_stride;
-    W.x_ok = (x >= IMAGE_BORDER) && (x < p.w - IMAGE_BORDER);
+    W.ls = (int)p.layer_stride;
+    const int x0 = strip * EX_SPAN - 2 + 2 * lane;
+    // column pairs outside [0, pitch-2] load a clamped pair instead: only halo lanes and columns inside the
+    // IMAGE_BORDER margin can be affected, and neither they nor their neighbours can be candidates
+    W.g = p.gauss + img * p.img_stride + min(max(x0, 0), p.pitch - 2);
+    const int sl = min(lane, SCALES_PER_OCTAVE - 1);  // lanes 0..2 write the words of scales 1..3
+    W.mask = p.mask + img * p.mask_img_stride + (long long)sl * W.h * W.mask_pitch + 2 * strip;
+    W.rows = p.rows + img * p.rows_img_stride + sl * W.h;
+    const bool inner = (lane >= 1) & (lane <= 30);
+    W.ok = (inner & (x0 >= IMAGE_BORDER) & (x0 < p.w - IMAGE_BORDER) ? 1u : 0u) |
+           (inner & (x0 + 1 >= IMAGE_BORDER) & (x0 + 1 < p.w - IMAGE_BORDER) ? 2u : 0u);
+}
+
+template <bool KEEP_FLAT>
+__global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema(const ExtremaParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y0 = (blockIdx.y * EX_WARPS + warp) * EX_ROWS;
+    if (y0 >= p.h) return;
+    ExWarp W;
+    ex_setup(W, p, blockIdx.x, lane, blockIdx.z);
     ExState S;
-    const int r_end = min(W.y0 + EX_ROWS, W.h);  // centre rows [y0, r_end): image rows y0-1 .. r_end
-    float gv[N_LAYERS][3];
-    ex_load(W, W.y0 - 1, gv);
-    for (int r = W.y0 - 1; r <= r_end; r += 3) {
-        ex_step<0, KEEP_FLAT>(W, S, r, r_end, gv);
-        if (r + 1 <= r_end) ex_step<1, KEEP_FLAT>(W, S, r + 1, r_end, gv);
-        if (r + 2 <= r_end) ex_step<2, KEEP_FLAT>(W, S, r + 2, r_end, gv);
+    const int r_end = min(y0 + EX_ROWS, W.h);  // centre rows [y0, r_end): image rows y0-1 .. r_end
+    float2 gv[N_LAYERS];
+    ex_load(W, y0 - 1, gv);
+    ex_step<0, false, KEEP_FLAT>(W, S, y0 - 1, gv);
+    ex_step<1, false, KEEP_FLAT>(W, S, y0, gv);
+    for (int r = y0 + 1; r <= r_end; r += 3) {
+        ex_step<2, true, KEEP_FLAT>(W, S, r, gv);
+        if (r + 1 <= r_end) ex_step<0, true, KEEP_FLAT>(W, S, r + 1, gv);
+        if (r + 2 <= r_end) ex_step<1, true, KEEP_FLAT>(W, S, r + 2, gv);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA-fed variant for octaves that own a tensor map (>= TMA_MIN_DIM per side).  Every warp is its
+// own pipeline: an elected lane streams (68 columns x 3 rows x 6 layers) boxes of its strip through a ring of
+// EXT_NS shared-memory stages (cp.async.bulk.tensor.4d completing on one mbarrier per stage), the warp consumes
+// a stage as three row steps -- the rotation period of the three-row state, so a stage is one trip of the
+// unrolled loop -- and hands it back for the box EXT_NS stages ahead.  The loads no longer occupy registers or
+// issue slots, and each warp keeps (EXT_NS - 1) x 4.5 KB in flight, which is what lets the kernel follow the
+// HBM stream.  Out-of-image box elements arrive as zeros; they only ever feed rows / columns inside the
+// IMAGE_BORDER margin, which cannot hold candidates.
+// ---------------------------------------------------------------------------
+constexpr int EXT_RB = 3;                         // rows per stage
+constexpr int EXT_NS = 3;                         // stages per warp
+constexpr int EXT_STEPS = 12;                     // stages per warp pass
+constexpr int EXT_ROWS = EXT_RB * EXT_STEPS - 2;  // centre rows per warp (two halo rows)
+// a TMA box must start on a 16-byte boundary of the row: the box begins 4 columns left of the strip (60j - 4)
+// and is 68 columns wide, the lane's pair sits at box column 2 + 2*lane
+constexpr int EXT_BOX_W = 68;
+constexpr int EXT_BOX_X0 = 4;
+constexpr uint32_t EXT_STAGE_BYTES = N_LAYERS * EXT_RB * EXT_BOX_W * sizeof(float);   // bytes one box delivers
+constexpr int EXT_STAGE_FLOATS = (EXT_STAGE_BYTES + 127) / 128 * 128 / sizeof(float);  // stage stride (128-byte aligned)
+constexpr size_t EXT_SMEM = (size_t)EX_WARPS * EXT_NS * EXT_STAGE_FLOATS * sizeof(float);
+
+template <int K, bool EVAL, bool KEEP_FLAT>
+__device__ __forceinline__ void ext_step(const ExWarp& W, ExState& S, const float2* sp, const int r) {
+    float2 gv[N_LAYERS];
+#pragma unroll
+    for (int l = 0; l < N_LAYERS; l++) gv[l] = sp[(l * EXT_RB + K) * (EXT_BOX_W / 2)];  // sp: lane's pair in row 0, layer 0
+#pragma unroll
+    for (int l = 0; l < N_DOG; l++) S.d[K][l] = sub2(gv[l + 1], gv[l]);
+    if (EVAL) ex_eval<K, KEEP_FLAT>(W, S, r - 1);
+}
+
+template <bool KEEP_FLAT>
+__global__ void __launch_bounds__(32 * EX_WARPS, 4) k_extrema_tma(const __grid_constant__ CUtensorMap tmap, const ExtremaParams p) {
+    extern __shared__ __align__(1024) float ext_smem[];
+    __shared__ __align__(8) uint64_t bar[EX_WARPS][EXT_NS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y0 = (blockIdx.y * EX_WARPS + warp) * EXT_ROWS;
+    if (y0 >= p.h) return;  // warps are independent: no CTA-wide barrier below
+    const int img = blockIdx.z;
+    ExWarp W;
+    ex_setup(W, p, blockIdx.x, lane, img);
+    float* ring = ext_smem + warp * EXT_NS * EXT_STAGE_FLOATS;
+    // image rows y0-1 .. min(y0 + EXT_ROWS, h), three per stage
+    const int n_stages = (min(y0 + EXT_ROWS, p.h) - y0 + 2 + EXT_RB - 1) / EXT_RB;
+    const int bx = blockIdx.x * EX_SPAN - EXT_BOX_X0;
+    auto issue = [&](const int s, const int slot) {
+        const uint32_t bar_a = smem_u32(&bar[warp][slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(EXT_STAGE_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(ring + slot * EXT_STAGE_FLOATS)), "l"(&tmap), "r"(bx), "r"(y0 - 1 + s * EXT_RB), "r"(0), "r"(img),
+              "r"(bar_a)
+            : "memory");
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < EXT_NS; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[warp][b])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int b = 0; b < EXT_NS; b++)
+            if (b < n_stages) issue(b, b);
+    }
+    __syncwarp();
+    ExState S;
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < n_stages; s++) {
+        {
+            const uint32_t bar_a = smem_u32(&bar[warp][slot]);
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                    : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+            }
+        }
+        const float2* sp = reinterpret_cast<const float2*>(ring + slot * EXT_STAGE_FLOATS) + (EXT_BOX_X0 - 2) / 2 + lane;
+        const int r = y0 - 1 + s * EXT_RB;
+        if (s == 0) {
+            ext_step<0, false, KEEP_FLAT>(W, S, sp, r);
+            ext_step<1, false, KEEP_FLAT>(W, S, sp, r + 1);
+        } else {
+            ext_step<0, true, KEEP_FLAT>(W, S, sp, r);
+            ext_step<1, true, KEEP_FLAT>(W, S, sp, r + 1);
+        }
+        ext_step<2, true, KEEP_FLAT>(W, S, sp, r + 2);
+        __syncwarp();  // every lane has consumed the stage: hand it back to the copy engine
+        if (lane == 0 && s + EXT_NS < n_stages) issue(s + EXT_NS, slot);
+        if (++slot == EXT_NS) { slot = 0; phase ^= 1u; }
     }
 }
 
@@ -675,6 +802,8 @@ __global__ void __launch_bounds__(1024) k_rowscan(const uint32_t* __restrict__ r
 
 // Ordered compaction: warp per (scale, row) entry; writes packed candidate keys in
 // raster order at the row's scanned offset => natural order of src/lib.rs:287-293,324-332.
+// A lane takes one strip's word pair {B0, B1} and emits its columns in ascending order
+// (bit l of B0 is column 60*strip - 2 + 2l, bit l of B1 the column after it).
 __global__ void __launch_bounds__(256) k_compact(const PyrLayout L, const uint32_t* __restrict__ mask,
                                                   const uint32_t* __restrict__ rows,
                                                   const uint32_t* __restrict__ rowoff, uint32_t* __restrict__ keys,
@@ -690,23 +819,26 @@ __global__ void __launch_bounds__(256) k_compact(const PyrLayout L, const uint32
     const OctLayout& ol = L.o[o];
     const int local = ridx - ol.row_base;
     const int s = local / ol.h + 1, y = local - (s - 1) * ol.h;
-    const uint32_t* words = mask + img * L.img_mask_words + ol.mask_off + (long long)local * ol.mask_pitch;
+    const uint2* words = reinterpret_cast<const uint2*>(mask + img * L.img_mask_words + ol.mask_off + (long long)local * ol.mask_pitch);
     uint32_t pos0 = rowoff[img * L.img_rows + ridx];
     uint32_t* out = keys + img * (long long)cap;
-    const int nw = (ol.w + 31) >> 5;
-    for (int wb = 0; wb < nw; wb += 32) {
-        uint32_t word = (wb + lane < nw) ? words[wb + lane] : 0u;
-        uint32_t c = __popc(word), incl = c;
+    const int ns = ol.mask_pitch >> 1;
+    for (int sb = 0; sb < ns; sb += 32) {
+        uint2 word = (sb + lane < ns) ? words[sb + lane] : make_uint2(0u, 0u);
+        uint32_t c = __popc(word.x) + __popc(word.y), incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
         uint32_t pos = pos0 + incl - c;
-        while (word) {
-            int b = __ffs(word) - 1;
-            word &= word - 1;
-            if (pos < cap) out[pos] = pack_key(o, s, y, (wb + lane) * 32 + b);
+        const int xbase = (sb + lane) * EX_SPAN - 2;
+        while (word.x | word.y) {
+            const int l0 = word.x ? __ffs(word.x) - 1 : 32, l1 = word.y ? __ffs(word.y) - 1 : 32;
+            int x;
+            if (l0 <= l1) { x = xbase + 2 * l0; word.x &= word.x - 1; }
+            else { x = xbase + 2 * l1 + 1; word.y &= word.y - 1; }
+            if (pos < cap) out[pos] = pack_key(o, s, y, x);
             pos++;
         }
         pos0 += __shfl_sync(0xffffffffu, incl, 31);

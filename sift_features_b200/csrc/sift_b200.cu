@@ -83,6 +83,7 @@ struct sb200_ctx {
     uint32_t cur_w = 0, cur_h = 0;
     // TMA descriptors of the Gaussian arenas: [slot][octave][destination layer 1..5]
     CUtensorMap tmap[2][MAX_OCT][N_LAYERS];
+    CUtensorMap tmap_ex[2][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
     bool tmap_ok[MAX_OCT] = {false};
     void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
     // capacities the arenas were sized for
@@ -162,7 +163,7 @@ PyrLayout make_layout(uint32_t w, uint32_t h) {
         OctLayout& ol = L.o[o];
         ol.w = cw; ol.h = ch;
         ol.pitch = (std::max(cw, 1) + 31) / 32 * 32;
-        ol.mask_pitch = (std::max(cw, 1) + 31) / 32;
+        ol.mask_pitch = 2 * ex_strips(std::max(cw, 1));
         ol.layer_stride = (long long)ol.pitch * std::max(ch, 1);
         ol.off = off;
         off += ol.layer_stride * N_LAYERS;
@@ -358,6 +359,21 @@ int encode_one(sb200_ctx* ctx, int slot, int o) {
     return SB200_OK;
 }
 
+int encode_extrema(sb200_ctx* ctx, int slot, int o) {
+    const OctLayout& ol = ctx->L.o[o];
+    const cuuint64_t gdim[4] = {(cuuint64_t)ol.w, (cuuint64_t)ol.h, (cuuint64_t)N_LAYERS, (cuuint64_t)ctx->max_batch};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ol.pitch * 4, (cuuint64_t)ol.layer_stride * 4,
+                                (cuuint64_t)ctx->L.img_floats * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)EXT_BOX_W, (cuuint32_t)EXT_RB, (cuuint32_t)N_LAYERS, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode_fn)(&ctx->tmap_ex[slot][o], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                                 ctx->slot[slot].d_gauss + ol.off, gdim, gstr, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SB200_E_CUDA, "cuTensorMapEncodeTiled failed (%d) octave %d (extrema)", (int)r, o);
+    return SB200_OK;
+}
+
 int build_tensor_maps(sb200_ctx* ctx) {
     for (int o = 0; o < MAX_OCT; o++) ctx->tmap_ok[o] = false;
     if (!ctx->encode_fn || getenv("SB200_NO_TMA")) return SB200_OK;  // env switch: debugging aid only
@@ -367,7 +383,7 @@ int build_tensor_maps(sb200_ctx* ctx) {
         for (int sl = 0; sl < 2; sl++) {
             int r;
             if ((o == 0 && (r = encode_one<0>(ctx, sl, o))) || (r = encode_one<1>(ctx, sl, o)) || (r = encode_one<2>(ctx, sl, o)) || (r = encode_one<3>(ctx, sl, o)) ||
-                (r = encode_one<4>(ctx, sl, o)) || (r = encode_one<5>(ctx, sl, o)))
+                (r = encode_one<4>(ctx, sl, o)) || (r = encode_one<5>(ctx, sl, o)) || (r = encode_extrema(ctx, sl, o)))
                 return r;
         }
         ctx->tmap_ok[o] = true;
@@ -420,6 +436,18 @@ void launch_blur_tma(cudaStream_t st, const CUtensorMap& tm, const BlurParams& p
     using C = TmaCfg<LI>;
     dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + C::TH - 1) / C::TH, n);
     k_blur_tma<LI, DEC><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer);
+}
+
+template <bool KEEP_FLAT>
+void launch_extrema(sb200_ctx* ctx, cudaStream_t st, int slot, int o, const ExtremaParams& e, uint32_t n) {
+    const OctLayout& ol = ctx->L.o[o];
+    if (ctx->tmap_ok[o]) {
+        dim3 grid(ex_strips(ol.w), (ol.h + EXT_ROWS * EX_WARPS - 1) / (EXT_ROWS * EX_WARPS), n);
+        k_extrema_tma<KEEP_FLAT><<<grid, 32 * EX_WARPS, EXT_SMEM, st>>>(ctx->tmap_ex[slot][o], e);
+    } else {
+        dim3 grid(ex_strips(ol.w), (ol.h + EX_ROWS * EX_WARPS - 1) / (EX_ROWS * EX_WARPS), n);
+        k_extrema<KEEP_FLAT><<<grid, 32 * EX_WARPS, 0, st>>>(e);
+    }
 }
 
 // Gaussian scale space + DoG/extrema masks for the n images staged in slot.d_in
@@ -511,8 +539,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             e.mask_pitch = ol.mask_pitch;
             e.rows = s.d_rows + ol.row_base;
             e.rows_img_stride = L.img_rows;
-            dim3 grid((ol.w + EX_COLS - 1) / EX_COLS, (ol.h + EX_ROWS * EX_WARPS - 1) / (EX_ROWS * EX_WARPS), n);
-            k_extrema<false><<<grid, 32 * EX_WARPS, 0, st>>>(e);
+            launch_extrema<false>(ctx, st, s.index, o, e, n);
             count_launch(ctx, SB200_STAGE_EXTREMA);
         }
     }
@@ -773,6 +800,9 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         if ((r = set_tma_attr<0, false>(ctx)) || (r = set_tma_attr<1, false>(ctx)) || (r = set_tma_attr<2, false>(ctx)) || (r = set_tma_attr<3, false>(ctx)) ||
             (r = set_tma_attr<3, true>(ctx)) || (r = set_tma_attr<4, false>(ctx)) || (r = set_tma_attr<5, false>(ctx)))
             return r;
+        CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));
+        CU(cudaFuncSetAttribute(k_extrema_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));
+        CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CU(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DESC_SMEM_BYTES));
         CU(cudaFuncSetAttribute(k_descriptor_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DESC_SMEM_BYTES));
         {
@@ -1019,8 +1049,7 @@ int sb200_last_candidates(sb200_ctx* ctx, sb200_candidate* out, uint64_t cap, ui
             e.w = ol.w; e.h = ol.h; e.pitch = ol.pitch;
             e.mask = d_mask + ol.mask_off; e.mask_img_stride = L.img_mask_words; e.mask_pitch = ol.mask_pitch;
             e.rows = d_rows + ol.row_base; e.rows_img_stride = L.img_rows;
-            dim3 grid((ol.w + EX_COLS - 1) / EX_COLS, (ol.h + EX_ROWS * EX_WARPS - 1) / (EX_ROWS * EX_WARPS), 1);
-            k_extrema<true><<<grid, 32 * EX_WARPS, 0, st>>>(e);
+            launch_extrema<true>(ctx, st, s.index, o, e, 1);
             ctx->launches++;
         }
         k_rowscan<<<1, 1024, 0, st>>>(d_rows, d_rowoff, L.img_rows, d_cnt);
