@@ -489,6 +489,209 @@ __global__ void __launch_bounds__(256, TmaCfg<L>::CTAS_PER_SM) k_blur_tma(const 
 }
 
 // ---------------------------------------------------------------------------
+// Marching variant of the TMA blur (the one the pipeline uses for octaves of at least TMA_MIN_DIM pixels per
+// side).  A CTA owns a 128-column strip of one vertical segment of the image and walks down it in bands of 32
+// rows: while band b+1 is in flight (cp.async.bulk.tensor, two stage buffers, one mbarrier each) the CTA runs
+// the row pass of band b into a ring of row-pass results and the column pass of the 32 output rows whose
+// (2R+1)-row window is complete.  Compared with independent (64 + 2R)-row tiles this computes every row-pass
+// result once instead of (64 + 2R) / 64 times, keeps one band in flight per CTA at all times, and needs a
+// single __syncthreads per band.
+//   * ring: three 32-row slots (band b in slot b % 3) plus a fourth that mirrors slot 0, so the two bands a
+//     column-pass thread reads (b, b+1) are always contiguous and every smem offset is an immediate;
+//   * step j = { issue TMA of band j+2; row pass of band j+1; column pass of band j-1; barrier };
+//   * BORDER_REFLECT_101: left/right halo columns are patched in the stage buffer (edge strips only, as in
+//     k_blur_tma); rows above / below the image are row-passed from the stage row they mirror, or copied from
+//     the ring when that row belongs to the previous band.
+// Same arithmetic, operation for operation, as k_blur / k_blur_tma.
+// ---------------------------------------------------------------------------
+template <int L>
+struct MarchCfg {
+    static constexpr int R = blur_radius(L);
+    static constexpr int RA = (R + 3) / 4 * 4;   // left halo of the box: a TMA box starts on a 16-byte boundary
+    static constexpr int XO = RA - R;            // box column of the first element the filter needs
+    static constexpr int TW = 128, BH = 32;
+    static constexpr int SW = TW + 2 * R;
+    static constexpr int WIN = XO + 8 + 2 * R;   // box floats read for 8 consecutive row-pass outputs (aligned start)
+    static constexpr int NV4 = (WIN + 3) / 4;
+    static constexpr int BW_MIN = (XO + SW > TW - 8 + 4 * NV4) ? XO + SW : TW - 8 + 4 * NV4;
+    static constexpr int BW4 = (BW_MIN + 3) / 4;
+    static constexpr int BW = 4 * ((BW4 % 2) ? BW4 : BW4 + 1);   // BW/4 odd: conflict-free LDS.128 with lanes <-> rows
+    static constexpr int IPITCH = TW + 4;        // == 4 (mod 32)
+    static constexpr int PY = 8;                 // output rows per column-pass thread (which owns two adjacent columns)
+    static constexpr int THREADS = 256;
+    static constexpr int NSTG = 2;
+    static constexpr int NSLOT = 4;
+    static constexpr uint32_t BAND_BYTES = (uint32_t)BH * BW * sizeof(float);
+    static constexpr size_t SMEM = (size_t)NSTG * BAND_BYTES + (size_t)NSLOT * BH * IPITCH * sizeof(float);
+    static_assert(BW >= XO + SW && (BW / 4) % 2 == 1 && TW - 8 + 4 * NV4 <= BW && BW <= 256, "box width");
+    static_assert(BAND_BYTES % 128 == 0, "128-byte aligned stage buffers");
+    static_assert(2 * R + 1 <= BH && PY + 2 * R <= 2 * BH, "window spans at most two bands");
+    static_assert((TW / 2) * (BH / PY) == THREADS, "one column-pass task per thread");
+};
+
+template <int L, bool DECIMATE>
+__global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
+                                                        const int src_layer, const int seg_rows) {
+    using C = MarchCfg<L>;
+    constexpr int R = C::R;
+    extern __shared__ __align__(1024) float smem_march[];
+    __shared__ __align__(8) uint64_t bar[C::NSTG];
+    float* const stage = smem_march;                                  // NSTG x BH x BW (TMA box layout)
+    float* const inter = smem_march + C::NSTG * C::BH * C::BW;        // NSLOT x BH x IPITCH
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * C::TW;
+    const int ya = blockIdx.y * seg_rows;
+    const int img = blockIdx.z;
+    const int w = p.w, h = p.h;
+    const int yb = min(ya + seg_rows, h);
+    const int n_out = (yb - ya + C::BH - 1) / C::BH;           // output bands
+    const int n_in = (yb - ya + 2 * R + C::BH - 1) / C::BH;    // input bands (n_out or n_out + 1)
+    const int in0 = ya - R;                                    // first input row of band 0
+    const bool hedge = tx0 - R < 0 || tx0 + C::TW + R > w;
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < C::NSTG; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[b])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](const int b) {
+        const uint32_t bar_a = smem_u32(&bar[b & 1]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(C::BAND_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(stage + (b & 1) * C::BH * C::BW)), "l"(&tmap), "r"(tx0 - C::RA), "r"(in0 + b * C::BH),
+              "r"(src_layer), "r"(img), "r"(bar_a)
+            : "memory");
+    };
+    if (tid == 0) {
+        issue(0);
+        if (n_in > 1) issue(1);
+    }
+
+    // ---- row pass of input band b: warp = the band's 32 rows x one 8-pixel segment ----
+    auto row_pass = [&](const int b) {
+        {
+            const uint32_t bar_a = smem_u32(&bar[b & 1]);
+            const uint32_t parity = (uint32_t)(b >> 1) & 1u;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                    : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
+            }
+        }
+        float* const st = stage + (b & 1) * C::BH * C::BW;
+        const int band_y0 = in0 + b * C::BH;
+        if (hedge) {  // block-uniform: box element (row, XO + col) holds image pixel (band_y0 + row, tx0 - R + col)
+            for (int idx = tid; idx < C::BH * C::SW; idx += C::THREADS) {
+                const int row = idx / C::SW, col = idx - row * C::SW;
+                const int gx = tx0 - R + col;
+                if (gx < 0 || gx >= w) {
+                    const int rx = reflect101(gx, w) - (tx0 - R);
+                    if (rx >= 0 && rx < C::SW) st[row * C::BW + C::XO + col] = st[row * C::BW + C::XO + rx];
+                }
+            }
+            __syncthreads();
+        }
+        const int slot = b % 3;
+        float* const ib = inter + slot * C::BH * C::IPITCH;
+        const bool vedge = band_y0 < 0 || band_y0 + C::BH > h;                      // block-uniform
+        const int rows_needed = min(C::BH, yb + R - band_y0);
+        const int row = lane;
+        int srow = row;         // stage row this lane filters
+        bool copy_prev = false; // the mirrored row belongs to the previous band: copy its row-pass result from the ring
+        if (vedge) {
+            const int yy = reflect101(band_y0 + row, h);
+            srow = yy - band_y0;
+            copy_prev = srow < 0;
+        }
+        for (int seg = warp; seg < C::TW / 8; seg += C::THREADS / 32) {
+            if (row >= rows_needed) continue;
+            float4* const ip = reinterpret_cast<float4*>(ib + row * C::IPITCH + seg * 8);
+            float4 o0, o1;
+            if (copy_prev) {
+                const float4* src = reinterpret_cast<const float4*>(inter + ((b + 2) % 3) * C::BH * C::IPITCH +
+                                                                    (srow + C::BH) * C::IPITCH + seg * 8);
+                o0 = src[0]; o1 = src[1];
+            } else {
+                float win[4 * C::NV4];
+                const float4* sp = reinterpret_cast<const float4*>(st + srow * C::BW + seg * 8);
+#pragma unroll
+                for (int v = 0; v < C::NV4; v++) {
+                    float4 q = sp[v];
+                    win[4 * v + 0] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
+                }
+                // packed arithmetic: outputs (2jp, 2jp+1) share one FFMA2 chain; the operand pair for tap i starts
+                // at window index XO + 2jp + i, which is an aligned register pair of `win` when even and comes
+                // from the one-float-shifted copy `sh` when odd
+                float2 sh[2 * C::NV4];
+#pragma unroll
+                for (int m = 0; 2 * m + 2 < 4 * C::NV4; m++) sh[m] = make_float2(win[2 * m + 1], win[2 * m + 2]);
+                float2 acc[4];
+#pragma unroll
+                for (int jp = 0; jp < 4; jp++) {
+#pragma unroll
+                    for (int i = 0; i <= 2 * R; i++) {
+                        const int sidx = C::XO + 2 * jp + i;
+                        const float2 in = (sidx & 1) ? sh[sidx >> 1] : make_float2(win[sidx], win[sidx + 1]);
+                        acc[jp] = (i == 0) ? mul2(in, c_taps2[L][0]) : fma2(in, c_taps2[L][i], acc[jp]);
+                    }
+                }
+                o0 = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+                o1 = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+            }
+            ip[0] = o0; ip[1] = o1;
+            if (slot == 0) {  // mirror of slot 0 behind slot 2
+                float4* const im = ip + 3 * C::BH * C::IPITCH / 4;
+                im[0] = o0; im[1] = o1;
+            }
+        }
+    };
+
+    // ---- column pass of output band jb: thread = two adjacent columns x PY consecutive rows, packed f32x2 ----
+    float* const dst = p.dst + (long long)img * p.img_stride;
+    float* const dec = DECIMATE ? p.dec + (long long)img * p.img_stride : nullptr;
+    auto col_pass = [&](const int jb) {
+        const int cy = tid / (C::TW / 2), xp = tid - cy * (C::TW / 2);
+        const int y0 = cy * C::PY;
+        const int gy0 = ya + jb * C::BH + y0;
+        if (gy0 >= yb) return;  // whole chunk below the segment (warp-uniform)
+        const int gx = tx0 + 2 * xp;
+        // ring row of output row y0 + j, tap offset i: band jb starts at its slot, band jb+1 follows contiguously
+        const float* const base = inter + (jb % 3) * C::BH * C::IPITCH + y0 * C::IPITCH + 2 * xp;
+        float2 c[C::PY + 2 * R];
+#pragma unroll
+        for (int j = 0; j < C::PY + 2 * R; j++) c[j] = *reinterpret_cast<const float2*>(base + j * C::IPITCH);
+#pragma unroll
+        for (int j = 0; j < C::PY; j++) {
+            float2 acc = mul2(c[j + R], c_taps2[L][R]);
+#pragma unroll
+            for (int i = 1; i <= R; i++) acc = fma2(add2(c[j + R + i], c[j + R - i]), c_taps2[L][R + i], acc);
+            const int gy = gy0 + j;
+            if (gy < yb && gx < w) {
+                float* q = dst + (long long)gy * p.pitch + gx;
+                if (gx + 1 < w) *reinterpret_cast<float2*>(q) = acc;
+                else q[0] = acc.x;
+                if (DECIMATE && !(gy & 1)) {   // gx is even
+                    const int dy = gy >> 1, dx = gx >> 1;
+                    if (dy < p.dec_h && dx < p.dec_w) dec[(long long)dy * p.dec_pitch + dx] = acc.x;
+                }
+            }
+        }
+    };
+
+    row_pass(0);
+    __syncthreads();
+    for (int j = 0; j <= n_out; j++) {
+        // band j was row-passed before the last barrier: its stage buffer is free for band j+2
+        if (tid == 0 && j + 2 < n_in) issue(j + 2);
+        if (j + 1 < n_in) row_pass(j + 1);
+        if (j >= 1) col_pass(j - 1);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // DoG + 3x3x3 extrema (build_dog + point_is_local_extremum, src/lib.rs:271-279,
 // 437-506) for the three scales of one octave in one pass over its six Gaussian
 // layers.  A warp owns a strip of EX_SPAN = 60 output columns: lane l holds the

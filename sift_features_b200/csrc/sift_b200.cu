@@ -83,6 +83,8 @@ struct sb200_ctx {
     uint32_t cur_w = 0, cur_h = 0;
     // TMA descriptors of the Gaussian arenas: [slot][octave][destination layer 1..5]
     CUtensorMap tmap[2][MAX_OCT][N_LAYERS];
+    CUtensorMap tmap_m[2][MAX_OCT][N_LAYERS];  // marching blur: (BW x 32) boxes
+    bool march = true;                         // SB200_BLUR=tile selects the independent-tile TMA blur (debugging aid)
     CUtensorMap tmap_ex[2][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
     bool tmap_ok[MAX_OCT] = {false};
     void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
@@ -359,6 +361,23 @@ int encode_one(sb200_ctx* ctx, int slot, int o) {
     return SB200_OK;
 }
 
+template <int LI>
+int encode_march(sb200_ctx* ctx, int slot, int o) {
+    using C = MarchCfg<LI>;
+    const OctLayout& ol = ctx->L.o[o];
+    const cuuint64_t gdim[4] = {(cuuint64_t)ol.w, (cuuint64_t)ol.h, (cuuint64_t)N_LAYERS, (cuuint64_t)ctx->max_batch};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ol.pitch * 4, (cuuint64_t)ol.layer_stride * 4,
+                                (cuuint64_t)ctx->L.img_floats * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)C::BW, (cuuint32_t)C::BH, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode_fn)(&ctx->tmap_m[slot][o][LI], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                                 ctx->slot[slot].d_gauss + ol.off, gdim, gstr, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SB200_E_CUDA, "cuTensorMapEncodeTiled failed (%d) octave %d layer %d (march)", (int)r, o, LI);
+    return SB200_OK;
+}
+
 int encode_extrema(sb200_ctx* ctx, int slot, int o) {
     const OctLayout& ol = ctx->L.o[o];
     const cuuint64_t gdim[4] = {(cuuint64_t)ol.w, (cuuint64_t)ol.h, (cuuint64_t)N_LAYERS, (cuuint64_t)ctx->max_batch};
@@ -383,7 +402,9 @@ int build_tensor_maps(sb200_ctx* ctx) {
         for (int sl = 0; sl < 2; sl++) {
             int r;
             if ((o == 0 && (r = encode_one<0>(ctx, sl, o))) || (r = encode_one<1>(ctx, sl, o)) || (r = encode_one<2>(ctx, sl, o)) || (r = encode_one<3>(ctx, sl, o)) ||
-                (r = encode_one<4>(ctx, sl, o)) || (r = encode_one<5>(ctx, sl, o)) || (r = encode_extrema(ctx, sl, o)))
+                (r = encode_one<4>(ctx, sl, o)) || (r = encode_one<5>(ctx, sl, o)) || (r = encode_extrema(ctx, sl, o)) ||
+                (o == 0 && (r = encode_march<0>(ctx, sl, o))) || (r = encode_march<1>(ctx, sl, o)) || (r = encode_march<2>(ctx, sl, o)) ||
+                (r = encode_march<3>(ctx, sl, o)) || (r = encode_march<4>(ctx, sl, o)) || (r = encode_march<5>(ctx, sl, o)))
                 return r;
         }
         ctx->tmap_ok[o] = true;
@@ -438,6 +459,32 @@ void launch_blur_tma(cudaStream_t st, const CUtensorMap& tm, const BlurParams& p
     k_blur_tma<LI, DEC><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer);
 }
 
+template <int LI, bool DEC>
+int set_march_attr(sb200_ctx* ctx) {
+    CU(cudaFuncSetAttribute(k_blur_march<LI, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MarchCfg<LI>::SMEM));
+    CU(cudaFuncSetAttribute(k_blur_march<LI, DEC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    return SB200_OK;
+}
+
+// rows per vertical segment of the marching blur: as tall as possible (the row pass of 2R halo rows is the
+// only redundant work) while the launch still holds several CTAs per resident slot
+int march_seg_rows(const sb200_ctx* ctx, int w, int h, uint32_t n) {
+    const long long strips = (w + 127) / 128;
+    const long long target = 8LL * 2 * ctx->sm_count;
+    const long long segs = std::max<long long>(1, (target + strips * n - 1) / (strips * n));
+    long long rows = ((h + segs - 1) / segs + 31) / 32 * 32;
+    rows = std::min<long long>(std::max<long long>(rows, 64), 512);
+    return (int)rows;
+}
+
+template <int LI, bool DEC>
+void launch_blur_march(sb200_ctx* ctx, cudaStream_t st, const CUtensorMap& tm, const BlurParams& p, uint32_t n, int src_layer) {
+    using C = MarchCfg<LI>;
+    const int seg = march_seg_rows(ctx, p.w, p.h, n);
+    dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + seg - 1) / seg, n);
+    k_blur_march<LI, DEC><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer, seg);
+}
+
 template <bool KEEP_FLAT>
 void launch_extrema(sb200_ctx* ctx, cudaStream_t st, int slot, int o, const ExtremaParams& e, uint32_t n) {
     const OctLayout& ol = ctx->L.o[o];
@@ -474,7 +521,8 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             u.img_stride = L.img_floats; u.pitch = L.o[0].pitch;
             dim3 grid((((int)w + 1) / 2 + 255) / 256, h + 1, n);
             k_upsample2x<<<grid, 256, 0, st>>>(u);
-            launch_blur_tma<0, false>(st, ctx->tmap[s.index][0][0], p, n, 5);
+            if (ctx->march) launch_blur_march<0, false>(ctx, st, ctx->tmap_m[s.index][0][0], p, n, 5);
+            else launch_blur_tma<0, false>(st, ctx->tmap[s.index][0][0], p, n, 5);
             count_launch(ctx, SB200_STAGE_SEED, 2);
         } else {
             launch_blur<0, true, false>(st, p, n);
@@ -499,7 +547,19 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
                     p.dec = s.d_gauss + L.o[o + 1].off;
                     p.dec_w = L.o[o + 1].w; p.dec_h = L.o[o + 1].h; p.dec_pitch = L.o[o + 1].pitch;
                 }
-                if (ctx->tmap_ok[o]) {
+                if (ctx->tmap_ok[o] && ctx->march) {
+                    const CUtensorMap& tm = ctx->tmap_m[s.index][o][l];
+                    switch (l) {
+                        case 1: launch_blur_march<1, false>(ctx, st, tm, p, n, 0); break;
+                        case 2: launch_blur_march<2, false>(ctx, st, tm, p, n, 1); break;
+                        case 3:
+                            if (dec) launch_blur_march<3, true>(ctx, st, tm, p, n, 2);
+                            else launch_blur_march<3, false>(ctx, st, tm, p, n, 2);
+                            break;
+                        case 4: launch_blur_march<4, false>(ctx, st, tm, p, n, 3); break;
+                        default: launch_blur_march<5, false>(ctx, st, tm, p, n, 4); break;
+                    }
+                } else if (ctx->tmap_ok[o]) {
                     const CUtensorMap& tm = ctx->tmap[s.index][o][l];
                     switch (l) {
                         case 1: launch_blur_tma<1, false>(st, tm, p, n, 0); break;
@@ -800,6 +860,14 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         if ((r = set_tma_attr<0, false>(ctx)) || (r = set_tma_attr<1, false>(ctx)) || (r = set_tma_attr<2, false>(ctx)) || (r = set_tma_attr<3, false>(ctx)) ||
             (r = set_tma_attr<3, true>(ctx)) || (r = set_tma_attr<4, false>(ctx)) || (r = set_tma_attr<5, false>(ctx)))
             return r;
+        if ((r = set_march_attr<0, false>(ctx)) || (r = set_march_attr<1, false>(ctx)) || (r = set_march_attr<2, false>(ctx)) ||
+            (r = set_march_attr<3, false>(ctx)) || (r = set_march_attr<3, true>(ctx)) || (r = set_march_attr<4, false>(ctx)) ||
+            (r = set_march_attr<5, false>(ctx)))
+            return r;
+        {
+            const char* e = getenv("SB200_BLUR");
+            ctx->march = !(e && !strcmp(e, "tile"));
+        }
         CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));
         CU(cudaFuncSetAttribute(k_extrema_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));
         CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
