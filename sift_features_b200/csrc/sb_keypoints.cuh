@@ -448,14 +448,17 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 //     at the end (f32 sums in a different order than the reference's raster order: the +-1 byte
 //     tolerance of the north star covers it; everything up to the accumulation is the reference's
 //     arithmetic).
-//   * Window samples that fall outside the rotated 4x4 grid (about half) are filtered by a cheap
-//     pass and the survivors queued, so the expensive gradient / exp / atan2 / trilinear part
-//     always runs with 32 active lanes.
+//   * Window samples that fall outside the rotated 4x4 grid (about half) are never visited: the lanes
+//     compute, in parallel, the column span of every window row that can intersect the grid and a running
+//     sample count (one packed word per non-empty row in shared memory); sample i of the keypoint is then
+//     found from that table with one warp-wide OR-reduction per 32 samples, so the expensive gradient /
+//     exp / atan2 / trilinear part always runs with 32 active lanes.
+//   * The four pixel loads of the next 32 samples are issued before the arithmetic of the current 32.
 // ---------------------------------------------------------------------------
 constexpr int DESC_WARPS = 8;
 constexpr int DESC_COPIES = 16;
-constexpr int DESC_QCAP = 64;
-constexpr int DESC_SMEM_WORDS = DESC_SIZE * DESC_COPIES + DESC_QCAP;  // per warp
+constexpr int DESC_MAXROWS = 256;  // window rows: 2 * radius + 1 with radius <= 127
+constexpr int DESC_SMEM_WORDS = DESC_SIZE * DESC_COPIES + DESC_MAXROWS;  // per warp
 constexpr size_t DESC_SMEM_BYTES = 256 + (size_t)DESC_WARPS * DESC_SMEM_WORDS * sizeof(float);
 
 struct DescTarget {
@@ -495,8 +498,20 @@ __device__ __forceinline__ float fast_atan2_deg(const float y, const float x) {
 }
 
 // one queued sample per active lane: gradient, weight, angle, trilinear split, accumulation
+struct DescPix { float xp, xm, ym, yp; };  // I[y][x+1], I[y][x-1], I[y-1][x], I[y+1][x]
+
+__device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const uint32_t packed, const bool active) {
+    DescPix q{0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
+        const float* c = G.img + (long long)(G.y + yw) * G.pitch + (G.x + xw);
+        q.xp = __ldg(c + 1); q.xm = __ldg(c - 1); q.ym = __ldg(c - G.pitch); q.yp = __ldg(c + G.pitch);
+    }
+    return q;
+}
+
 __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint32_t packed, const bool active,
-                                                  float* hist, const int lane) {
+                                                  const DescPix px, float* hist, const int lane) {
     float cv[8];
     bool ok[8];
     int b0 = 0, b1 = 0;  // word offsets of the (first cell, o0) and (first cell, o1) bins
@@ -510,9 +525,8 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     // src/lib.rs:834-837 (the image-bounds half of the test, :838-841, is enforced by the span construction)
     if (active && row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f) {
         const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
-        const float* c = G.img + (long long)(G.y + yw) * G.pitch + (G.x + xw);
-        const float dx = __ldg(c + 1) - __ldg(c - 1);
-        const float dy = __ldg(c - G.pitch) - __ldg(c + G.pitch);
+        const float dx = px.xp - px.xm;
+        const float dy = px.ym - px.yp;
         // magnitude, Gaussian weight and angle: fast approximations (relative error ~1e-6), see header comment
         const float d2 = fmaf(dx, dx, dy * dy);
         const float wgt = fmaf(col_rot, col_rot, row_rot * row_rot);
@@ -566,7 +580,7 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
 __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /* smem [DESC_SMEM_WORDS] */, int lane,
                                                 uint8_t* out /* 128 B */) {
     float* hist = wsm;
-    uint32_t* queue = reinterpret_cast<uint32_t*>(wsm + DESC_SIZE * DESC_COPIES);
+    uint32_t* rows = reinterpret_cast<uint32_t*>(wsm + DESC_SIZE * DESC_COPIES);  // [DESC_MAXROWS] row table
     {
         float4* h4 = reinterpret_cast<float4*>(hist);
         for (int k = lane; k < DESC_SIZE * DESC_COPIES / 4; k += 32) h4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -588,46 +602,76 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     const float inv_s = fabsf(G.sin_s) > 1e-7f ? 1.0f / G.sin_s : 0.f;
     const float inv_c = fabsf(G.cos_s) > 1e-7f ? 1.0f / G.cos_s : 0.f;
     const int xw_min = max(-G.radius, 1 - G.x), xw_max = min(G.radius, G.w - 2 - G.x);
-    __syncwarp();
-    uint32_t qhead = 0, qtail = 0;  // warp-uniform
     const uint32_t lt = (1u << lane) - 1u;
-    for (int yw = -G.radius; yw <= G.radius; yw++) {
+    // ---- row table: lanes take window rows in parallel.  Word k describes the k-th non-empty row:
+    //      running sample count (inclusive) : 16 | first column xlo + radius : 8 | row yw + radius : 8.
+    //      At most a couple of samples per row fail the exact test, which the sample step repeats. ----
+    uint32_t n_rows = 0, total = 0;  // warp-uniform
+    const int nwin = 2 * G.radius + 1;
+    for (int rb = 0; rb < nwin; rb += 32) {
+        const int yq = rb + lane, yw = yq - G.radius;
         const int ay = G.y + yw;
-        if (ay <= 0 || ay >= G.h - 1) continue;  // warp-uniform
-        const float ys = (float)yw * G.sin_s, yc = (float)yw * G.cos_s;
-        float lo = (float)xw_min, hi = (float)xw_max;
-        if (inv_s != 0.f) {  // row_rot = x*sin_s + yc
-            const float a = (-2.5f - yc) * inv_s, b = (2.5f - yc) * inv_s;
-            lo = fmaxf(lo, floorf(fminf(a, b)));
-            hi = fminf(hi, ceilf(fmaxf(a, b)));
-        }
-        if (inv_c != 0.f) {  // col_rot = x*cos_s - ys
-            const float a = (-2.5f + ys) * inv_c, b = (2.5f + ys) * inv_c;
-            lo = fmaxf(lo, floorf(fminf(a, b)));
-            hi = fminf(hi, ceilf(fmaxf(a, b)));
-        }
-        const int xlo = (int)lo, xhi = (int)hi;
-        const uint32_t yq = (uint32_t)(yw + G.radius);
-        // queue the whole conservative span (at most a couple of samples per row fail the exact test, which the
-        // sample step repeats); no floating-point work and no ballots in the scan
-        for (int xb = xlo; xb <= xhi; xb += 32) {
-            const int xw = xb + lane;
-            const int cnt = min(32, xhi - xb + 1);
-            if (lane < cnt) queue[(qtail + lane) & (DESC_QCAP - 1)] = (yq << 8) | (uint32_t)(xw + G.radius);
-            qtail += cnt;
-            __syncwarp();
-            if (qtail - qhead >= 32) {
-                const uint32_t e = queue[(qhead + lane) & (DESC_QCAP - 1)];
-                qhead += 32;
-                descriptor_sample(G, e, true, hist, lane);
+        int xlo = 0, len = 0;
+        if (yq < nwin && ay > 0 && ay < G.h - 1) {
+            const float ys = (float)yw * G.sin_s, yc = (float)yw * G.cos_s;
+            float lo = (float)xw_min, hi = (float)xw_max;
+            if (inv_s != 0.f) {  // row_rot = x*sin_s + yc
+                const float a = (-2.5f - yc) * inv_s, b = (2.5f - yc) * inv_s;
+                lo = fmaxf(lo, floorf(fminf(a, b)));
+                hi = fminf(hi, ceilf(fmaxf(a, b)));
             }
+            if (inv_c != 0.f) {  // col_rot = x*cos_s - ys
+                const float a = (-2.5f + ys) * inv_c, b = (2.5f + ys) * inv_c;
+                lo = fmaxf(lo, floorf(fminf(a, b)));
+                hi = fminf(hi, ceilf(fmaxf(a, b)));
+            }
+            xlo = (int)lo;
+            len = max((int)hi - xlo + 1, 0);
         }
+        const uint32_t ne = __ballot_sync(0xffffffffu, len > 0);
+        uint32_t incl = (uint32_t)len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (len > 0)
+            rows[n_rows + __popc(ne & lt)] = ((total + incl) << 16) | ((uint32_t)(xlo + G.radius) << 8) | (uint32_t)yq;
+        n_rows += __popc(ne);
+        total += __shfl_sync(0xffffffffu, incl, 31);
     }
-    {
-        const uint32_t n = qtail - qhead;  // < 32
-        if (n) {
-            const uint32_t e = queue[(qhead + lane) & (DESC_QCAP - 1)];
-            descriptor_sample(G, e, lane < n, hist, lane);
+    __syncwarp();
+    // ---- samples, 32 at a time: sample i lives in the table row whose running count first exceeds i ----
+    uint32_t r_cur = 0;  // first table row with samples at or after the current batch (warp-uniform)
+    auto lookup = [&](const uint32_t base, uint32_t& packed) -> bool {
+        const uint32_t wj = (r_cur + lane < n_rows) ? rows[r_cur + lane] : 0xffffffffu;
+        const uint32_t last = (wj >> 16) - base - 1u;   // batch position of the row's last sample
+        const uint32_t ends = __reduce_or_sync(0xffffffffu, last < 32u ? 1u << last : 0u);
+        const uint32_t k = r_cur + __popc(ends & lt);    // rows that end before this lane's sample
+        const uint32_t i = base + lane;
+        const bool active = i < total;
+        packed = 0;
+        if (active) {
+            const uint32_t wk = rows[k];
+            const uint32_t before = k ? rows[k - 1] >> 16 : 0u;
+            packed = ((wk & 255u) << 8) | (((wk >> 8) & 255u) + (i - before));
+        }
+        r_cur += __popc(ends);
+        return active;
+    };
+    if (total) {
+        uint32_t e_next;
+        bool a_next = lookup(0, e_next);
+        DescPix p_next = descriptor_fetch(G, e_next, a_next);
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t e = e_next;
+            const bool a = a_next;
+            const DescPix px = p_next;
+            if (base + 32 < total) {
+                a_next = lookup(base + 32, e_next);
+                p_next = descriptor_fetch(G, e_next, a_next);
+            }
+            descriptor_sample(G, e, a, px, hist, lane);
         }
     }
     __syncwarp();
