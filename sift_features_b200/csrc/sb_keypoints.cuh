@@ -458,7 +458,10 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 constexpr int DESC_WARPS = 8;
 constexpr int DESC_COPIES = 16;
 constexpr int DESC_MAXROWS = 256;  // window rows: 2 * radius + 1 with radius <= 127
-constexpr int DESC_SMEM_WORDS = DESC_SIZE * DESC_COPIES + DESC_MAXROWS;  // per warp
+constexpr int DESC_CELL_WORDS = 8 * DESC_COPIES;               // one spatial cell: 8 orientation bins x copies
+constexpr int DESC_HIST_WORDS = 17 * DESC_CELL_WORDS;          // 16 cells + one that swallows out-of-grid parts
+// per warp: histogram copies, row table (running count u16[256], first column u8[256])
+constexpr int DESC_SMEM_WORDS = DESC_HIST_WORDS + DESC_MAXROWS / 2 + DESC_MAXROWS / 4;
 constexpr size_t DESC_SMEM_BYTES = 256 + (size_t)DESC_WARPS * DESC_SMEM_WORDS * sizeof(float);
 
 struct DescTarget {
@@ -510,68 +513,66 @@ __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const uin
     return q;
 }
 
+// one sample per lane: gradient, weight, angle, trilinear split, accumulation.  Branch-free up to the
+// accumulation: lanes without a sample (or whose sample fails the exact membership test) and the parts of a
+// sample that fall outside the 4x4 grid are steered into the spare 17th cell instead of being predicated off.
 __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint32_t packed, const bool active,
                                                   const DescPix px, float* hist, const int lane) {
-    float cv[8];
-    bool ok[8];
-    int b0 = 0, b1 = 0;  // word offsets of the (first cell, o0) and (first cell, o1) bins
-#pragma unroll
-    for (int k = 0; k < 8; k++) { cv[k] = 0.f; ok[k] = false; }
     // geometry: the reference's f32 operations, so the membership test, cell indices and fractions are its values
     const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
-    const float col_rot = (float)xw * G.cos_s - (float)yw * G.sin_s;
-    const float row_rot = (float)xw * G.sin_s + (float)yw * G.cos_s;
+    const float fx = (float)xw, fy = (float)yw;
+    const float col_rot = fx * G.cos_s - fy * G.sin_s;
+    const float row_rot = fx * G.sin_s + fy * G.cos_s;
     const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
     // src/lib.rs:834-837 (the image-bounds half of the test, :838-841, is enforced by the span construction)
-    if (active && row_bin > -0.5f && row_bin < 4.5f && col_bin > -0.5f && col_bin < 4.5f) {
-        const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
-        const float dx = px.xp - px.xm;
-        const float dy = px.ym - px.yp;
-        // magnitude, Gaussian weight and angle: fast approximations (relative error ~1e-6), see header comment
-        const float d2 = fmaf(dx, dx, dy * dy);
-        const float wgt = fmaf(col_rot, col_rot, row_rot * row_rot);
-        const float mag = (d2 > 0.f ? d2 * rsqrtf(d2) : 0.f) * __expf(wgt * -0.125f);  // exp(-2/4^2 * wgt), :859
-        const float orient = fast_atan2_deg(dy, dx) - G.orientation;                   // :871
-        const float obin = orient * (8.0f / 360.0f);
-        const float row_floor = floorf(rb), col_floor = floorf(cbn), ori_floor = floorf(obin);
-        const float row_frac = rb - row_floor, col_frac = cbn - col_floor, ori_frac = obin - ori_floor;
-        // trilinear split exactly as src/lib.rs:906-919
-        const float c1 = mag * row_frac, c0 = mag - c1;
-        const float c11 = c1 * col_frac, c10 = c1 - c11;
-        const float c01 = c0 * col_frac, c00 = c0 - c01;
-        cv[7] = c11 * ori_frac; cv[6] = c11 - cv[7];   // c111, c110
-        cv[5] = c10 * ori_frac; cv[4] = c10 - cv[5];   // c101, c100
-        cv[3] = c01 * ori_frac; cv[2] = c01 - cv[3];   // c011, c010
-        cv[1] = c00 * ori_frac; cv[0] = c00 - cv[1];   // c001, c000
-        // the reference adds into cells (row_floor+1 .. +2, col_floor+1 .. +2) of its 6x6 grid and keeps
-        // cells 1..4 (:951): in inner-grid terms the first cell is (r1, q1) in -1..3
-        const int r1 = (int)row_floor, q1 = (int)col_floor;
-        const int o0 = ((int)ori_floor) & 7;           // ori_floor in [-16, 16): wrap like :926-938
-        const int o1 = (o0 + 1) & 7;
-        const bool r0ok = r1 >= 0, r1ok = r1 <= 2, q0ok = q1 >= 0, q1ok = q1 <= 2;
-        ok[0] = ok[1] = r0ok && q0ok;
-        ok[2] = ok[3] = r0ok && q1ok;
-        ok[4] = ok[5] = r1ok && q0ok;
-        ok[6] = ok[7] = r1ok && q1ok;
-        const int base = (r1 * 4 + q1) * 8;
-        b0 = (base + o0) * DESC_COPIES;
-        b1 = (base + o1) * DESC_COPIES;
-    }
-    float* mine = hist + (lane & (DESC_COPIES - 1));
-    // word offsets of the 8 bins: +8 bins per column step, +32 bins per row step
+    const bool member = active & (row_bin > -0.5f) & (row_bin < 4.5f) & (col_bin > -0.5f) & (col_bin < 4.5f);
+    const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
+    const float dx = px.xp - px.xm;
+    const float dy = px.ym - px.yp;
+    // magnitude, Gaussian weight and angle: fast approximations (relative error ~1e-6), see header comment
+    const float d2 = fmaf(dx, dx, dy * dy);
+    const float wgt = fmaf(col_rot, col_rot, row_rot * row_rot);
+    const float mag = (d2 > 0.f ? d2 * rsqrtf(d2) : 0.f) * __expf(wgt * -0.125f);  // exp(-2/4^2 * wgt), :859
+    const float orient = fast_atan2_deg(dy, dx) - G.orientation;                   // :871
+    const float obin = orient * (8.0f / 360.0f);
+    const float row_floor = floorf(rb), col_floor = floorf(cbn), ori_floor = floorf(obin);
+    const float row_frac = rb - row_floor, col_frac = cbn - col_floor, ori_frac = obin - ori_floor;
+    // trilinear split exactly as src/lib.rs:906-919
+    float cv[8];
+    const float c1 = mag * row_frac, c0 = mag - c1;
+    const float c11 = c1 * col_frac, c10 = c1 - c11;
+    const float c01 = c0 * col_frac, c00 = c0 - c01;
+    cv[7] = c11 * ori_frac; cv[6] = c11 - cv[7];   // c111, c110
+    cv[5] = c10 * ori_frac; cv[4] = c10 - cv[5];   // c101, c100
+    cv[3] = c01 * ori_frac; cv[2] = c01 - cv[3];   // c011, c010
+    cv[1] = c00 * ori_frac; cv[0] = c00 - cv[1];   // c001, c000
+    // the reference adds into cells (row_floor+1 .. +2, col_floor+1 .. +2) of its 6x6 grid and keeps
+    // cells 1..4 (:951): in inner-grid terms the first cell is (r1, q1) in -1..3
+    const int r1 = (int)row_floor, q1 = (int)col_floor;
+    const int o0 = ((int)ori_floor) & 7;           // ori_floor in [-16, 16): wrap like :926-938
+    const int o1 = (o0 + 1) & 7;
+    const bool r0ok = member & ((unsigned)r1 <= 3u), r1ok = member & ((unsigned)(r1 + 1) <= 3u);
+    const bool q0ok = (unsigned)q1 <= 3u, q1ok = (unsigned)(q1 + 1) <= 3u;
+    const int cell00 = r1 * 4 + q1;
+    int cw[4];  // word offsets of the four spatial cells (k >> 1: bit 0 = column step, bit 1 = row step)
+    cw[0] = ((r0ok & q0ok) ? cell00 : 16) * DESC_CELL_WORDS;
+    cw[1] = ((r0ok & q1ok) ? cell00 + 1 : 16) * DESC_CELL_WORDS;
+    cw[2] = ((r1ok & q0ok) ? cell00 + 4 : 16) * DESC_CELL_WORDS;
+    cw[3] = ((r1ok & q1ok) ? cell00 + 5 : 16) * DESC_CELL_WORDS;
+    float* const m0 = hist + (lane & (DESC_COPIES - 1)) + o0 * DESC_COPIES;
+    float* const m1 = hist + (lane & (DESC_COPIES - 1)) + o1 * DESC_COPIES;
+    float* pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) pk[k] = ((k & 1) ? m1 : m0) + cw[k >> 1];
+    // lanes l and l + DESC_COPIES share a copy: two phases
 #pragma unroll
     for (int phase = 0; phase < 32 / DESC_COPIES; phase++) {
-        const bool on = (lane / DESC_COPIES) == phase;
-        float old[8];
+        if ((lane / DESC_COPIES) == phase) {
+            float old[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int off = ((k & 1) ? b1 : b0) + (((k >> 1) & 1) * 8 + (k >> 2) * 32) * DESC_COPIES;
-            old[k] = (on && ok[k]) ? mine[off] : 0.f;
-        }
+            for (int k = 0; k < 8; k++) old[k] = *pk[k];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int off = ((k & 1) ? b1 : b0) + (((k >> 1) & 1) * 8 + (k >> 2) * 32) * DESC_COPIES;
-            if (on && ok[k]) mine[off] = old[k] + cv[k];
+            for (int k = 0; k < 8; k++) *pk[k] = old[k] + cv[k];
         }
         __syncwarp();
     }
@@ -580,10 +581,11 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
 __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /* smem [DESC_SMEM_WORDS] */, int lane,
                                                 uint8_t* out /* 128 B */) {
     float* hist = wsm;
-    uint32_t* rows = reinterpret_cast<uint32_t*>(wsm + DESC_SIZE * DESC_COPIES);  // [DESC_MAXROWS] row table
+    uint16_t* row_cnt = reinterpret_cast<uint16_t*>(wsm + DESC_HIST_WORDS);              // [DESC_MAXROWS] running sample count
+    uint8_t* row_x0 = reinterpret_cast<uint8_t*>(wsm + DESC_HIST_WORDS + DESC_MAXROWS / 2);  // [DESC_MAXROWS] xlo + radius
     {
         float4* h4 = reinterpret_cast<float4*>(hist);
-        for (int k = lane; k < DESC_SIZE * DESC_COPIES / 4; k += 32) h4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = lane; k < DESC_HIST_WORDS / 4; k += 32) h4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     DescGeom G;
     G.img = t.img; G.w = t.w; G.h = t.h; G.pitch = t.pitch; G.orientation = t.orientation;
@@ -603,10 +605,11 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     const float inv_c = fabsf(G.cos_s) > 1e-7f ? 1.0f / G.cos_s : 0.f;
     const int xw_min = max(-G.radius, 1 - G.x), xw_max = min(G.radius, G.w - 2 - G.x);
     const uint32_t lt = (1u << lane) - 1u;
-    // ---- row table: lanes take window rows in parallel.  Word k describes the k-th non-empty row:
-    //      running sample count (inclusive) : 16 | first column xlo + radius : 8 | row yw + radius : 8.
-    //      At most a couple of samples per row fail the exact test, which the sample step repeats. ----
-    uint32_t n_rows = 0, total = 0;  // warp-uniform
+    // ---- row table: lanes take window rows in parallel.  Entry k describes the k-th non-empty row (the
+    //      non-empty rows are consecutive: convex square, convex image): running sample count (inclusive)
+    //      and first column.  At most a couple of samples per row fail the exact test, which the sample
+    //      step repeats. ----
+    uint32_t n_rows = 0, total = 0, yq_first = 0;  // warp-uniform
     const int nwin = 2 * G.radius + 1;
     for (int rb = 0; rb < nwin; rb += 32) {
         const int yq = rb + lane, yw = yq - G.radius;
@@ -635,8 +638,12 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
             const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
         }
-        if (len > 0)
-            rows[n_rows + __popc(ne & lt)] = ((total + incl) << 16) | ((uint32_t)(xlo + G.radius) << 8) | (uint32_t)yq;
+        if (len > 0) {
+            const uint32_t k = n_rows + __popc(ne & lt);
+            row_cnt[k] = (uint16_t)(total + incl);
+            row_x0[k] = (uint8_t)(xlo + G.radius);
+        }
+        if (n_rows == 0 && ne) yq_first = rb + __ffs(ne) - 1;
         n_rows += __popc(ne);
         total += __shfl_sync(0xffffffffu, incl, 31);
     }
@@ -644,17 +651,16 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     // ---- samples, 32 at a time: sample i lives in the table row whose running count first exceeds i ----
     uint32_t r_cur = 0;  // first table row with samples at or after the current batch (warp-uniform)
     auto lookup = [&](const uint32_t base, uint32_t& packed) -> bool {
-        const uint32_t wj = (r_cur + lane < n_rows) ? rows[r_cur + lane] : 0xffffffffu;
-        const uint32_t last = (wj >> 16) - base - 1u;   // batch position of the row's last sample
+        const uint32_t cj = (r_cur + lane < n_rows) ? row_cnt[r_cur + lane] : 0xffffu;
+        const uint32_t last = cj - base - 1u;           // batch position of the row's last sample
         const uint32_t ends = __reduce_or_sync(0xffffffffu, last < 32u ? 1u << last : 0u);
         const uint32_t k = r_cur + __popc(ends & lt);    // rows that end before this lane's sample
         const uint32_t i = base + lane;
         const bool active = i < total;
         packed = 0;
         if (active) {
-            const uint32_t wk = rows[k];
-            const uint32_t before = k ? rows[k - 1] >> 16 : 0u;
-            packed = ((wk & 255u) << 8) | (((wk >> 8) & 255u) + (i - before));
+            const uint32_t before = k ? row_cnt[k - 1] : 0u;
+            packed = ((yq_first + k) << 8) | ((uint32_t)row_x0[k] + (i - before));
         }
         r_cur += __popc(ends);
         return active;
