@@ -201,18 +201,32 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P) {
         const float gws = -1.0f / (2.0f * sigma * sigma);         // :667
         const int side = 2 * radius + 1, total = side * side;
         float acc0 = 0.f, acc1 = 0.f;  // bins `lane` and `32 + lane`
+        // sample `idx` of the (2r+1)^2 window in raster order: pixel loads are issued one batch of 32 ahead
+        auto fetch = [&](const int idx, int& yp, int& xp, float4& q) -> bool {
+            const int yq = idx / side;
+            yp = yq - radius; xp = idx - yq * side - radius;
+            const int yi = y + yp, xi = x + xp;
+            const bool in = idx < total && yi > 0 && yi < h - 1 && xi > 0 && xi < w - 1;
+            if (in) {
+                const float* c = I + (yi * pitch + xi);
+                q = make_float4(__ldg(c + 1), __ldg(c - 1), __ldg(c - pitch), __ldg(c + pitch));
+            }
+            return in;
+        };
+        int yp_n, xp_n;
+        float4 q_n = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool in_n = fetch(lane, yp_n, xp_n, q_n);
         for (int base = 0; base < total; base += 32) {
-            const int idx = base + lane;
+            const int yp = yp_n, xp = xp_n;
+            const float4 q = q_n;
+            const bool in = in_n;
+            if (base + 32 < total) in_n = fetch(base + 32 + lane, yp_n, xp_n, q_n);
             int bin = -1;
             float val = 0.f;
-            if (idx < total) {
-                const int yq = idx / side;
-                const int yp = yq - radius, xp = idx - yq * side - radius;
-                const int yi = y + yp, xi = x + xp;
-                if (yi > 0 && yi < h - 1 && xi > 0 && xi < w - 1) {
-                    const float* c = I + (long long)yi * pitch + xi;
-                    const float dx = __ldg(c + 1) - __ldg(c - 1);
-                    const float dy = __ldg(c - pitch) - __ldg(c + pitch);
+            if (in) {
+                {
+                    const float dx = q.x - q.y;
+                    const float dy = q.z - q.w;
                     const float wexp = (float)(yp * yp + xp * xp) * gws;
                     const float weight = sbm::expf_glibc(s_tab, wexp);
                     const float mag = sqrtf(dx * dx + dy * dy);
@@ -476,13 +490,18 @@ struct DescGeom {
     float sin_s, cos_s, orientation;
 };
 
+// single-instruction SFU approximations (flush-to-zero: no denormal rescaling sequences around the MUFU)
+__device__ __forceinline__ float rcp_approx(const float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_approx(const float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(const float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // atan2(y, x) in degrees, [0, 360): minimax polynomial of atan on [0,1] (|error| < 3.3e-7 rad) plus octant
 // folding.  The reference's f64 atan2 only feeds the trilinear orientation weights here (continuous in the
 // angle), so a 2e-5 degree error is far below the u8 quantisation step of the descriptor.
 __device__ __forceinline__ float fast_atan2_deg(const float y, const float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+    const float a = (mx > 0.f) ? mn * rcp_approx(mx) : 0.f;
     const float s = a * a;
     float p = 0x1.be6ae0p-8f;
     p = fmaf(p, s, -0x1.134924p-5f);
@@ -507,7 +526,7 @@ __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const uin
     DescPix q{0.f, 0.f, 0.f, 0.f};
     if (active) {
         const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
-        const float* c = G.img + (long long)(G.y + yw) * G.pitch + (G.x + xw);
+        const float* c = G.img + ((G.y + yw) * G.pitch + (G.x + xw));   // a layer holds < 2^31 floats: 32-bit offsets
         q.xp = __ldg(c + 1); q.xm = __ldg(c - 1); q.ym = __ldg(c - G.pitch); q.yp = __ldg(c + G.pitch);
     }
     return q;
@@ -532,7 +551,7 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     // magnitude, Gaussian weight and angle: fast approximations (relative error ~1e-6), see header comment
     const float d2 = fmaf(dx, dx, dy * dy);
     const float wgt = fmaf(col_rot, col_rot, row_rot * row_rot);
-    const float mag = (d2 > 0.f ? d2 * rsqrtf(d2) : 0.f) * __expf(wgt * -0.125f);  // exp(-2/4^2 * wgt), :859
+    const float mag = (d2 > 0.f ? d2 * rsqrt_approx(d2) : 0.f) * ex2_approx(wgt * (-0.125f * 1.44269504088896341f));  // exp(-2/4^2 * wgt), :859
     const float orient = fast_atan2_deg(dy, dx) - G.orientation;                   // :871
     const float obin = orient * (8.0f / 360.0f);
     const float row_floor = floorf(rb), col_floor = floorf(cbn), ori_floor = floorf(obin);
