@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (width, height, images per group (= context max_batch), groups per step)
-    "1080p": (1920, 1080, 32, 2),  # BASELINE.json configs[1] shape, batched
+    "1080p": (1920, 1080, 32, 4),  # BASELINE.json configs[1] shape, batched
     "4k": (3840, 2160, 2, 2),      # configs[2]
     "vga": (640, 480, 64, 2),      # configs[3] shape (8192 images = 64 such steps)
 }
@@ -210,6 +210,8 @@ def run_b200(args, rank, local_rank, world):
     w, h, B, G = WORKLOADS[args.workload]
     if args.batch:
         B = args.batch
+    if args.groups:
+        G = args.groups
     per_step = B * G
     ex = sf.Extractor(w, h, B, device=local_rank)
     H = ex.handle
@@ -339,7 +341,7 @@ def run_b200(args, rank, local_rank, world):
         if stats is not None:
             blur_ms = stats["blur"]["ms"]
             pyr_ms = stats["seed"]["ms"] + stats["blur"]["ms"] + stats["extrema"]["ms"]
-            # dominant kernel: the 27-tap blur of octave 0 (k_blur_tma<5>), one launch per group of B images;
+            # dominant kernel: the 27-tap blur of octave 0 (k_blur_march<5>), one launch per group of B images;
             # algorithmic bytes = read 4 B + write 4 B per pixel of the 2W x 2H layer
             top_ms, top_n = stats["top_blur"]["ms"], max(1, stats["top_blur"]["launches"])
             top_bytes = 8.0 * (2 * w) * (2 * h) * B
@@ -348,13 +350,13 @@ def run_b200(args, rank, local_rank, world):
             tp = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tp):
                 try:
-                    t = json.load(open(tp)).get(f"k_blur_tma5_{args.workload}")
+                    t = json.load(open(tp)).get(f"k_blur_march5_{args.workload}")
                     if t:
                         traffic = t["dram_bytes_per_image"] * B   # ncu --set full capture, scaled to this launch
                 except Exception:
                     pass
             line["roofline"] = {
-                "bound": "hbm", "kernel": "k_blur_tma<5,0> (27-tap separable Gaussian, octave 0, one launch per group)",
+                "bound": "hbm", "kernel": "k_blur_march<5,0> (27-tap separable Gaussian, octave 0, one launch per group)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                 "traffic": traffic, "peak_source": peak_src,
                 "measured": "CUDA events around the launch on its launching stream, in a serialised repeat of the "
@@ -458,6 +460,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS) + ["desc"])
     ap.add_argument("--batch", type=int, default=0, help="images per group (context max_batch)")
+    ap.add_argument("--groups", type=int, default=0, help="groups per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-profile-stages", dest="profile_stages", action="store_false",
                     help="do not bracket stages with CUDA events during the timed region")

@@ -501,7 +501,10 @@ __device__ __forceinline__ float ex2_approx(const float x) { float r; asm("ex2.a
 __device__ __forceinline__ float fast_atan2_deg(const float y, const float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = (mx > 0.f) ? mn * rcp_approx(mx) : 0.f;
+    // the flush-to-zero reciprocal needs a normal operand: gradients deep inside constant regions are denormal
+    // (scaling numerator and denominator by 2^64 is exact)
+    const float sc = mx < 1e-30f ? 0x1p64f : 1.0f;
+    const float a = (mx > 0.f) ? (mn * sc) * rcp_approx(mx * sc) : 0.f;
     const float s = a * a;
     float p = 0x1.be6ae0p-8f;
     p = fmaf(p, s, -0x1.134924p-5f);
@@ -551,7 +554,10 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     // magnitude, Gaussian weight and angle: fast approximations (relative error ~1e-6), see header comment
     const float d2 = fmaf(dx, dx, dy * dy);
     const float wgt = fmaf(col_rot, col_rot, row_rot * row_rot);
-    const float mag = (d2 > 0.f ? d2 * rsqrt_approx(d2) : 0.f) * ex2_approx(wgt * (-0.125f * 1.44269504088896341f));  // exp(-2/4^2 * wgt), :859
+    // sqrt(d2) = d2 * rsqrt(d2); a denormal d2 (constant image regions) is scaled into the normal range first
+    const float d2s = d2 < 1e-30f ? d2 * 0x1p64f : d2;
+    const float root = (d2 > 0.f ? d2s * rsqrt_approx(d2s) : 0.f) * (d2 < 1e-30f ? 0x1p-32f : 1.0f);
+    const float mag = root * ex2_approx(wgt * (-0.125f * 1.44269504088896341f));  // exp(-2/4^2 * wgt), :859
     const float orient = fast_atan2_deg(dy, dx) - G.orientation;                   // :871
     const float obin = orient * (8.0f / 360.0f);
     const float row_floor = floorf(rb), col_floor = floorf(cbn), ori_floor = floorf(obin);

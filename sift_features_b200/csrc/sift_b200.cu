@@ -85,6 +85,7 @@ struct sb200_ctx {
     CUtensorMap tmap[2][MAX_OCT][N_LAYERS];
     CUtensorMap tmap_m[2][MAX_OCT][N_LAYERS];  // marching blur: (BW x 32) boxes
     bool march = true;                         // SB200_BLUR=tile selects the independent-tile TMA blur (debugging aid)
+    int seg_rows_override = 0;                 // SB200_SEG_ROWS: fixed segment height of the marching blur (tests)
     CUtensorMap tmap_ex[2][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
     bool tmap_ok[MAX_OCT] = {false};
     void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
@@ -469,6 +470,7 @@ int set_march_attr(sb200_ctx* ctx) {
 // rows per vertical segment of the marching blur: as tall as possible (the row pass of 2R halo rows is the
 // only redundant work) while the launch still holds several CTAs per resident slot
 int march_seg_rows(const sb200_ctx* ctx, int w, int h, uint32_t n) {
+    if (ctx->seg_rows_override > 0) return ctx->seg_rows_override;
     const long long strips = (w + 127) / 128;
     const long long target = 8LL * 2 * ctx->sm_count;
     const long long segs = std::max<long long>(1, (target + strips * n - 1) / (strips * n));
@@ -867,6 +869,8 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         {
             const char* e = getenv("SB200_BLUR");
             ctx->march = !(e && !strcmp(e, "tile"));
+            const char* sr = getenv("SB200_SEG_ROWS");
+            if (sr && atoi(sr) >= 32) ctx->seg_rows_override = atoi(sr) / 32 * 32;
         }
         CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));
         CU(cudaFuncSetAttribute(k_extrema_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));

@@ -89,6 +89,24 @@ def test_1080p_noise_full_size(sf, oracle):
     assert 6000 < len(res) < 12000
 
 
+@pytest.mark.parametrize("seg_rows", [512, 96])
+def test_blur_segment_heights(sf, oracle, monkeypatch, seg_rows):
+    """The marching blur cuts an octave into vertical segments whose height depends on the batch; a large batch
+    of 1080p images uses 512-row segments.  Same bit-exact pyramid whatever the segmentation."""
+    monkeypatch.setenv("SB200_SEG_ROWS", str(seg_rows))
+    _check_image(sf, oracle, noise_image(700, 650, 21))
+
+
+def test_flat_regions(sf, oracle):
+    """Saturated / constant blocks: every pixel of such a block passes the reference's extremum test with
+    ties (src/lib.rs:437-506) and dies in interpolate_extremum; the candidate list must still be the reference's."""
+    g = noise_image(300, 260, 31)
+    g[20:120, 30:150] = 255
+    g[150:240, 100:290] = 0
+    g[125:140, :] = 77
+    _check_image(sf, oracle, g)
+
+
 def test_edge_cases(sf, oracle):
     # constant image, tiny images (never scanned, src/lib.rs:315-317), 1-pixel image
     for g in [np.full((64, 64), 128, np.uint8), noise_image(4, 4, 1), noise_image(1, 1, 1), noise_image(3, 2, 1),
