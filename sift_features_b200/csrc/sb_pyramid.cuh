@@ -534,10 +534,11 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
                                                         const int src_layer, const int seg_rows) {
     using C = MarchCfg<L>;
     constexpr int R = C::R;
+    constexpr int STAGE_FLOATS = C::BH * C::BW, SLOT_FLOATS = C::BH * C::IPITCH;
     extern __shared__ __align__(1024) float smem_march[];
     __shared__ __align__(8) uint64_t bar[C::NSTG];
-    float* const stage = smem_march;                                  // NSTG x BH x BW (TMA box layout)
-    float* const inter = smem_march + C::NSTG * C::BH * C::BW;        // NSLOT x BH x IPITCH
+    float* const stage = smem_march;                               // NSTG x BH x BW (TMA box layout)
+    float* const inter = smem_march + C::NSTG * STAGE_FLOATS;      // NSLOT x BH x IPITCH
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * C::TW;
     const int ya = blockIdx.y * seg_rows;
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(C::BAND_BYTES) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-            ::"r"(smem_u32(stage + (b & 1) * C::BH * C::BW)), "l"(&tmap), "r"(tx0 - C::RA), "r"(in0 + b * C::BH),
+            ::"r"(smem_u32(stage + (b & 1) * STAGE_FLOATS)), "l"(&tmap), "r"(tx0 - C::RA), "r"(in0 + b * C::BH),
               "r"(src_layer), "r"(img), "r"(bar_a)
             : "memory");
     };
@@ -568,8 +569,8 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
         if (n_in > 1) issue(1);
     }
 
-    // ---- row pass of input band b: warp = the band's 32 rows x one 8-pixel segment ----
-    auto row_pass = [&](const int b) {
+    // ---- row pass of input band b (ring slot `slot`): warp = the band's 32 rows x one 8-pixel segment ----
+    auto row_pass = [&](const int b, const int slot) {
         {
             const uint32_t bar_a = smem_u32(&bar[b & 1]);
             const uint32_t parity = (uint32_t)(b >> 1) & 1u;
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
                     : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
             }
         }
-        float* const st = stage + (b & 1) * C::BH * C::BW;
+        float* const st = stage + (b & 1) * STAGE_FLOATS;
         const int band_y0 = in0 + b * C::BH;
         if (hedge) {  // block-uniform: box element (row, XO + col) holds image pixel (band_y0 + row, tx0 - R + col)
             for (int idx = tid; idx < C::BH * C::SW; idx += C::THREADS) {
@@ -593,11 +594,11 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
             }
             __syncthreads();
         }
-        const int slot = b % 3;
-        float* const ib = inter + slot * C::BH * C::IPITCH;
+        float* const ib = inter + slot * SLOT_FLOATS;
         const bool vedge = band_y0 < 0 || band_y0 + C::BH > h;                      // block-uniform
-        const int rows_needed = min(C::BH, yb + R - band_y0);
+        const int rows_needed = yb + R - band_y0;   // >= BH except in the last band
         const int row = lane;
+        if (row >= rows_needed) return;
         int srow = row;         // stage row this lane filters
         bool copy_prev = false; // the mirrored row belongs to the previous band: copy its row-pass result from the ring
         if (vedge) {
@@ -605,88 +606,108 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
             srow = yy - band_y0;
             copy_prev = srow < 0;
         }
+        const float* const srcrow = st + srow * C::BW;
+        float* const dstrow = ib + row * C::IPITCH;
+#pragma unroll 1
         for (int seg = warp; seg < C::TW / 8; seg += C::THREADS / 32) {
-            if (row >= rows_needed) continue;
-            float4* const ip = reinterpret_cast<float4*>(ib + row * C::IPITCH + seg * 8);
             float4 o0, o1;
             if (copy_prev) {
-                const float4* src = reinterpret_cast<const float4*>(inter + ((b + 2) % 3) * C::BH * C::IPITCH +
-                                                                    (srow + C::BH) * C::IPITCH + seg * 8);
+                const int pslot = slot == 0 ? 2 : slot - 1;
+                const float4* src = reinterpret_cast<const float4*>(inter + pslot * SLOT_FLOATS + (srow + C::BH) * C::IPITCH + seg * 8);
                 o0 = src[0]; o1 = src[1];
             } else {
                 float win[4 * C::NV4];
-                const float4* sp = reinterpret_cast<const float4*>(st + srow * C::BW + seg * 8);
+                const float4* sp = reinterpret_cast<const float4*>(srcrow + seg * 8);
 #pragma unroll
                 for (int v = 0; v < C::NV4; v++) {
                     float4 q = sp[v];
                     win[4 * v + 0] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
                 }
-                // packed arithmetic: outputs (2jp, 2jp+1) share one FFMA2 chain; the operand pair for tap i starts
-                // at window index XO + 2jp + i, which is an aligned register pair of `win` when even and comes
-                // from the one-float-shifted copy `sh` when odd
-                float2 sh[2 * C::NV4];
-#pragma unroll
-                for (int m = 0; 2 * m + 2 < 4 * C::NV4; m++) sh[m] = make_float2(win[2 * m + 1], win[2 * m + 2]);
+                // outputs (2jp, 2jp+1) share one accumulator pair.  The operands of tap i start at window index
+                // XO + 2jp + i: when that is even they are an aligned register pair and the step is one packed
+                // FFMA2; when it is odd the pair straddles two registers pairs, and two scalar FFMAs on the halves
+                // of the accumulator cost less than assembling the shifted pair (same FMA-pipe cycles, no MOVs)
                 float2 acc[4];
 #pragma unroll
                 for (int jp = 0; jp < 4; jp++) {
 #pragma unroll
                     for (int i = 0; i <= 2 * R; i++) {
                         const int sidx = C::XO + 2 * jp + i;
-                        const float2 in = (sidx & 1) ? sh[sidx >> 1] : make_float2(win[sidx], win[sidx + 1]);
-                        acc[jp] = (i == 0) ? mul2(in, c_taps2[L][0]) : fma2(in, c_taps2[L][i], acc[jp]);
+                        if ((sidx & 1) == 0) {
+                            const float2 in = make_float2(win[sidx], win[sidx + 1]);
+                            acc[jp] = (i == 0) ? mul2(in, c_taps2[L][0]) : fma2(in, c_taps2[L][i], acc[jp]);
+                        } else if (i == 0) {
+                            acc[jp] = make_float2(win[sidx] * c_taps[L][0], win[sidx + 1] * c_taps[L][0]);
+                        } else {
+                            acc[jp].x = fmaf(win[sidx], c_taps[L][i], acc[jp].x);
+                            acc[jp].y = fmaf(win[sidx + 1], c_taps[L][i], acc[jp].y);
+                        }
                     }
                 }
                 o0 = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
                 o1 = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
             }
+            float4* const ip = reinterpret_cast<float4*>(dstrow + seg * 8);
             ip[0] = o0; ip[1] = o1;
             if (slot == 0) {  // mirror of slot 0 behind slot 2
-                float4* const im = ip + 3 * C::BH * C::IPITCH / 4;
-                im[0] = o0; im[1] = o1;
+                ip[3 * SLOT_FLOATS / 4] = o0; ip[3 * SLOT_FLOATS / 4 + 1] = o1;
             }
         }
     };
 
-    // ---- column pass of output band jb: thread = two adjacent columns x PY consecutive rows, packed f32x2 ----
-    float* const dst = p.dst + (long long)img * p.img_stride;
-    float* const dec = DECIMATE ? p.dec + (long long)img * p.img_stride : nullptr;
-    auto col_pass = [&](const int jb) {
-        const int cy = tid / (C::TW / 2), xp = tid - cy * (C::TW / 2);
-        const int y0 = cy * C::PY;
+    // ---- column pass: thread = two adjacent columns x PY consecutive rows of the band, packed f32x2 ----
+    const int cy = tid / (C::TW / 2), xp = tid - cy * (C::TW / 2);
+    const int y0 = cy * C::PY;
+    const int gx = tx0 + 2 * xp;
+    const bool x_full = gx + 1 < w;
+    float* qband = p.dst + (long long)img * p.img_stride + (long long)(ya + y0) * p.pitch + gx;   // first output row of band 0
+    float* dband = nullptr;
+    if (DECIMATE) dband = p.dec + (long long)img * p.img_stride + (long long)((ya + y0) >> 1) * p.dec_pitch + (gx >> 1);
+    const float* const cbase = inter + y0 * C::IPITCH + 2 * xp;
+    // output band jb (ring slot `slot`; band jb+1 follows contiguously: slot 3 mirrors slot 0)
+    auto col_pass = [&](const int jb, const int slot) {
         const int gy0 = ya + jb * C::BH + y0;
-        if (gy0 >= yb) return;  // whole chunk below the segment (warp-uniform)
-        const int gx = tx0 + 2 * xp;
-        // ring row of output row y0 + j, tap offset i: band jb starts at its slot, band jb+1 follows contiguously
-        const float* const base = inter + (jb % 3) * C::BH * C::IPITCH + y0 * C::IPITCH + 2 * xp;
-        float2 c[C::PY + 2 * R];
+        if (gy0 < yb && gx < w) {  // else: whole chunk below the segment (warp-uniform) / columns right of the image
+            const float* const base = cbase + slot * SLOT_FLOATS;
+            float2 c[C::PY + 2 * R];
 #pragma unroll
-        for (int j = 0; j < C::PY + 2 * R; j++) c[j] = *reinterpret_cast<const float2*>(base + j * C::IPITCH);
+            for (int j = 0; j < C::PY + 2 * R; j++) c[j] = *reinterpret_cast<const float2*>(base + j * C::IPITCH);
+            float* q = qband;
+            const bool fast = x_full && gy0 + C::PY <= yb;
 #pragma unroll
-        for (int j = 0; j < C::PY; j++) {
-            float2 acc = mul2(c[j + R], c_taps2[L][R]);
+            for (int j = 0; j < C::PY; j++) {
+                float2 acc = mul2(c[j + R], c_taps2[L][R]);
 #pragma unroll
-            for (int i = 1; i <= R; i++) acc = fma2(add2(c[j + R + i], c[j + R - i]), c_taps2[L][R + i], acc);
-            const int gy = gy0 + j;
-            if (gy < yb && gx < w) {
-                float* q = dst + (long long)gy * p.pitch + gx;
-                if (gx + 1 < w) *reinterpret_cast<float2*>(q) = acc;
-                else q[0] = acc.x;
-                if (DECIMATE && !(gy & 1)) {   // gx is even
-                    const int dy = gy >> 1, dx = gx >> 1;
-                    if (dy < p.dec_h && dx < p.dec_w) dec[(long long)dy * p.dec_pitch + dx] = acc.x;
+                for (int i = 1; i <= R; i++) acc = fma2(add2(c[j + R + i], c[j + R - i]), c_taps2[L][R + i], acc);
+                if (fast) {
+                    *reinterpret_cast<float2*>(q) = acc;
+                } else if (gy0 + j < yb) {
+                    if (x_full) *reinterpret_cast<float2*>(q) = acc;
+                    else q[0] = acc.x;
                 }
+                if (DECIMATE && !(j & 1)) {   // ya, y0 and gx are even: output row gy0 + j is even
+                    const int dy = (gy0 + j) >> 1, dx = gx >> 1;
+                    if (gy0 + j < yb && dy < p.dec_h && dx < p.dec_w) dband[(long long)(j >> 1) * p.dec_pitch] = acc.x;
+                }
+                q += p.pitch;
             }
         }
+        qband += (long long)C::BH * p.pitch;
+        if (DECIMATE) dband += (long long)(C::BH / 2) * p.dec_pitch;
     };
 
-    row_pass(0);
+    row_pass(0, 0);
     __syncthreads();
+    int rslot = 1, cslot = 0;   // ring slots of band j+1 (row pass) and band j-1 (column pass)
     for (int j = 0; j <= n_out; j++) {
         // band j was row-passed before the last barrier: its stage buffer is free for band j+2
         if (tid == 0 && j + 2 < n_in) issue(j + 2);
-        if (j + 1 < n_in) row_pass(j + 1);
-        if (j >= 1) col_pass(j - 1);
+        if (j + 1 < n_in) row_pass(j + 1, rslot);
+        rslot = rslot == 2 ? 0 : rslot + 1;
+        if (j >= 1) {
+            col_pass(j - 1, cslot);
+            cslot = cslot == 2 ? 0 : cslot + 1;
+        }
         __syncthreads();
     }
 }
