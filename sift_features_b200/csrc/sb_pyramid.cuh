@@ -496,20 +496,28 @@ __global__ void __launch_bounds__(256, TmaCfg<L>::CTAS_PER_SM) k_blur_tma(const 
 // (2R+1)-row window is complete.  Compared with independent (64 + 2R)-row tiles this computes every row-pass
 // result once instead of (64 + 2R) / 64 times, keeps one band in flight per CTA at all times, and needs a
 // single __syncthreads per band.
-//   * ring: three 32-row slots (band b in slot b % 3) plus a fourth that mirrors slot 0, so the two bands a
-//     column-pass thread reads (b, b+1) are always contiguous and every smem offset is an immediate;
-//   * step j = { issue TMA of band j+2; row pass of band j+1; column pass of band j-1; barrier };
+//   * ring: three 32-row slots (band b in slot b % 3) followed by a mirror of the first 2R rows of slot 0, so
+//     the rows a column-pass thread reads (band b and the first 2R rows of band b+1) are always contiguous and
+//     every smem offset is an immediate;
+//   * step j = { issue TMA of band j+NSTG; row pass of band j+1; column pass of band j-1; barrier };
 //   * BORDER_REFLECT_101: left/right halo columns are patched in the stage buffer (edge strips only, as in
 //     k_blur_tma); rows above / below the image are row-passed from the stage row they mirror, or copied from
 //     the ring when that row belongs to the previous band.
 // Same arithmetic, operation for operation, as k_blur / k_blur_tma.
 // ---------------------------------------------------------------------------
+// strip width per tap set (measured on B200): the 17- and 21-tap kernels run faster as four 128-thread CTAs per SM
+// on 64-column strips, the others as two 256-thread CTAs on 128-column strips
+#ifndef SB_MARCH_TW
+#define SB_MARCH_TW(l) (((l) == 3 || (l) == 4) ? 64 : 128)
+#endif
+__host__ __device__ constexpr int march_tile_w(int l) { return SB_MARCH_TW(l); }
+
 template <int L>
 struct MarchCfg {
     static constexpr int R = blur_radius(L);
     static constexpr int RA = (R + 3) / 4 * 4;   // left halo of the box: a TMA box starts on a 16-byte boundary
     static constexpr int XO = RA - R;            // box column of the first element the filter needs
-    static constexpr int TW = 128, BH = 32;
+    static constexpr int TW = march_tile_w(L), BH = 32;
     static constexpr int SW = TW + 2 * R;
     static constexpr int WIN = XO + 8 + 2 * R;   // box floats read for 8 consecutive row-pass outputs (aligned start)
     static constexpr int NV4 = (WIN + 3) / 4;
@@ -518,11 +526,15 @@ struct MarchCfg {
     static constexpr int BW = 4 * ((BW4 % 2) ? BW4 : BW4 + 1);   // BW/4 odd: conflict-free LDS.128 with lanes <-> rows
     static constexpr int IPITCH = TW + 4;        // == 4 (mod 32)
     static constexpr int PY = 8;                 // output rows per column-pass thread (which owns two adjacent columns)
-    static constexpr int THREADS = 256;
-    static constexpr int NSTG = 2;
-    static constexpr int NSLOT = 4;
+    static constexpr int THREADS = (TW / 2) * (BH / PY);   // one column-pass task per thread
+    static constexpr int CTAS_PER_SM = 512 / THREADS;
+    // stage buffers (bands in flight + the one being filtered): the narrow tap sets are memory-bound and need two
+    // bands in flight per CTA to hide the TMA latency behind their short steps; the wide ones have no room for a
+    // third buffer next to two resident CTAs and do not need it
+    static constexpr int NSTG = (L <= 2) ? 3 : 2;
+    static constexpr int RING_ROWS = 3 * BH + 2 * R;   // three band slots + a mirror of the first 2R rows of slot 0
     static constexpr uint32_t BAND_BYTES = (uint32_t)BH * BW * sizeof(float);
-    static constexpr size_t SMEM = (size_t)NSTG * BAND_BYTES + (size_t)NSLOT * BH * IPITCH * sizeof(float);
+    static constexpr size_t SMEM = (size_t)NSTG * BAND_BYTES + (size_t)RING_ROWS * IPITCH * sizeof(float);
     static_assert(BW >= XO + SW && (BW / 4) % 2 == 1 && TW - 8 + 4 * NV4 <= BW && BW <= 256, "box width");
     static_assert(BAND_BYTES % 128 == 0, "128-byte aligned stage buffers");
     static_assert(2 * R + 1 <= BH && PY + 2 * R <= 2 * BH, "window spans at most two bands");
@@ -530,7 +542,7 @@ struct MarchCfg {
 };
 
 template <int L, bool DECIMATE>
-__global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
+__global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM) k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
                                                         const int src_layer, const int seg_rows) {
     using C = MarchCfg<L>;
     constexpr int R = C::R;
@@ -538,7 +550,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
     extern __shared__ __align__(1024) float smem_march[];
     __shared__ __align__(8) uint64_t bar[C::NSTG];
     float* const stage = smem_march;                               // NSTG x BH x BW (TMA box layout)
-    float* const inter = smem_march + C::NSTG * STAGE_FLOATS;      // NSLOT x BH x IPITCH
+    float* const inter = smem_march + C::NSTG * STAGE_FLOATS;      // RING_ROWS x IPITCH
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * C::TW;
     const int ya = blockIdx.y * seg_rows;
@@ -555,25 +567,26 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](const int b) {
-        const uint32_t bar_a = smem_u32(&bar[b & 1]);
+    auto issue = [&](const int b, const int stg) {   // band b into stage buffer stg == b % NSTG
+        const uint32_t bar_a = smem_u32(&bar[stg]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(C::BAND_BYTES) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-            ::"r"(smem_u32(stage + (b & 1) * STAGE_FLOATS)), "l"(&tmap), "r"(tx0 - C::RA), "r"(in0 + b * C::BH),
+            ::"r"(smem_u32(stage + stg * STAGE_FLOATS)), "l"(&tmap), "r"(tx0 - C::RA), "r"(in0 + b * C::BH),
               "r"(src_layer), "r"(img), "r"(bar_a)
             : "memory");
     };
     if (tid == 0) {
-        issue(0);
-        if (n_in > 1) issue(1);
+#pragma unroll
+        for (int b = 0; b < C::NSTG; b++)
+            if (b < n_in) issue(b, b);
     }
 
-    // ---- row pass of input band b (ring slot `slot`): warp = the band's 32 rows x one 8-pixel segment ----
-    auto row_pass = [&](const int b, const int slot) {
+    // ---- row pass of input band b (stage buffer stg, its mbarrier at `parity`; ring slot `slot`):
+    //      warp = the band's 32 rows x one 8-pixel segment ----
+    auto row_pass = [&](const int b, const int stg, const uint32_t parity, const int slot) {
         {
-            const uint32_t bar_a = smem_u32(&bar[b & 1]);
-            const uint32_t parity = (uint32_t)(b >> 1) & 1u;
+            const uint32_t bar_a = smem_u32(&bar[stg]);
             uint32_t done = 0;
             while (!done) {
                 asm volatile(
@@ -581,7 +594,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
                     : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
             }
         }
-        float* const st = stage + (b & 1) * STAGE_FLOATS;
+        float* const st = stage + stg * STAGE_FLOATS;
         const int band_y0 = in0 + b * C::BH;
         if (hedge) {  // block-uniform: box element (row, XO + col) holds image pixel (band_y0 + row, tx0 - R + col)
             for (int idx = tid; idx < C::BH * C::SW; idx += C::THREADS) {
@@ -649,7 +662,7 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
             }
             float4* const ip = reinterpret_cast<float4*>(dstrow + seg * 8);
             ip[0] = o0; ip[1] = o1;
-            if (slot == 0) {  // mirror of slot 0 behind slot 2
+            if (slot == 0 && row < 2 * R) {  // mirror of the head of slot 0 behind slot 2
                 ip[3 * SLOT_FLOATS / 4] = o0; ip[3 * SLOT_FLOATS / 4 + 1] = o1;
             }
         }
@@ -696,13 +709,18 @@ __global__ void __launch_bounds__(256, 2) k_blur_march(const __grid_constant__ C
         if (DECIMATE) dband += (long long)(C::BH / 2) * p.dec_pitch;
     };
 
-    row_pass(0, 0);
+    row_pass(0, 0, 0u, 0);
     __syncthreads();
     int rslot = 1, cslot = 0;   // ring slots of band j+1 (row pass) and band j-1 (column pass)
+    int fstg = 0;               // stage buffer of band j (free again), == j % NSTG
+    int rstg = 1;               // stage buffer of band j+1, == (j+1) % NSTG
+    uint32_t rpar = 0;          // ... and the phase of its mbarrier, == ((j+1) / NSTG) & 1
     for (int j = 0; j <= n_out; j++) {
-        // band j was row-passed before the last barrier: its stage buffer is free for band j+2
-        if (tid == 0 && j + 2 < n_in) issue(j + 2);
-        if (j + 1 < n_in) row_pass(j + 1, rslot);
+        // band j was row-passed before the last barrier: its stage buffer is free for band j+NSTG
+        if (tid == 0 && j + C::NSTG < n_in) issue(j + C::NSTG, fstg);
+        fstg = fstg == C::NSTG - 1 ? 0 : fstg + 1;
+        if (j + 1 < n_in) row_pass(j + 1, rstg, rpar, rslot);
+        if (rstg == C::NSTG - 1) { rstg = 0; rpar ^= 1u; } else rstg++;
         rslot = rslot == 2 ? 0 : rslot + 1;
         if (j >= 1) {
             col_pass(j - 1, cslot);

@@ -472,7 +472,7 @@ int set_march_attr(sb200_ctx* ctx) {
 int march_seg_rows(const sb200_ctx* ctx, int w, int h, uint32_t n) {
     if (ctx->seg_rows_override > 0) return ctx->seg_rows_override;
     const long long strips = (w + 127) / 128;
-    const long long target = 8LL * 2 * ctx->sm_count;
+    const long long target = 8LL * 2 * ctx->sm_count;  // a few waves of resident CTAs
     const long long segs = std::max<long long>(1, (target + strips * n - 1) / (strips * n));
     long long rows = ((h + segs - 1) / segs + 31) / 32 * 32;
     rows = std::min<long long>(std::max<long long>(rows, 64), 512);
