@@ -261,6 +261,10 @@ struct UpsampleParams {
 };
 
 __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
+    // v / 255 for the 256 possible pixel values (the IEEE division itself, done once per CTA instead of 8x per thread)
+    __shared__ float s_norm[256];
+    s_norm[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;      // output columns 4k .. 4k+3
     const int y = (int)blockIdx.y - 1;                        // input row pair (y, y+1); y = -1 yields output row 0
     const long long img = blockIdx.z;
@@ -272,8 +276,8 @@ __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const int x = min(max(2 * k - 1 + c, 0), W - 1);
-        a[0][c] = (float)in[(long long)y0 * p.in_stride + x] / 255.0f;
-        a[1][c] = (float)in[(long long)y1 * p.in_stride + x] / 255.0f;
+        a[0][c] = s_norm[in[(long long)y0 * p.in_stride + x]];
+        a[1][c] = s_norm[in[(long long)y1 * p.in_stride + x]];
     }
     // horizontal pass: out col 4k = lerp(c0, c1, .75), 4k+1 = lerp(c1, c2, .25), 4k+2 = lerp(c1, c2, .75), 4k+3 = lerp(c2, c3, .25)
     float hrow[2][4];
