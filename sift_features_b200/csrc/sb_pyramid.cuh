@@ -794,6 +794,7 @@ struct ExWarp {
     int ls;                    // layer stride in floats
     int h, pitch, mask_pitch, lane;
     uint32_t ok;               // bit k: the lane's column k can hold candidates (IMAGE_BORDER, halo lanes excluded)
+    bool coherent;             // the layers were written earlier in this launch (k_tail): no read-only-path loads
 };
 
 __device__ __forceinline__ const float2* ex_addr(const float* base, const int off) {
@@ -805,7 +806,10 @@ __device__ __forceinline__ const float2* ex_addr(const float* base, const int of
 __device__ __forceinline__ void ex_load(const ExWarp& W, const int r, float2* gv) {
     const int roff = min(max(r, 0), W.h - 1) * W.pitch;
 #pragma unroll
-    for (int l = 0; l < N_LAYERS; l++) gv[l] = __ldg(ex_addr(W.g, roff + l * W.ls));
+    for (int l = 0; l < N_LAYERS; l++) {
+        const float2* q = ex_addr(W.g, roff + l * W.ls);
+        gv[l] = W.coherent ? *q : __ldg(q);
+    }
 }
 
 // (v > 0 and v >= Mx) or (v < 0 and v <= mn), gated by `ok`, without short-circuit branches
@@ -883,6 +887,7 @@ __device__ __forceinline__ void ex_step(const ExWarp& W, ExState& S, const int r
 __device__ __forceinline__ void ex_setup(ExWarp& W, const ExtremaParams& p, const int strip, const int lane, const long long img) {
     W.h = p.h; W.pitch = p.pitch; W.mask_pitch = p.mask_pitch; W.lane = lane;
     W.ls = (int)p.layer_stride;
+    W.coherent = false;
     const int x0 = strip * EX_SPAN - 2 + 2 * lane;
     // column pairs outside [0, pitch-2] load a clamped pair instead: only halo lanes and columns inside the
     // IMAGE_BORDER margin can be affected, and neither they nor their neighbours can be candidates
@@ -895,13 +900,13 @@ __device__ __forceinline__ void ex_setup(ExWarp& W, const ExtremaParams& p, cons
            (inner & (x0 + 1 >= IMAGE_BORDER) & (x0 + 1 < p.w - IMAGE_BORDER) ? 2u : 0u);
 }
 
+// one warp: strip `strip`, centre rows [y0, y0 + EX_ROWS) of image `img`
 template <bool KEEP_FLAT>
-__global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema(const ExtremaParams p) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int y0 = (blockIdx.y * EX_WARPS + warp) * EX_ROWS;
-    if (y0 >= p.h) return;
+__device__ __forceinline__ void ex_strip(const ExtremaParams& p, const int strip, const int y0, const int lane,
+                                         const long long img, const bool coherent) {
     ExWarp W;
-    ex_setup(W, p, blockIdx.x, lane, blockIdx.z);
+    ex_setup(W, p, strip, lane, img);
+    W.coherent = coherent;
     ExState S;
     const int r_end = min(y0 + EX_ROWS, W.h);  // centre rows [y0, r_end): image rows y0-1 .. r_end
     float2 gv[N_LAYERS];
@@ -913,6 +918,14 @@ __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema(const ExtremaParam
         if (r + 1 <= r_end) ex_step<0, true, KEEP_FLAT>(W, S, r + 1, gv);
         if (r + 2 <= r_end) ex_step<1, true, KEEP_FLAT>(W, S, r + 2, gv);
     }
+}
+
+template <bool KEEP_FLAT>
+__global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema(const ExtremaParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y0 = (blockIdx.y * EX_WARPS + warp) * EX_ROWS;
+    if (y0 >= p.h) return;
+    ex_strip<KEEP_FLAT>(p, blockIdx.x, y0, lane, blockIdx.z, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -1005,6 +1018,103 @@ __global__ void __launch_bounds__(32 * EX_WARPS, 4) k_extrema_tma(const __grid_c
         __syncwarp();  // every lane has consumed the stage: hand it back to the copy engine
         if (lane == 0 && s + EXT_NS < n_stages) issue(s + EXT_NS, slot);
         if (++slot == EXT_NS) { slot = 0; phase ^= 1u; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Tail of the pyramid: every octave small enough for a whole layer to sit in shared memory (w*h <= TAIL_MAX_PX)
+// is processed by ONE CTA per image in ONE launch -- five blurs, decimation into the next octave and the
+// DoG/extrema scan, octave after octave -- instead of six launch-latency-bound kernels per octave.  Same
+// arithmetic as k_blur (row pass left-to-right FMA chain, column pass symmetric-folded chain,
+// BORDER_REFLECT_101) and the same extrema code as k_extrema (generic loads, coherent path: the layers were
+// written by this CTA).
+// ---------------------------------------------------------------------------
+constexpr int TAIL_MAX_PX = 9216;     // 36 KB per buffer, e.g. 128 x 72
+constexpr int TAIL_THREADS = 512;
+constexpr size_t TAIL_SMEM = 2 * (size_t)TAIL_MAX_PX * sizeof(float);
+
+struct TailParams {
+    PyrLayout L;
+    int o_first;                 // first octave of the tail
+    float* gauss;                // Gaussian arena, image 0
+    uint32_t* mask;              // mask arena, image 0
+    uint32_t* rows;              // row counters, image 0
+};
+
+template <int LI>
+__device__ __forceinline__ void tail_blur(const float* __restrict__ a /* smem w x h */, float* __restrict__ b /* smem */,
+                                          float* __restrict__ a_next /* smem: becomes the next source */,
+                                          float* __restrict__ dst, float* __restrict__ dec, const int w, const int h,
+                                          const int pitch, const int dec_w, const int dec_h, const int dec_pitch) {
+    constexpr int R = blur_radius(LI);
+    const int n = w * h;
+    for (int idx = threadIdx.x; idx < n; idx += TAIL_THREADS) {
+        const int y = idx / w, x = idx - y * w;
+        const float* row = a + y * w;
+        float acc = row[reflect101(x - R, w)] * c_taps[LI][0];
+#pragma unroll
+        for (int i = 1; i <= 2 * R; i++) acc = fmaf(row[reflect101(x - R + i, w)], c_taps[LI][i], acc);
+        b[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n; idx += TAIL_THREADS) {
+        const int y = idx / w, x = idx - y * w;
+        float acc = b[idx] * c_taps[LI][R];
+#pragma unroll
+        for (int i = 1; i <= R; i++)
+            acc = fmaf(b[reflect101(y + i, h) * w + x] + b[reflect101(y - i, h) * w + x], c_taps[LI][R + i], acc);
+        a_next[idx] = acc;
+        dst[(long long)y * pitch + x] = acc;
+        if (dec && !(y & 1) && !(x & 1)) {
+            const int dy = y >> 1, dx = x >> 1;
+            if (dy < dec_h && dx < dec_w) dec[(long long)dy * dec_pitch + dx] = acc;
+        }
+    }
+    __syncthreads();
+}
+
+template <bool KEEP_FLAT>
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
+    extern __shared__ __align__(16) float tail_smem[];
+    float* const a = tail_smem;
+    float* const b = tail_smem + TAIL_MAX_PX;
+    const long long img = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* const gimg = p.gauss + img * p.L.img_floats;
+    for (int o = p.o_first; o < p.L.n_oct; o++) {
+        const OctLayout& ol = p.L.o[o];
+        const int w = ol.w, h = ol.h;
+        if (w < 1 || h < 1) break;
+        float* const g0 = gimg + ol.off;
+        // layer 0: written by the previous octave's decimation (an earlier launch for o_first, this CTA otherwise)
+        for (int idx = tid; idx < w * h; idx += TAIL_THREADS) {
+            const int y = idx / w, x = idx - y * w;
+            a[idx] = g0[(long long)y * ol.pitch + x];
+        }
+        __syncthreads();
+        float* dec = nullptr;
+        int dw = 0, dh = 0, dp = 0;
+        if (o + 1 < p.L.n_oct && p.L.o[o + 1].w >= 1 && p.L.o[o + 1].h >= 1) {
+            dec = gimg + p.L.o[o + 1].off; dw = p.L.o[o + 1].w; dh = p.L.o[o + 1].h; dp = p.L.o[o + 1].pitch;
+        }
+        tail_blur<1>(a, b, a, g0 + 1 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<2>(a, b, a, g0 + 2 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<3>(a, b, a, g0 + 3 * ol.layer_stride, dec, w, h, ol.pitch, dw, dh, dp);
+        tail_blur<4>(a, b, a, g0 + 4 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<5>(a, b, a, g0 + 5 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        if (ol.scanned) {
+            ExtremaParams e;
+            e.gauss = p.gauss + ol.off; e.img_stride = p.L.img_floats; e.layer_stride = ol.layer_stride;
+            e.w = w; e.h = h; e.pitch = ol.pitch;
+            e.mask = p.mask + ol.mask_off; e.mask_img_stride = p.L.img_mask_words; e.mask_pitch = ol.mask_pitch;
+            e.rows = p.rows + ol.row_base; e.rows_img_stride = p.L.img_rows;
+            const int strips = ex_strips(w), blocks = (h + EX_ROWS - 1) / EX_ROWS;
+            for (int t = warp; t < strips * blocks; t += TAIL_THREADS / 32) {
+                const int strip = t % strips, y0 = (t / strips) * EX_ROWS;
+                ex_strip<KEEP_FLAT>(e, strip, y0, lane, img, true);
+            }
+        }
+        __syncthreads();
     }
 }
 

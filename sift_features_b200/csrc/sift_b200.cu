@@ -86,6 +86,7 @@ struct sb200_ctx {
     CUtensorMap tmap_m[2][MAX_OCT][N_LAYERS];  // marching blur: (BW x 32) boxes
     bool march = true;                         // SB200_BLUR=tile selects the independent-tile TMA blur (debugging aid)
     int seg_rows_override = 0;                 // SB200_SEG_ROWS: fixed segment height of the marching blur (tests)
+    bool tail = true;                          // SB200_TAIL=0: per-layer launches for the small octaves too (debugging aid)
     CUtensorMap tmap_ex[2][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
     bool tmap_ok[MAX_OCT] = {false};
     void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
@@ -499,6 +500,14 @@ void launch_extrema(sb200_ctx* ctx, cudaStream_t st, int slot, int o, const Extr
     }
 }
 
+// first octave of the fused tail (k_tail): every octave from there on fits a shared-memory buffer
+int tail_first_octave(const sb200_ctx* ctx) {
+    if (!ctx->tail) return ctx->L.n_oct;
+    int o = ctx->L.n_oct;
+    while (o > 1 && (long long)ctx->L.o[o - 1].w * ctx->L.o[o - 1].h <= TAIL_MAX_PX) o--;   // octave 0 always takes the seed path
+    return o;
+}
+
 // Gaussian scale space + DoG/extrema masks for the n images staged in slot.d_in
 int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, uint32_t in_stride,
                     uint64_t in_img_stride, const uint8_t* d_in) {
@@ -531,7 +540,8 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             count_launch(ctx, SB200_STAGE_SEED);
         }
     }
-    for (int o = 0; o < L.n_oct; o++) {
+    const int o_tail = tail_first_octave(ctx);
+    for (int o = 0; o < o_tail; o++) {
         const OctLayout& ol = L.o[o];
         if (ol.w < 1 || ol.h < 1) continue;
         {
@@ -604,6 +614,15 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             launch_extrema<false>(ctx, st, s.index, o, e, n);
             count_launch(ctx, SB200_STAGE_EXTREMA);
         }
+    }
+    if (o_tail < L.n_oct && L.o[o_tail].w >= 1 && L.o[o_tail].h >= 1) {
+        // blurs + decimation + extrema of all the remaining (small) octaves: one CTA per image, one launch
+        StageScope sc(ctx, st, SB200_STAGE_BLUR);
+        TailParams t{};
+        t.L = L; t.o_first = o_tail;
+        t.gauss = s.d_gauss; t.mask = s.d_mask; t.rows = s.d_rows;
+        k_tail<false><<<n, TAIL_THREADS, TAIL_SMEM, st>>>(t);
+        count_launch(ctx, SB200_STAGE_BLUR);
     }
     CU(cudaGetLastError());
     return SB200_OK;
@@ -869,6 +888,9 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         {
             const char* e = getenv("SB200_BLUR");
             ctx->march = !(e && !strcmp(e, "tile"));
+            const char* tl = getenv("SB200_TAIL");
+            ctx->tail = !(tl && !strcmp(tl, "0"));
+            CU(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM));
             const char* sr = getenv("SB200_SEG_ROWS");
             if (sr && atoi(sr) >= 32) ctx->seg_rows_override = atoi(sr) / 32 * 32;
         }
