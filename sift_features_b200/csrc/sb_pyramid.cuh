@@ -1051,18 +1051,31 @@ __device__ __forceinline__ void tail_blur(const float* __restrict__ a /* smem w 
     for (int idx = threadIdx.x; idx < n; idx += TAIL_THREADS) {
         const int y = idx / w, x = idx - y * w;
         const float* row = a + y * w;
-        float acc = row[reflect101(x - R, w)] * c_taps[LI][0];
+        float acc;
+        if (x >= R && x + R < w) {   // interior: no border arithmetic
+            const float* q = row + x - R;
+            acc = q[0] * c_taps[LI][0];
 #pragma unroll
-        for (int i = 1; i <= 2 * R; i++) acc = fmaf(row[reflect101(x - R + i, w)], c_taps[LI][i], acc);
+            for (int i = 1; i <= 2 * R; i++) acc = fmaf(q[i], c_taps[LI][i], acc);
+        } else {
+            acc = row[reflect101(x - R, w)] * c_taps[LI][0];
+#pragma unroll
+            for (int i = 1; i <= 2 * R; i++) acc = fmaf(row[reflect101(x - R + i, w)], c_taps[LI][i], acc);
+        }
         b[idx] = acc;
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < n; idx += TAIL_THREADS) {
         const int y = idx / w, x = idx - y * w;
         float acc = b[idx] * c_taps[LI][R];
+        if (y >= R && y + R < h) {
 #pragma unroll
-        for (int i = 1; i <= R; i++)
-            acc = fmaf(b[reflect101(y + i, h) * w + x] + b[reflect101(y - i, h) * w + x], c_taps[LI][R + i], acc);
+            for (int i = 1; i <= R; i++) acc = fmaf(b[idx + i * w] + b[idx - i * w], c_taps[LI][R + i], acc);
+        } else {
+#pragma unroll
+            for (int i = 1; i <= R; i++)
+                acc = fmaf(b[reflect101(y + i, h) * w + x] + b[reflect101(y - i, h) * w + x], c_taps[LI][R + i], acc);
+        }
         a_next[idx] = acc;
         dst[(long long)y * pitch + x] = acc;
         if (dec && !(y & 1) && !(x & 1)) {
