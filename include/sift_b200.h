@@ -66,6 +66,12 @@ typedef struct {
     float x, y, scale, orientation;
 } sb200_desc_in;
 
+/* one mutual nearest-neighbour pair of sb200_match_descriptors (cv::DMatch of examples/sift-match.rs:30-35):
+ * row indices into the query / train descriptor matrices and the squared L2 distance (exact integer) */
+typedef struct {
+    uint32_t query, train, dist2;
+} sb200_dmatch;
+
 /* initial discrete extremum, src/lib.rs:324-332 (parity tests) */
 typedef struct {
     int32_t octave, scale, y, x;
@@ -148,6 +154,20 @@ int sb200_compute_descriptors(sb200_ctx* ctx, const float* img, uint32_t w, uint
 int sb200_compute_descriptors_device(sb200_ctx* ctx, const float* d_img, uint32_t w, uint32_t h,
                                      uint32_t stride, const sb200_desc_in* d_kps, uint64_t n,
                                      uint8_t* d_out);
+
+/* ---- descriptor matching: the step after the path in the reference's examples ----
+ * examples/sift-match.rs:30-35 and examples/opencv-cross-match.rs:34-43 hand the (N,128) u8 descriptor
+ * matrices to OpenCV's BFMatcher(NORM_L2, crossCheck = true).  sb200_match_descriptors computes the same mutual nearest
+ * neighbours on the GPU (u8 x u8 Gram matrix on the tensor cores, exact integer distances): for every query
+ * row the train row with the smallest squared L2 distance (smallest index on ties), kept when the query row
+ * is in turn the nearest of that train row.  Matches are written in ascending query order; *n_out receives
+ * their number (SB200_E_CAPACITY if it exceeds cap; n_query always suffices). */
+int sb200_match_descriptors(sb200_ctx* ctx, const uint8_t* query, uint64_t n_query, const uint8_t* train, uint64_t n_train,
+                sb200_dmatch* out, uint64_t cap, uint64_t* n_out);
+/* device-pointer variant: descriptor matrices already in device memory (16-byte aligned, e.g. the
+ * d_descriptors of sb200_device_result); `out` is host memory */
+int sb200_match_descriptors_device(sb200_ctx* ctx, const uint8_t* d_query, uint64_t n_query, const uint8_t* d_train,
+                       uint64_t n_train, sb200_dmatch* out, uint64_t cap, uint64_t* n_out);
 
 /* ---- multi-GPU: contiguous shards of a batch over several contexts ------
  * One host thread per context; image i goes to context i / ceil(n/n_ctx); the

@@ -205,3 +205,31 @@ def compute_descriptor(img: np.ndarray, x: float, y: float, scale: float, orient
     out = np.zeros(128, np.uint8)
     lib().so_compute_descriptor(img, img.shape[1], img.shape[0], x, y, scale, orientation, out)
     return out
+
+
+def match_cross_check(query: np.ndarray, train: np.ndarray) -> np.ndarray:
+    """What examples/sift-match.rs:30-35 and examples/opencv-cross-match.rs:34-43 ask of OpenCV:
+    BFMatcher(NORM_L2, crossCheck=true).match(query, train) over (N,128) u8 descriptor matrices -- for every query
+    row the nearest train row, kept when the query row is in turn the nearest of that train row.  Exact integer
+    squared distances; ties resolve to the smallest index.  Returns rows (query, train, dist2), ascending query."""
+    q = np.ascontiguousarray(query, np.uint8).reshape(-1, 128).astype(np.int64)
+    t = np.ascontiguousarray(train, np.uint8).reshape(-1, 128).astype(np.int64)
+    out = np.zeros((0, 3), np.int64)
+    if len(q) == 0 or len(t) == 0:
+        return out
+    best_q = np.empty(len(q), np.int64)
+    best_d = np.empty(len(q), np.int64)
+    col_min = np.full(len(t), np.iinfo(np.int64).max)
+    col_arg = np.zeros(len(t), np.int64)
+    tn = (t * t).sum(1)
+    for s in range(0, len(q), 2048):                      # blocked so that 100k x 100k stays in memory
+        blk = q[s:s + 2048]
+        d = (blk * blk).sum(1)[:, None] + tn[None, :] - 2 * (blk @ t.T)
+        best_q[s:s + len(blk)] = d.argmin(1)
+        best_d[s:s + len(blk)] = d.min(1)
+        cm, ca = d.min(0), d.argmin(0) + s
+        upd = cm < col_min                                # strict: earlier blocks (smaller query index) win ties
+        col_min[upd], col_arg[upd] = cm[upd], ca[upd]
+    keep = col_arg[best_q] == np.arange(len(q))
+    idx = np.nonzero(keep)[0]
+    return np.stack([idx, best_q[idx], best_d[idx]], 1)

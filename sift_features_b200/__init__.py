@@ -35,7 +35,7 @@ from . import _ffi
 __all__ = [
     "KeyPoint", "SiftResult", "PrecomputedImages", "OpenCVProcessing", "ImageprocProcessing", "Extractor",
     "SiftError", "sift", "sift_with_processing", "precompute_images", "sift_with_precomputed",
-    "compute_descriptor", "compute_descriptors", "sift_batch", "KEYPOINT_DTYPE",
+    "compute_descriptor", "compute_descriptors", "sift_batch", "match", "MATCH_DTYPE", "KEYPOINT_DTYPE",
 ]
 
 #: layout of sb200_keypoint == the crate's KeyPoint (src/lib.rs:48-56)
@@ -44,6 +44,7 @@ SIFT_KEYPOINT_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angl
                                 ("octave", "i4"), ("scale", "i4")])
 CANDIDATE_DTYPE = np.dtype([("octave", "i4"), ("scale", "i4"), ("y", "i4"), ("x", "i4")])
 DESC_IN_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("scale", "f4"), ("orientation", "f4")])
+MATCH_DTYPE = np.dtype([("queryIdx", "i4"), ("trainIdx", "i4"), ("distance", "f4")])   # cv::DMatch fields
 STAGE_NAMES = ("seed", "blur", "extrema", "refine", "orient", "descriptor", "top_blur")
 
 
@@ -231,6 +232,22 @@ class Extractor:
                                                         img.shape[1], k.ctypes.data, len(k), out.ctypes.data))
         return out
 
+    def match(self, query_descriptors, train_descriptors) -> np.ndarray:
+        """Mutual nearest neighbours of two (N,128) u8 descriptor matrices -- what the reference's examples get
+        from OpenCV's BFMatcher(NORM_L2, crossCheck=True).match(query, train) (examples/sift-match.rs:30-35).
+        Returns MATCH_DTYPE rows (queryIdx, trainIdx, distance) in ascending query order."""
+        q = np.ascontiguousarray(query_descriptors, np.uint8).reshape(-1, 128)
+        t = np.ascontiguousarray(train_descriptors, np.uint8).reshape(-1, 128)
+        raw = np.zeros(len(q), np.dtype([("query", np.uint32), ("train", np.uint32), ("dist2", np.uint32)]))
+        n = C.c_uint64()
+        self._check(self._lib.sb200_match_descriptors(self._h, q.ctypes.data, len(q), t.ctypes.data, len(t), raw.ctypes.data,
+                                          len(raw), C.byref(n)))
+        raw = raw[: n.value]
+        out = np.zeros(len(raw), MATCH_DTYPE)
+        out["queryIdx"], out["trainIdx"] = raw["query"], raw["train"]
+        out["distance"] = np.sqrt(raw["dist2"].astype(np.float64)).astype(np.float32)
+        return out
+
     # -- parity / debug views ------------------------------------------
     def last_candidates(self) -> np.ndarray:
         n = C.c_uint64()
@@ -337,6 +354,11 @@ def precompute_images(img, device: int = 0) -> PrecomputedImages:
 def sift_with_precomputed(pre: PrecomputedImages, features_limit: Optional[int] = None) -> SiftResult:
     """src/lib.rs:147."""
     return pre.extractor.sift_with_precomputed(features_limit)
+
+
+def match(query_descriptors, train_descriptors, device: int = 0) -> np.ndarray:
+    """BFMatcher(NORM_L2, crossCheck=True).match(query, train) of examples/sift-match.rs:30-35 on the GPU."""
+    return _extractor(8, 8, 1, device).match(query_descriptors, train_descriptors)
 
 
 def compute_descriptors(img_f32, keypoints, device: int = 0) -> np.ndarray:

@@ -23,12 +23,14 @@
 #include "../../include/sift_b200.h"
 #include "sb_common.cuh"
 #include "sb_keypoints.cuh"
+#include "sb_match.cuh"
 #include "sb_pyramid.cuh"
 
 using namespace sb;
 
 static_assert(sizeof(OutKeyPoint) == sizeof(sb200_keypoint), "keypoint layout");
 static_assert(sizeof(DescIn) == sizeof(sb200_desc_in), "desc_in layout");
+static_assert(sizeof(MatchOut) == sizeof(sb200_dmatch), "match layout");
 
 namespace {
 
@@ -112,6 +114,15 @@ struct sb200_ctx {
     DescIn* d_dkps = nullptr;
     uint8_t* d_ddesc = nullptr;
     size_t dkps_cap = 0;
+    // matcher scratch (grow-only)
+    uint8_t* d_mdesc[2] = {nullptr, nullptr};        // query / train descriptors
+    uint32_t* d_mnorm[2] = {nullptr, nullptr};
+    uint32_t* d_mnbp[2] = {nullptr, nullptr};
+    unsigned long long* d_mbest[2] = {nullptr, nullptr};
+    size_t m_cap[2] = {0, 0};
+    MatchOut* d_mout = nullptr;
+    size_t mout_cap = 0;
+    uint32_t* d_mcount = nullptr;
     // measurement
     bool profiling = false;
     std::vector<StageEvents> pending;
@@ -894,6 +905,7 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
             const char* sr = getenv("SB200_SEG_ROWS");
             if (sr && atoi(sr) >= 32) ctx->seg_rows_override = atoi(sr) / 32 * 32;
         }
+        CU(cudaFuncSetAttribute(k_match_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
         CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));
         CU(cudaFuncSetAttribute(k_extrema_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));
         CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -935,6 +947,8 @@ void sb200_destroy(sb200_ctx* ctx) {
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     cudaFreeHost(ctx->h_offsets); cudaFreeHost(ctx->h_kps); cudaFreeHost(ctx->h_desc);
     cudaFree(ctx->d_dimg); cudaFree(ctx->d_dkps); cudaFree(ctx->d_ddesc); cudaFree(ctx->d_flush);
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->d_mdesc[i]); cudaFree(ctx->d_mnorm[i]); cudaFree(ctx->d_mnbp[i]); cudaFree(ctx->d_mbest[i]); }
+    cudaFree(ctx->d_mout); cudaFree(ctx->d_mcount);
     delete ctx;
 }
 
@@ -1288,6 +1302,110 @@ int sb200_extract_batch_multi(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint
     ctx->res_n = pos;
     fill_result(ctx, n, out);
     return SB200_OK;
+}
+
+// ---- descriptor matching (examples/sift-match.rs:30-35: BFMatcher(NORM_L2, crossCheck = true)) -----------------
+namespace {
+int encode_desc_map(sb200_ctx* ctx, CUtensorMap* tm, const uint8_t* d, uint64_t n, uint32_t box_rows) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)DESC_SIZE, (cuuint64_t)n};
+    const cuuint64_t gstr[1] = {(cuuint64_t)DESC_SIZE};
+    const cuuint32_t box[2] = {(cuuint32_t)DESC_SIZE, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode_fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)d, gdim, gstr, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SB200_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a descriptor matrix", (int)r);
+    return SB200_OK;
+}
+}  // namespace
+
+int sb200_match_descriptors_device(sb200_ctx* ctx, const uint8_t* d_query, uint64_t n_query, const uint8_t* d_train, uint64_t n_train,
+                       sb200_dmatch* out, uint64_t cap, uint64_t* n_out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!n_out || (cap && !out) || (n_query && !d_query) || (n_train && !d_train) || n_query > 0x7fffffffull ||
+        n_train > 0x7fffffffull)
+        return fail(ctx, SB200_E_INVALID, "bad arguments to match");
+    CU(cudaSetDevice(ctx->device));
+    *n_out = 0;
+    if (n_query == 0 || n_train == 0) return SB200_OK;
+    if (((uintptr_t)d_query | (uintptr_t)d_train) & 15) return fail(ctx, SB200_E_INVALID, "descriptor matrices must be 16-byte aligned");
+    cudaStream_t st = ctx->slot[0].stream;
+    const uint8_t* d[2] = {d_query, d_train};
+    const uint64_t n[2] = {n_query, n_train};
+    for (int i = 0; i < 2; i++) {
+        const size_t pad = (size_t)((n[i] + MT_N - 1) / MT_N) * MT_N;
+        if (pad > ctx->m_cap[i]) {
+            cudaFree(ctx->d_mnorm[i]); cudaFree(ctx->d_mnbp[i]); cudaFree(ctx->d_mbest[i]);
+            ctx->d_mnorm[i] = nullptr; ctx->d_mnbp[i] = nullptr; ctx->d_mbest[i] = nullptr; ctx->m_cap[i] = 0;
+            CU(dalloc(&ctx->d_mnorm[i], pad));
+            CU(dalloc(&ctx->d_mnbp[i], pad));
+            CU(dalloc(&ctx->d_mbest[i], pad));
+            ctx->m_cap[i] = pad;
+        }
+        k_match_prep<<<(unsigned)((pad + 7) / 8), 256, 0, st>>>(d[i], (uint32_t)n[i], ctx->d_mnorm[i], ctx->d_mnbp[i], (uint32_t)pad);
+        ctx->launches++;
+    }
+    if (n_query > ctx->mout_cap) {
+        cudaFree(ctx->d_mout);
+        ctx->d_mout = nullptr; ctx->mout_cap = 0;
+        CU(dalloc(&ctx->d_mout, (size_t)n_query));
+        ctx->mout_cap = n_query;
+    }
+    if (!ctx->d_mcount) CU(dalloc(&ctx->d_mcount, 1));
+    // nearest neighbour in both directions: rows of `a` against all rows of `b`
+    for (int dir = 0; dir < 2; dir++) {
+        const int a = dir, b = 1 - dir;
+        CUtensorMap tm_a, tm_b;
+        int rc;
+        if ((rc = encode_desc_map(ctx, &tm_a, d[a], n[a], MT_M)) || (rc = encode_desc_map(ctx, &tm_b, d[b], n[b], MT_N))) return rc;
+        MatchParams mp{};
+        mp.norm_a = ctx->d_mnorm[a]; mp.nbp = ctx->d_mnbp[b];
+        mp.n_a = (uint32_t)n[a]; mp.n_b = (uint32_t)n[b];
+        mp.best = ctx->d_mbest[a];
+        k_match_nn<<<(unsigned)((n[a] + MT_M - 1) / MT_M), MT_THREADS, MT_SMEM, st>>>(tm_a, tm_b, mp);
+        ctx->launches++;
+    }
+    k_match_cross<<<1, 1024, 0, st>>>(ctx->d_mbest[0], ctx->d_mbest[1], (uint32_t)n_query, (uint32_t)n_train, ctx->d_mout,
+                                      (uint32_t)std::min<uint64_t>(ctx->mout_cap, 0xffffffffull), ctx->d_mcount);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    uint32_t cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, ctx->d_mcount, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_out = cnt;
+    const uint64_t m = std::min<uint64_t>(cnt, cap);
+    if (m) {
+        CU(cudaMemcpyAsync(out, ctx->d_mout, m * sizeof(sb200_dmatch), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return cnt > cap ? fail(ctx, SB200_E_CAPACITY, "%u matches exceed the output capacity %llu", cnt, (unsigned long long)cap) : SB200_OK;
+}
+
+int sb200_match_descriptors(sb200_ctx* ctx, const uint8_t* query, uint64_t n_query, const uint8_t* train, uint64_t n_train,
+                sb200_dmatch* out, uint64_t cap, uint64_t* n_out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!n_out || (n_query && !query) || (n_train && !train)) return fail(ctx, SB200_E_INVALID, "bad arguments to match");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slot[0].stream;
+    const uint8_t* h[2] = {query, train};
+    const uint64_t n[2] = {n_query, n_train};
+    for (int i = 0; i < 2; i++) {
+        // the descriptor buffers are sized with the other scratch arrays of the same side
+        const size_t pad = (size_t)((n[i] + MT_N - 1) / MT_N) * MT_N;
+        if (pad > ctx->m_cap[i] || !ctx->d_mdesc[i]) {
+            cudaFree(ctx->d_mdesc[i]); cudaFree(ctx->d_mnorm[i]); cudaFree(ctx->d_mnbp[i]); cudaFree(ctx->d_mbest[i]);
+            ctx->d_mdesc[i] = nullptr; ctx->d_mnorm[i] = nullptr; ctx->d_mnbp[i] = nullptr; ctx->d_mbest[i] = nullptr;
+            ctx->m_cap[i] = 0;
+            const size_t cap_rows = std::max<size_t>(pad, MT_N);
+            CU(dalloc(&ctx->d_mdesc[i], cap_rows * DESC_SIZE));
+            CU(dalloc(&ctx->d_mnorm[i], cap_rows));
+            CU(dalloc(&ctx->d_mnbp[i], cap_rows));
+            CU(dalloc(&ctx->d_mbest[i], cap_rows));
+            ctx->m_cap[i] = cap_rows;
+        }
+        if (n[i]) CU(cudaMemcpyAsync(ctx->d_mdesc[i], h[i], n[i] * DESC_SIZE, cudaMemcpyHostToDevice, st));
+    }
+    return sb200_match_descriptors_device(ctx, ctx->d_mdesc[0], n_query, ctx->d_mdesc[1], n_train, out, cap, n_out);
 }
 
 // ---- measurement ---------------------------------------------------------------
