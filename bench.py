@@ -452,13 +452,86 @@ def run_desc(args, rank, local_rank, world):
     dist.close()
 
 
+def run_match(args, rank, local_rank, world):
+    """Descriptor matching (examples/sift-match.rs:30-35): mutual nearest neighbours of
+    two 1080p-sized descriptor sets (8648 x 128 u8 each, the keypoint count of the 1080p workload)."""
+    import sift_features_b200 as sf
+    from sift_features_b200 import _ffi
+    lib = _ffi.load()
+    dist = Dist(rank, local_rank, world)
+    n = 8648
+    ex = sf.Extractor(8, 8, 1, device=local_rank)
+    H = ex.handle
+
+    def chk(st):
+        if st:
+            raise RuntimeError(lib.sb200_last_error(H).decode())
+    rng = np.random.default_rng(7 + rank)
+    q = np.minimum(rng.gamma(0.6, 30.0, (n, 128)), 255).astype(np.uint8)
+    t = np.minimum(rng.gamma(0.6, 30.0, (n, 128)), 255).astype(np.uint8)
+    t[: n // 2] = q[rng.permutation(n)[: n // 2]]
+    d_q, d_t = C.c_void_p(), C.c_void_p()
+    chk(lib.sb200_device_alloc(H, q.nbytes, C.byref(d_q)))
+    chk(lib.sb200_device_alloc(H, t.nbytes, C.byref(d_t)))
+    chk(lib.sb200_memcpy_h2d(H, d_q, q.ctypes.data, q.nbytes))
+    chk(lib.sb200_memcpy_h2d(H, d_t, t.ctypes.data, t.nbytes))
+    out = np.zeros(n, np.dtype([("query", np.uint32), ("train", np.uint32), ("dist2", np.uint32)]))
+    cnt = C.c_uint64()
+    for _ in range(args.warmup):
+        chk(lib.sb200_match_descriptors_device(H, d_q, n, d_t, n, out.ctypes.data, n, C.byref(cnt)))
+    dist.barrier()
+    l0 = ex.launch_count
+    chk(lib.sb200_timer_start(H))
+    for _ in range(args.steps):
+        chk(lib.sb200_match_descriptors_device(H, d_q, n, d_t, n, out.ctypes.data, n, C.byref(cnt)))
+    chk(lib.sb200_timer_stop(H))
+    ms = C.c_float()
+    chk(lib.sb200_timer_elapsed_ms(H, C.byref(ms)))
+    dev_ms = dist.reduce(ms.value, "max")
+    launches = ex.launch_count - l0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chk(lib.sb200_match_descriptors(H, q.ctypes.data, n, t.ctypes.data, n, out.ctypes.data, n, C.byref(cnt)))
+    t_e2e = dist.reduce(time.perf_counter() - t0, "max")
+    if rank == 0:
+        pairs = float(n) * n
+        val = args.steps * pairs * world / (dev_ms * 1e-3)
+        flops = 2.0 * 2 * pairs * 128          # both directions, multiply + add
+        tf = None
+        try:
+            tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops"))
+        except Exception:
+            pass
+        line = {"metric": "descriptor pairs/sec (mutual nearest neighbours, 8648 x 8648)", "value": val, "unit": "pairs/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> s32",
+                "data": "synthetic", "config": {"workload": "match: two 8648 x 128 u8 descriptor sets, cross-check"},
+                "e2e": {"value": args.steps * pairs * world / t_e2e, "unit": "pairs/s",
+                        "h2d_bytes_per_step": int(q.nbytes + t.nbytes), "d2h_bytes_per_step": int(cnt.value) * 12},
+                "gpu_launches": int(launches), "matches": int(cnt.value),
+                "roofline": {"bound": "tensor", "kernel": "k_match_nn (tcgen05.mma kind::i8 + fused argmin epilogue)",
+                             "achieved": flops * args.steps / (dev_ms * 1e-3) / 1e12, "peak": tf, "unit": "TOP/s (peak: dense bf16 TFLOP/s)",
+                             "frac": (flops * args.steps / (dev_ms * 1e-3) / 1e12 / tf) if tf else None, "traffic": None,
+                             "note": "timed through the synchronous device-pointer call (includes the count read-back); "
+                                     "the step is epilogue / launch bound, not MMA bound, at this size"}}
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as O
+            t0 = time.perf_counter()
+            O.match_cross_check(q[:2048], t)
+            line["cpu_baseline"] = {"value": 2048.0 * n / (time.perf_counter() - t0), "unit": "pairs/s", "cores": os.cpu_count(),
+                                    "kind": "port", "sample": "2048 query rows against all train rows (numpy int64 GEMM)"}
+        print(json.dumps(line), flush=True)
+    ex.close()
+    dist.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS) + ["desc"])
+    ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS) + ["desc", "match"])
     ap.add_argument("--batch", type=int, default=0, help="images per group (context max_batch)")
     ap.add_argument("--groups", type=int, default=0, help="groups per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -468,11 +541,13 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
-        if args.workload == "desc":
+        if args.workload in ("desc", "match"):
             args.workload = "1080p"
         return run_reference(args, rank, world)
     if args.workload == "desc":
         return run_desc(args, rank, local_rank, world)
+    if args.workload == "match":
+        return run_match(args, rank, local_rank, world)
     return run_b200(args, rank, local_rank, world)
 
 
