@@ -84,6 +84,15 @@ public:
         check(sb200_compute_descriptors(ctx_, img, w, h, w, &k, 1, out.data()));
         return out;
     }
+    // BFMatcher(NORM_L2, crossCheck = true).match(query, train), examples/sift-match.rs:30-35: mutual nearest
+    // neighbours of two (n,128) u8 descriptor matrices, ascending query order
+    std::vector<sb200_dmatch> match(const uint8_t* query, uint64_t n_query, const uint8_t* train, uint64_t n_train) {
+        std::vector<sb200_dmatch> out(n_query);
+        uint64_t n = 0;
+        check(sb200_match_descriptors(ctx_, query, n_query, train, n_train, out.data(), out.size(), &n));
+        out.resize(n);
+        return out;
+    }
     sb200_ctx* handle() { return ctx_; }
 
 private:

@@ -53,6 +53,31 @@ extern "C" {
     fn sb200_extract_precomputed(ctx: *mut Sb200Ctx, limit: i64, out: *mut Sb200Result) -> c_int;
     fn sb200_compute_descriptors(ctx: *mut Sb200Ctx, img: *const f32, w: u32, h: u32, stride: u32,
                                  kps: *const Sb200DescIn, n: u64, out: *mut u8) -> c_int;
+    fn sb200_match_descriptors(ctx: *mut Sb200Ctx, query: *const u8, n_query: u64, train: *const u8, n_train: u64,
+                               out: *mut DMatch, cap: u64, n_out: *mut u64) -> c_int;
+}
+
+/// One mutual nearest-neighbour pair (the fields of `cv::DMatch` the examples use; `dist2` is the exact squared L2).
+#[repr(C)]
+#[derive(Debug, Clone, Copy, PartialEq, Eq)]
+pub struct DMatch {
+    pub query: u32,
+    pub train: u32,
+    pub dist2: u32,
+}
+
+/// `BFMatcher::new(NORM_L2, true)` + `match_(query, train)` of `examples/sift-match.rs:30-35` on the GPU.
+pub fn match_descriptors(query: &Array2<u8>, train: &Array2<u8>) -> Vec<DMatch> {
+    assert!(query.ncols() == 128 && train.ncols() == 128);
+    let (q, t) = (query.as_standard_layout(), train.as_standard_layout());
+    let ctx = Context::new(8, 8);
+    let mut out = Vec::<DMatch>::with_capacity(q.nrows());
+    let mut n = 0u64;
+    let st = unsafe { sb200_match_descriptors(ctx.0, q.as_ptr(), q.nrows() as u64, t.as_ptr(), t.nrows() as u64,
+                                              out.as_mut_ptr(), out.capacity() as u64, &mut n) };
+    ctx.check(st);
+    unsafe { out.set_len(n as usize) };
+    out
 }
 
 /// One context per (thread, device); owns the device arenas.
