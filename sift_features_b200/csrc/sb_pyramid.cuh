@@ -939,7 +939,7 @@ __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema(const ExtremaParam
 // IMAGE_BORDER margin, which cannot hold candidates.
 // ---------------------------------------------------------------------------
 constexpr int EXT_RB = 3;                         // rows per stage
-constexpr int EXT_NS = 3;                         // stages per warp
+constexpr int EXT_NS = 2;                         // stages per warp
 constexpr int EXT_STEPS = 12;                     // stages per warp pass
 constexpr int EXT_ROWS = EXT_RB * EXT_STEPS - 2;  // centre rows per warp (two halo rows)
 // a TMA box must start on a 16-byte boundary of the row: the box begins 4 columns left of the strip (60j - 4)
@@ -961,7 +961,7 @@ __device__ __forceinline__ void ext_step(const ExWarp& W, ExState& S, const floa
 }
 
 template <bool KEEP_FLAT>
-__global__ void __launch_bounds__(32 * EX_WARPS, 4) k_extrema_tma(const __grid_constant__ CUtensorMap tmap, const ExtremaParams p) {
+__global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema_tma(const __grid_constant__ CUtensorMap tmap, const ExtremaParams p) {
     extern __shared__ __align__(1024) float ext_smem[];
     __shared__ __align__(8) uint64_t bar[EX_WARPS][EXT_NS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
