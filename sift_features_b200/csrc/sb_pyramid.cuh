@@ -793,7 +793,7 @@ struct ExWarp {
     uint32_t* rows;            // lanes 0..2: row counter of (scale lane+1, row 0)
     int ls;                    // layer stride in floats
     int h, pitch, mask_pitch, lane;
-    uint32_t ok;               // bit k: the lane's column k can hold candidates (IMAGE_BORDER, halo lanes excluded)
+    uint32_t cmask0, cmask1;   // warp-wide: lanes whose column 0 / 1 can hold candidates (IMAGE_BORDER, halo lanes excluded)
     bool coherent;             // the layers were written earlier in this launch (k_tail): no read-only-path loads
 };
 
@@ -812,9 +812,11 @@ __device__ __forceinline__ void ex_load(const ExWarp& W, const int r, float2* gv
     }
 }
 
-// (v > 0 and v >= Mx) or (v < 0 and v <= mn), gated by `ok`, without short-circuit branches
-__device__ __forceinline__ bool ex_is_extremum(const bool ok, const float v, const float Mx, const float mn) {
-    return (ok & (v > 0.0f) & (v >= Mx)) | (ok & (v < 0.0f) & (v <= mn));
+// (v > 0 and v >= Mx) or (v < 0 and v <= mn) where Mx / mn are the max / min of a neighbourhood that contains v
+// (so >= / <= can only hold with equality): one select and three compares, no branches
+__device__ __forceinline__ bool ex_is_extremum(const float v, const float Mx, const float mn) {
+    const float t = v > 0.0f ? Mx : mn;
+    return (v == t) & (v != 0.0f);
 }
 
 // Evaluates the centre row c = r-1 once rows r-2, r-1, r sit in slots A, B, K of the state (K a compile-time
@@ -830,9 +832,8 @@ __device__ __forceinline__ void ex_eval(const ExWarp& W, const ExState& S, const
         VM[l] = make_float2(fmax3(S.d[A][l].x, S.d[B][l].x, S.d[K][l].x), fmax3(S.d[A][l].y, S.d[B][l].y, S.d[K][l].y));
         Vm[l] = make_float2(fmin3(S.d[A][l].x, S.d[B][l].x, S.d[K][l].x), fmin3(S.d[A][l].y, S.d[B][l].y, S.d[K][l].y));
     }
-    const bool row_ok = (c >= IMAGE_BORDER) & (c < W.h - IMAGE_BORDER);  // warp-uniform
-    const bool ok0 = row_ok & ((W.ok & 1u) != 0), ok1 = row_ok & ((W.ok & 2u) != 0);
     uint32_t mine0 = 0, mine1 = 0;  // lane s-1 keeps the ballots of scale s
+    if ((c >= IMAGE_BORDER) & (c < W.h - IMAGE_BORDER)) {  // warp-uniform: rows inside the border margin hold no candidates
 #pragma unroll
     for (int s = 1; s <= SCALES_PER_OCTAVE; s++) {
         const float2 v = S.d[B][s];
@@ -841,9 +842,9 @@ __device__ __forceinline__ void ex_eval(const ExWarp& W, const ExState& S, const
         const float2 Xm = make_float2(fmin3(Vm[s - 1].x, Vm[s].x, Vm[s + 1].x), fmin3(Vm[s - 1].y, Vm[s].y, Vm[s + 1].y));
         const float lM = __shfl_up_sync(0xffffffffu, XM.y, 1), rM = __shfl_down_sync(0xffffffffu, XM.x, 1);
         const float lm = __shfl_up_sync(0xffffffffu, Xm.y, 1), rm = __shfl_down_sync(0xffffffffu, Xm.x, 1);
-        const bool e0 = ex_is_extremum(ok0, v.x, fmax3(lM, XM.x, XM.y), fmin3(lm, Xm.x, Xm.y));
-        const bool e1 = ex_is_extremum(ok1, v.y, fmax3(XM.x, XM.y, rM), fmin3(Xm.x, Xm.y, rm));
-        uint32_t b0 = __ballot_sync(0xffffffffu, e0), b1 = __ballot_sync(0xffffffffu, e1);
+        const bool e0 = ex_is_extremum(v.x, fmax3(lM, XM.x, XM.y), fmin3(lm, Xm.x, Xm.y));
+        const bool e1 = ex_is_extremum(v.y, fmax3(XM.x, XM.y, rM), fmin3(Xm.x, Xm.y, rm));
+        uint32_t b0 = __ballot_sync(0xffffffffu, e0) & W.cmask0, b1 = __ballot_sync(0xffffffffu, e1) & W.cmask1;
         // A candidate whose three DoG layers are each spatially constant over its 3x3 window has zero
         // spatial derivatives (h12 = h13 = h22 = h33 = h23 = 0, g2 = g3 = 0), so interpolate_extremum
         // computes det = 0, every cofactor quotient is 0/0 = NaN, the NaN offsets never pass `abs() < 0.5`,
@@ -863,10 +864,11 @@ __device__ __forceinline__ void ex_eval(const ExWarp& W, const ExState& S, const
                 f0 &= mid & lc & (lv == VM[l].x);
                 f1 &= mid & rc & (rv == VM[l].y);
             }
-            b0 = __ballot_sync(0xffffffffu, e0 & !f0);
-            b1 = __ballot_sync(0xffffffffu, e1 & !f1);
+            b0 = __ballot_sync(0xffffffffu, e0 & !f0) & W.cmask0;
+            b1 = __ballot_sync(0xffffffffu, e1 & !f1) & W.cmask1;
         }
         if (W.lane == s - 1) { mine0 = b0; mine1 = b1; }
+    }
     }
     if (W.lane < SCALES_PER_OCTAVE && c < W.h) {
         *reinterpret_cast<uint2*>(W.mask + (long long)c * W.mask_pitch) = make_uint2(mine0, mine1);
@@ -896,8 +898,8 @@ __device__ __forceinline__ void ex_setup(ExWarp& W, const ExtremaParams& p, cons
     W.mask = p.mask + img * p.mask_img_stride + (long long)sl * W.h * W.mask_pitch + 2 * strip;
     W.rows = p.rows + img * p.rows_img_stride + sl * W.h;
     const bool inner = (lane >= 1) & (lane <= 30);
-    W.ok = (inner & (x0 >= IMAGE_BORDER) & (x0 < p.w - IMAGE_BORDER) ? 1u : 0u) |
-           (inner & (x0 + 1 >= IMAGE_BORDER) & (x0 + 1 < p.w - IMAGE_BORDER) ? 2u : 0u);
+    W.cmask0 = __ballot_sync(0xffffffffu, inner & (x0 >= IMAGE_BORDER) & (x0 < p.w - IMAGE_BORDER));
+    W.cmask1 = __ballot_sync(0xffffffffu, inner & (x0 + 1 >= IMAGE_BORDER) & (x0 + 1 < p.w - IMAGE_BORDER));
 }
 
 // one warp: strip `strip`, centre rows [y0, y0 + EX_ROWS) of image `img`
