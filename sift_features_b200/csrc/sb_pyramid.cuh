@@ -538,7 +538,10 @@ struct MarchCfg {
     static constexpr int NSTG = (L <= 2) ? 3 : 2;
     static constexpr int RING_ROWS = 3 * BH + 2 * R;   // three band slots + a mirror of the first 2R rows of slot 0
     static constexpr uint32_t BAND_BYTES = (uint32_t)BH * BW * sizeof(float);
-    static constexpr size_t SMEM = (size_t)NSTG * BAND_BYTES + (size_t)RING_ROWS * IPITCH * sizeof(float);
+#ifndef SB_MARCH_PAD
+#define SB_MARCH_PAD 0
+#endif
+    static constexpr size_t SMEM = (size_t)NSTG * BAND_BYTES + (size_t)RING_ROWS * IPITCH * sizeof(float) + SB_MARCH_PAD;
     static_assert(BW >= XO + SW && (BW / 4) % 2 == 1 && TW - 8 + 4 * NV4 <= BW && BW <= 256, "box width");
     static_assert(BAND_BYTES % 128 == 0, "128-byte aligned stage buffers");
     static_assert(2 * R + 1 <= BH && PY + 2 * R <= 2 * BH, "window spans at most two bands");
