@@ -905,15 +905,15 @@ __device__ __forceinline__ void ex_setup(ExWarp& W, const ExtremaParams& p, cons
     W.cmask1 = __ballot_sync(0xffffffffu, inner & (x0 + 1 >= IMAGE_BORDER) & (x0 + 1 < p.w - IMAGE_BORDER));
 }
 
-// one warp: strip `strip`, centre rows [y0, y0 + EX_ROWS) of image `img`
+// one warp: strip `strip`, centre rows [y0, y0 + rows) of image `img`
 template <bool KEEP_FLAT>
-__device__ __forceinline__ void ex_strip(const ExtremaParams& p, const int strip, const int y0, const int lane,
-                                         const long long img, const bool coherent) {
+__device__ __forceinline__ void ex_strip(const ExtremaParams& p, const int strip, const int y0, const int rows,
+                                         const int lane, const long long img, const bool coherent) {
     ExWarp W;
     ex_setup(W, p, strip, lane, img);
     W.coherent = coherent;
     ExState S;
-    const int r_end = min(y0 + EX_ROWS, W.h);  // centre rows [y0, r_end): image rows y0-1 .. r_end
+    const int r_end = min(y0 + rows, W.h);  // centre rows [y0, r_end): image rows y0-1 .. r_end
     float2 gv[N_LAYERS];
     ex_load(W, y0 - 1, gv);
     ex_step<0, false, KEEP_FLAT>(W, S, y0 - 1, gv);
@@ -930,7 +930,7 @@ __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema(const ExtremaParam
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = (blockIdx.y * EX_WARPS + warp) * EX_ROWS;
     if (y0 >= p.h) return;
-    ex_strip<KEEP_FLAT>(p, blockIdx.x, y0, lane, blockIdx.z, false);
+    ex_strip<KEEP_FLAT>(p, blockIdx.x, y0, EX_ROWS, lane, blockIdx.z, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -1034,7 +1034,7 @@ __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema_tma(const __grid_c
 // BORDER_REFLECT_101) and the same extrema code as k_extrema (generic loads, coherent path: the layers were
 // written by this CTA).
 // ---------------------------------------------------------------------------
-constexpr int TAIL_MAX_PX = 9216;     // 36 KB per buffer, e.g. 128 x 72
+constexpr int TAIL_MAX_PX = 2304;     // 9 KB per buffer, e.g. 64 x 36: larger octaves keep one CTA busy for too long
 constexpr int TAIL_THREADS = 512;
 constexpr size_t TAIL_SMEM = 2 * (size_t)TAIL_MAX_PX * sizeof(float);
 
@@ -1126,10 +1126,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
             e.w = w; e.h = h; e.pitch = ol.pitch;
             e.mask = p.mask + ol.mask_off; e.mask_img_stride = p.L.img_mask_words; e.mask_pitch = ol.mask_pitch;
             e.rows = p.rows + ol.row_base; e.rows_img_stride = p.L.img_rows;
-            const int strips = ex_strips(w), blocks = (h + EX_ROWS - 1) / EX_ROWS;
+            // short row blocks: the scan is a chain of dependent row loads, so the CTA's 16 warps want many short tasks
+            constexpr int TROWS = 6;
+            const int strips = ex_strips(w), blocks = (h + TROWS - 1) / TROWS;
             for (int t = warp; t < strips * blocks; t += TAIL_THREADS / 32) {
-                const int strip = t % strips, y0 = (t / strips) * EX_ROWS;
-                ex_strip<KEEP_FLAT>(e, strip, y0, lane, img, true);
+                const int strip = t % strips, y0 = (t / strips) * TROWS;
+                ex_strip<KEEP_FLAT>(e, strip, y0, TROWS, lane, img, true);
             }
         }
         __syncthreads();
