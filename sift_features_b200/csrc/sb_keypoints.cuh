@@ -167,7 +167,50 @@ __global__ void __launch_bounds__(128) k_refine(const KpParams P) {
 // reference's f32 results, not an approximation of them.
 constexpr int ORI_WARPS = 8;
 
-__global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P) {
+// largest img with off[img] <= j (off is an exclusive prefix sum with off[n] = total)
+__device__ __forceinline__ int find_image(const uint32_t* __restrict__ off, const int n, const uint32_t j) {
+    int lo = 0, hi = n;   // invariant: off[lo] <= j < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= j) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Launch-wide work list pulled in chunks from an atomic counter: lane 0 issues the atomic for the NEXT chunk before
+// the warp processes the current one and the result is only broadcast afterwards, so its latency is hidden.
+// With little work per warp (single images) a chunk is one item and nothing is requested ahead, so no warp sits on
+// work that an idle one could do.
+struct WorkQueue {
+    uint32_t* counter;
+    uint32_t pending;   // lane 0: first item of the chunk requested last
+    uint32_t chunk;     // items per request
+    bool ahead;         // request the next chunk before processing the current one
+    __device__ __forceinline__ WorkQueue(uint32_t* c, const uint32_t total, const uint32_t warps, const uint32_t max_chunk)
+        : counter(c), pending(0u) {
+        ahead = total > 8u * warps * max_chunk;
+        chunk = ahead ? max_chunk : 1u;
+    }
+    __device__ __forceinline__ void request(const int lane) {
+        if (lane == 0) pending = atomicAdd(counter, chunk);
+    }
+    __device__ __forceinline__ uint32_t take() const { return __shfl_sync(0xffffffffu, pending, 0); }
+    // first item of this warp's next chunk; call once per chunk
+    __device__ __forceinline__ uint32_t next(const int lane, const bool first_call) {
+        if (first_call || !ahead) request(lane);
+        const uint32_t v = take();
+        if (ahead) request(lane);   // in flight while the chunk is processed
+        return v;
+    }
+};
+
+constexpr int ORI_CHUNK = 4;
+
+// The candidates of all images of the group form one work list (cand_off = exclusive prefix sum of the per-image
+// counts); warps pull chunks of it from an atomic counter, so the launch is balanced whatever the per-image and
+// per-candidate cost, and its grid is exactly the number of resident CTAs.
+__global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, const uint32_t* __restrict__ cand_off,
+                                                            const int n_img, uint32_t* __restrict__ work) {
     __shared__ uint64_t s_tab[32];
     __shared__ float s_val[ORI_WARPS][32];
     __shared__ uint32_t s_msk[ORI_WARPS][40];
@@ -176,16 +219,19 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P) {
     if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long img = blockIdx.y;
-    const uint32_t n = min(P.cand_count[img], P.cap);
-    const Refined* refined = P.refined + img * (long long)P.cap;
-    uint32_t* n_ori = P.n_ori + img * (long long)P.cap;
-    float* angles = P.angles + img * (long long)P.cap * MAX_ORI;
-    const float* gimg = P.gauss + img * P.L.img_floats;
     const float PI32 = 3.14159265358979323846f;
     const float bin_angle_step = 36.0f / (PI32 * 2.f);  // src/lib.rs:718
+    const uint32_t total = __ldg(cand_off + n_img);
 
-    for (uint32_t i = blockIdx.x * ORI_WARPS + warp; i < n; i += gridDim.x * ORI_WARPS) {
+    WorkQueue wq(work, total, gridDim.x * ORI_WARPS, ORI_CHUNK);
+    for (uint32_t first = wq.next(lane, true); first < total; first = wq.next(lane, false)) {
+      for (uint32_t j = first; j < min(first + wq.chunk, total); j++) {
+        const int img = find_image(cand_off, n_img, j);
+        const uint32_t i = j - __ldg(cand_off + img);
+        const Refined* refined = P.refined + img * (long long)P.cap;
+        uint32_t* n_ori = P.n_ori + img * (long long)P.cap;
+        float* angles = P.angles + img * (long long)P.cap * MAX_ORI;
+        const float* gimg = P.gauss + img * P.L.img_floats;
         const Refined r = refined[i];
         if (r.octave_scale < 0) {
             if (lane == 0) n_ori[i] = 0;
@@ -307,6 +353,7 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P) {
         }
         if (lane == 0) n_ori[i] = min(count, (uint32_t)MAX_ORI);
         __syncwarp();
+      }
     }
 }
 
@@ -809,36 +856,41 @@ __global__ void __launch_bounds__(1024) k_out_offsets(const uint32_t* __restrict
 
 // compute_descriptors (src/lib.rs:759-782) over the keypoint list of each image and
 // the final KeyPoint records (src/lib.rs:164-174).
-__global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams P) {
+constexpr int DESC_CHUNK = 2;
+
+// The output keypoints of all images of the group form one work list (out_off is their exclusive prefix sum);
+// warps pull chunks from an atomic counter (see k_orient).
+__global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams P, const int n_img,
+                                                                uint32_t* __restrict__ work) {
     extern __shared__ __align__(16) unsigned char desc_smem[];  // DESC_SMEM_BYTES, dynamic (> 48 KB)
     uint64_t* s_tab = reinterpret_cast<uint64_t*>(desc_smem);
     float (*s_hist)[DESC_SMEM_WORDS] = reinterpret_cast<float (*)[DESC_SMEM_WORDS]>(desc_smem + 256);
     if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long img = blockIdx.y;
-    const uint32_t n = min(P.kp_count[img], P.kcap);
-    const uint32_t n_out = P.out_count[img];
-    const bool limited = n_out < n;
-    const DevKeyPoint* kps = P.kps + img * (long long)P.kcap;
-    const uint32_t* order = P.order + img * (long long)P.kcap;
-    const float* gimg = P.gauss + img * P.L.img_floats;
-    const long long obase = P.out_off[img];
-    for (uint32_t j = blockIdx.x * DESC_WARPS + warp; j < n_out; j += gridDim.x * DESC_WARPS) {
-        const DevKeyPoint kp = kps[limited ? order[j] : j];
-        const OctLayout& ol = P.L.o[kp.octave];
-        DescTarget t;
-        t.img = gimg + ol.off + (long long)kp.scale * ol.layer_stride;
-        t.w = ol.w; t.h = ol.h; t.pitch = ol.pitch;
-        const float f = pow2i(-kp.octave);  // 2_f32.powi(-octave), src/lib.rs:768
-        t.x = kp.x * f; t.y = kp.y * f; t.scale = kp.size * f;
-        t.orientation = 360.0f - kp.angle;   // :766
-        descriptor_warp(t, s_hist[warp], lane, P.out_desc + (obase + j) * DESC_SIZE);
-        if (lane == 0) {
-            OutKeyPoint o;  // DELTA_MIN = 0.5 undoes the seed upsampling, src/lib.rs:168-170
-            o.x = kp.x * 0.5f; o.y = kp.y * 0.5f; o.size = kp.size * 0.5f;
-            o.angle = kp.angle; o.response = kp.response;
-            P.out_kps[obase + j] = o;
+    const uint32_t total = __ldg(P.out_off + n_img);
+    WorkQueue wq(work, total, gridDim.x * DESC_WARPS, DESC_CHUNK);
+    for (uint32_t first = wq.next(lane, true); first < total; first = wq.next(lane, false)) {
+        for (uint32_t g = first; g < min(first + wq.chunk, total); g++) {
+            const int img = find_image(P.out_off, n_img, g);
+            const uint32_t j = g - __ldg(P.out_off + img);
+            const uint32_t n = min(P.kp_count[img], P.kcap);
+            const bool limited = P.out_count[img] < n;
+            const DevKeyPoint kp = (P.kps + img * (long long)P.kcap)[limited ? (P.order + img * (long long)P.kcap)[j] : j];
+            const OctLayout& ol = P.L.o[kp.octave];
+            DescTarget t;
+            t.img = P.gauss + img * P.L.img_floats + ol.off + (long long)kp.scale * ol.layer_stride;
+            t.w = ol.w; t.h = ol.h; t.pitch = ol.pitch;
+            const float f = pow2i(-kp.octave);  // 2_f32.powi(-octave), src/lib.rs:768
+            t.x = kp.x * f; t.y = kp.y * f; t.scale = kp.size * f;
+            t.orientation = 360.0f - kp.angle;   // :766
+            descriptor_warp(t, s_hist[warp], lane, P.out_desc + (size_t)g * DESC_SIZE);
+            if (lane == 0) {
+                OutKeyPoint o;  // DELTA_MIN = 0.5 undoes the seed upsampling, src/lib.rs:168-170
+                o.x = kp.x * 0.5f; o.y = kp.y * 0.5f; o.size = kp.size * 0.5f;
+                o.angle = kp.angle; o.response = kp.response;
+                P.out_kps[g] = o;
+            }
         }
     }
 }

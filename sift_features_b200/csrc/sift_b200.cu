@@ -50,6 +50,7 @@ struct Slot {
     uint32_t* d_rows = nullptr;  // [B][img_rows] counters, followed by [B] cand_count, kp_count
     uint32_t* d_rowoff = nullptr;
     uint32_t* d_counts = nullptr;  // cand_count[B], kp_count[B], out_count[B], out_off[B+1]
+    uint32_t* d_sched = nullptr;   // work counters [4], scratch counts [B], candidate prefix sums [B+1]
     // candidates / keypoints
     uint32_t* d_keys = nullptr;
     Refined* d_refined = nullptr;
@@ -134,6 +135,7 @@ struct sb200_ctx {
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     int sm_count = 148;
+    int ori_ctas = 148, desc_ctas = 148;   // resident CTAs of k_orient / k_descriptor (their grids)
 };
 
 namespace {
@@ -296,6 +298,7 @@ int alloc_slot(sb200_ctx* ctx, Slot& s) {
     CU(dalloc(&s.d_rows, (size_t)ctx->rows_cap * B));
     CU(dalloc(&s.d_rowoff, (size_t)ctx->rows_cap * B));
     CU(dalloc(&s.d_counts, 4 * B + 1));
+    CU(dalloc(&s.d_sched, 2 * B + 5));
     CU(cudaHostAlloc((void**)&s.h_counts, (4 * B + 1) * sizeof(uint32_t), cudaHostAllocDefault));
     CU(dalloc(&s.d_keys, cap * B));
     CU(dalloc(&s.d_refined, cap * B));
@@ -314,7 +317,7 @@ void free_slot(Slot& s) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.ev_counts) cudaEventDestroy(s.ev_counts);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
-    cudaFree(s.d_rowoff); cudaFree(s.d_counts); cudaFreeHost(s.h_counts); cudaFree(s.d_keys);
+    cudaFree(s.d_rowoff); cudaFree(s.d_counts); cudaFree(s.d_sched); cudaFreeHost(s.h_counts); cudaFree(s.d_keys);
     cudaFree(s.d_refined); cudaFree(s.d_nori); cudaFree(s.d_angles); cudaFree(s.d_kpoff); cudaFree(s.d_kps);
     cudaFree(s.d_sort); cudaFree(s.d_order); cudaFree(s.d_out_kps); cudaFree(s.d_out_desc);
     s = Slot{};
@@ -667,6 +670,9 @@ int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
     uint32_t* out_off = s.d_counts + 3 * B;
     KpParams P = make_kp_params(ctx, s);
     const int gx = std::max(1, std::min(4 * ctx->sm_count, (int)(8 * ctx->sm_count / std::max(1u, n)) + 1));
+    uint32_t* work = s.d_sched;                // [0]: orientation work list, [1]: descriptor work list
+    uint32_t* cand_off = s.d_sched + 4 + B;    // exclusive prefix sum of the per-image candidate counts, [n] = total
+    CU(cudaMemsetAsync(work, 0, 4 * sizeof(uint32_t), st));
     {
         StageScope sc(ctx, st, SB200_STAGE_EXTREMA);
         k_rowscan<<<n, 1024, 0, st>>>(s.d_rows, s.d_rowoff, L.img_rows, cand_count);
@@ -681,10 +687,11 @@ int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
     }
     {
         StageScope sc(ctx, st, SB200_STAGE_ORIENT);
-        k_orient<<<dim3(gx, n), 32 * ORI_WARPS, 0, st>>>(P);
+        k_out_offsets<<<1, 1024, 0, st>>>(cand_count, ctx->cap, -1LL, (int)n, s.d_sched + 4, cand_off);
+        k_orient<<<ctx->ori_ctas, 32 * ORI_WARPS, 0, st>>>(P, cand_off, (int)n, work);
         k_kpscan<<<n, 1024, 0, st>>>(P);
         k_emit<<<dim3(gx, n), 256, 0, st>>>(P);
-        count_launch(ctx, SB200_STAGE_ORIENT, 3);
+        count_launch(ctx, SB200_STAGE_ORIENT, 4);
     }
     {
         StageScope sc(ctx, st, SB200_STAGE_DESCRIPTOR);
@@ -705,7 +712,7 @@ int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
         D.out_off = out_off;
         D.out_kps = s.d_out_kps;
         D.out_desc = s.d_out_desc;
-        k_descriptor<<<dim3(gx, n), 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(D);
+        k_descriptor<<<ctx->desc_ctas, 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(D, (int)n, work + 1);
         count_launch(ctx, SB200_STAGE_DESCRIPTOR, 2);
     }
     CU(cudaGetLastError());
@@ -911,6 +918,13 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CU(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DESC_SMEM_BYTES));
         CU(cudaFuncSetAttribute(k_descriptor_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DESC_SMEM_BYTES));
+        {
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_descriptor, 32 * DESC_WARPS, DESC_SMEM_BYTES));
+            ctx->desc_ctas = std::max(1, per_sm) * ctx->sm_count;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orient, 32 * ORI_WARPS, 0));
+            ctx->ori_ctas = std::max(1, per_sm) * ctx->sm_count;
+        }
         {
             cudaDriverEntryPointQueryResult q;
             void* fn = nullptr;
