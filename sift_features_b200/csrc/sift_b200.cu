@@ -979,12 +979,27 @@ int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_
     rc = ensure_result_capacity(ctx, 0, n);
     if (rc) return rc;
     const uint32_t B = ctx->max_batch;
+    // group sizes: full groups of B images, but a long batch starts and ends with a quarter-size group so that the
+    // upload of the first group and the download of the last one -- the two copies nothing can overlap -- are short
+    std::vector<uint32_t> sizes;
+    {
+        uint64_t rem = n;
+        const uint32_t q = std::max<uint32_t>(1, B / 4);
+        if (n >= 2ull * B && B >= 4) {
+            sizes.push_back(q); rem -= q;
+            while (rem > (uint64_t)B + q) { sizes.push_back(B); rem -= B; }
+            if (rem > q) { sizes.push_back((uint32_t)(rem - q)); rem = q; }
+            sizes.push_back((uint32_t)rem);
+        } else {
+            while (rem) { const uint32_t c = (uint32_t)std::min<uint64_t>(B, rem); sizes.push_back(c); rem -= c; }
+        }
+    }
     uint32_t g = 0;
-    for (uint64_t first = 0; first < n; first += B, g++) {
+    uint64_t first = 0;
+    for (; g < sizes.size(); first += sizes[g], g++) {
         Slot& s = ctx->slot[g & 1];
         // groups complete in order: the slot's previous group (g-2) was collected before group g-1 launched
-        const uint32_t cnt = (uint32_t)std::min<uint64_t>(B, n - first);
-        rc = launch_group(ctx, s, gray + first * image_stride, cnt, w, h, stride, image_stride, features_limit, first);
+        rc = launch_group(ctx, s, gray + first * image_stride, sizes[g], w, h, stride, image_stride, features_limit, first);
         if (rc) return rc;
         if (g >= 1) {
             rc = collect_group(ctx, ctx->slot[(g - 1) & 1]);
