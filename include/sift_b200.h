@@ -155,6 +155,18 @@ int sb200_compute_descriptors_device(sb200_ctx* ctx, const float* d_img, uint32_
                                      uint32_t stride, const sb200_desc_in* d_kps, uint64_t n,
                                      uint8_t* d_out);
 
+/* ---- input prep: the step before the path in the reference's callers ----
+ * examples/run-sift.rs:8, examples/sift-match.rs:49, src/lib.rs:1012 turn the decoded image into a GrayImage with the
+ * `image` crate's grayscale(): L = (2126 R + 7152 G + 722 B) / 10000 in integer arithmetic (image 0.25; the crate's
+ * source is not part of the reference tree, so this formula is restated from its published algorithm).
+ * sb200_extract_batch_rgb takes n interleaved 8-bit RGB (channels = 3) or RGBA (channels = 4, alpha ignored) images
+ * of `stride` bytes per row, converts them on the device and runs the extraction path on the result. */
+int sb200_extract_batch_rgb(sb200_ctx* ctx, const uint8_t* rgb, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                            uint64_t image_stride, uint32_t channels, int64_t features_limit, sb200_result* out);
+/* the conversion alone (parity view): gray receives w x h bytes */
+int sb200_rgb_to_luma(sb200_ctx* ctx, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t stride, uint32_t channels,
+                      uint8_t* gray);
+
 /* ---- descriptor matching: the step after the path in the reference's examples ----
  * examples/sift-match.rs:30-35 and examples/opencv-cross-match.rs:34-43 hand the (N,128) u8 descriptor
  * matrices to OpenCV's BFMatcher(NORM_L2, crossCheck = true).  sb200_match_descriptors computes the same mutual nearest

@@ -233,3 +233,12 @@ def match_cross_check(query: np.ndarray, train: np.ndarray) -> np.ndarray:
     keep = col_arg[best_q] == np.arange(len(q))
     idx = np.nonzero(keep)[0]
     return np.stack([idx, best_q[idx], best_d[idx]], 1)
+
+
+def rgb_to_luma(rgb: np.ndarray) -> np.ndarray:
+    """DynamicImage::grayscale() / to_luma8() of the `image` crate (0.25: color.rs rgb_to_luma, SRGB_LUMA = [2126, 7152,
+    722], SRGB_LUMA_DIV = 10000, u32 arithmetic, truncating division), which the reference's callers apply before sift()
+    (examples/run-sift.rs:8, src/lib.rs:1012).  The crate's source is not in the reference tree: restated from its
+    published algorithm, unpinned."""
+    a = np.asarray(rgb).astype(np.uint32)
+    return ((2126 * a[..., 0] + 7152 * a[..., 1] + 722 * a[..., 2]) // 10000).astype(np.uint8)

@@ -209,6 +209,29 @@ class Extractor:
             -1 if features_limit is None else int(features_limit), C.byref(res)))
         return self._take(res)
 
+    def sift_rgb(self, rgb, features_limit: Optional[int] = None) -> SiftResult:
+        """sift() on an interleaved 8-bit RGB / RGBA image (H, W, 3|4): the `image` crate's grayscale() the reference's
+        callers run first (examples/run-sift.rs:8) is done on the device."""
+        a = np.ascontiguousarray(rgb)
+        if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] not in (3, 4):
+            raise ValueError("expected an (H, W, 3|4) uint8 array")
+        res = _ffi.Result()
+        self._retry_capacity(lambda: self._lib.sb200_extract_batch_rgb(
+            self._h, a.ctypes.data, 1, a.shape[1], a.shape[0], a.strides[0], a.strides[0] * a.shape[0], a.shape[2],
+            -1 if features_limit is None else int(features_limit), C.byref(res)))
+        _, kp, de = self._take(res)
+        return SiftResult(kp, de)
+
+    def rgb_to_luma(self, rgb) -> np.ndarray:
+        """The device-side RGB(A) -> luma conversion alone."""
+        a = np.ascontiguousarray(rgb)
+        if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] not in (3, 4):
+            raise ValueError("expected an (H, W, 3|4) uint8 array")
+        out = np.zeros(a.shape[:2], np.uint8)
+        self._check(self._lib.sb200_rgb_to_luma(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], a.shape[2],
+                                                out.ctypes.data))
+        return out
+
     def precompute_images(self, img) -> "PrecomputedImages":
         """precompute_images::<OpenCVProcessing> (src/lib.rs:131-143); the pyramid stays on the device."""
         a = _as_gray(img)

@@ -44,6 +44,9 @@ struct Slot {
     uint8_t* d_in = nullptr;
     uint8_t* h_in = nullptr;  // pinned staging for pageable callers
     size_t in_cap = 0;
+    uint8_t* d_rgb = nullptr;  // interleaved RGB / RGBA input of the colour entry point (allocated on first use)
+    uint8_t* h_rgb = nullptr;
+    size_t rgb_cap = 0;
     // pyramid
     float* d_gauss = nullptr;
     uint32_t* d_mask = nullptr;
@@ -316,7 +319,7 @@ int alloc_slot(sb200_ctx* ctx, Slot& s) {
 void free_slot(Slot& s) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.ev_counts) cudaEventDestroy(s.ev_counts);
-    cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
+    cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
     cudaFree(s.d_rowoff); cudaFree(s.d_counts); cudaFree(s.d_sched); cudaFreeHost(s.h_counts); cudaFree(s.d_keys);
     cudaFree(s.d_refined); cudaFree(s.d_nori); cudaFree(s.d_angles); cudaFree(s.d_kpoff); cudaFree(s.d_kps);
     cudaFree(s.d_sort); cudaFree(s.d_order); cudaFree(s.d_out_kps); cudaFree(s.d_out_desc);
@@ -728,29 +731,57 @@ bool is_device_accessible_host(const void* p) {
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-// upload + full pipeline + async read-back of the counts for one group
-int launch_group(sb200_ctx* ctx, Slot& s, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
-                 uint64_t image_stride, int64_t limit, uint64_t first_img) {
+// interleaved 8-bit RGB(A) -> luma, the integer arithmetic of the `image` crate's grayscale() that the reference's
+// callers run before sift() (examples/run-sift.rs:8, src/lib.rs:1012): (2126 R + 7152 G + 722 B) / 10000
+__global__ void __launch_bounds__(256) k_luma(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray, size_t n_px,
+                                               int channels) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    const uint8_t* p = rgb + i * channels;
+    gray[i] = (uint8_t)((2126u * p[0] + 7152u * p[1] + 722u * p[2]) / 10000u);
+}
+
+// upload + full pipeline + async read-back of the counts for one group; channels = 1 (gray) or 3 / 4 (RGB / RGBA,
+// converted to luma on the device)
+int launch_group(sb200_ctx* ctx, Slot& s, const uint8_t* img, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                 uint64_t image_stride, int64_t limit, uint64_t first_img, uint32_t channels = 1) {
     cudaStream_t st = s.stream;
+    const size_t rowb = (size_t)w * channels;   // bytes per packed row
+    if (channels > 1 && s.rgb_cap < rowb * h * ctx->max_batch) {
+        CU(cudaStreamSynchronize(st));
+        cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb);
+        s.d_rgb = nullptr; s.h_rgb = nullptr; s.rgb_cap = 0;
+        const size_t cap = (size_t)ctx->max_w * ctx->max_h * 4 * ctx->max_batch;
+        CU(dalloc(&s.d_rgb, cap));
+        CU(cudaHostAlloc((void**)&s.h_rgb, cap, cudaHostAllocDefault));
+        s.rgb_cap = cap;
+    }
+    uint8_t* const d_up = channels > 1 ? s.d_rgb : s.d_in;
+    uint8_t* const h_up = channels > 1 ? s.h_rgb : s.h_in;
     const bool contiguous = (image_stride == (uint64_t)stride * h);
-    if (is_device_accessible_host(gray)) {
+    if (is_device_accessible_host(img)) {
         if (contiguous) {
-            CU(cudaMemcpy2DAsync(s.d_in, w, gray, stride, w, (size_t)h * n, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpy2DAsync(d_up, rowb, img, stride, rowb, (size_t)h * n, cudaMemcpyHostToDevice, st));
         } else {
             for (uint32_t i = 0; i < n; i++)
-                CU(cudaMemcpy2DAsync(s.d_in + (size_t)i * w * h, w, gray + i * image_stride, stride, w, h,
+                CU(cudaMemcpy2DAsync(d_up + (size_t)i * rowb * h, rowb, img + i * image_stride, stride, rowb, h,
                                      cudaMemcpyHostToDevice, st));
         }
     } else {
         // pageable memory: pack into the pinned staging buffer, then one async copy
         CU(cudaStreamSynchronize(st));  // staging buffer may still feed the previous upload
         for (uint32_t i = 0; i < n; i++) {
-            const uint8_t* src = gray + i * image_stride;
-            uint8_t* dst = s.h_in + (size_t)i * w * h;
-            if (stride == w) memcpy(dst, src, (size_t)w * h);
-            else for (uint32_t y = 0; y < h; y++) memcpy(dst + (size_t)y * w, src + (size_t)y * stride, w);
+            const uint8_t* src = img + i * image_stride;
+            uint8_t* dst = h_up + (size_t)i * rowb * h;
+            if (stride == rowb) memcpy(dst, src, rowb * h);
+            else for (uint32_t y = 0; y < h; y++) memcpy(dst + (size_t)y * rowb, src + (size_t)y * stride, rowb);
         }
-        CU(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)w * h * n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_up, h_up, rowb * h * n, cudaMemcpyHostToDevice, st));
+    }
+    if (channels > 1) {
+        const size_t n_px = (size_t)w * h * n;
+        k_luma<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(s.d_rgb, s.d_in, n_px, (int)channels);
+        ctx->launches++;
     }
     int rc = enqueue_pyramid(ctx, s, n, w, h, w, (uint64_t)w * h, s.d_in);
     if (rc) return rc;
@@ -966,10 +997,11 @@ void sb200_destroy(sb200_ctx* ctx) {
     delete ctx;
 }
 
-int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
-                        uint64_t image_stride, int64_t features_limit, sb200_result* out) {
+static int extract_batch_impl(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                              uint64_t image_stride, int64_t features_limit, sb200_result* out, uint32_t channels) {
     if (!ctx) return SB200_E_INVALID;
-    if (!gray || !out || n == 0 || stride < w) return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch");
+    if (!gray || !out || n == 0 || (uint64_t)stride < (uint64_t)w * channels || (channels != 1 && channels != 3 && channels != 4))
+        return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch");
     CU(cudaSetDevice(ctx->device));
     int rc = set_image_size(ctx, w, h);
     if (rc) return rc;
@@ -999,7 +1031,7 @@ int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_
     for (; g < sizes.size(); first += sizes[g], g++) {
         Slot& s = ctx->slot[g & 1];
         // groups complete in order: the slot's previous group (g-2) was collected before group g-1 launched
-        rc = launch_group(ctx, s, gray + first * image_stride, sizes[g], w, h, stride, image_stride, features_limit, first);
+        rc = launch_group(ctx, s, gray + first * image_stride, sizes[g], w, h, stride, image_stride, features_limit, first, channels);
         if (rc) return rc;
         if (g >= 1) {
             rc = collect_group(ctx, ctx->slot[(g - 1) & 1]);
@@ -1015,6 +1047,40 @@ int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_
     ctx->last_slot = 0;
     ctx->last_limit = features_limit;
     fill_result(ctx, n, out);
+    return SB200_OK;
+}
+
+int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                        uint64_t image_stride, int64_t features_limit, sb200_result* out) {
+    return extract_batch_impl(ctx, gray, n, w, h, stride, image_stride, features_limit, out, 1);
+}
+
+int sb200_extract_batch_rgb(sb200_ctx* ctx, const uint8_t* rgb, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                            uint64_t image_stride, uint32_t channels, int64_t features_limit, sb200_result* out) {
+    if (ctx && channels != 3 && channels != 4) return fail(ctx, SB200_E_INVALID, "channels must be 3 (RGB) or 4 (RGBA)");
+    return extract_batch_impl(ctx, rgb, n, w, h, stride, image_stride, features_limit, out, channels);
+}
+
+int sb200_rgb_to_luma(sb200_ctx* ctx, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t stride, uint32_t channels,
+                      uint8_t* gray) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!rgb || !gray || w == 0 || h == 0 || (channels != 3 && channels != 4) || (uint64_t)stride < (uint64_t)w * channels)
+        return fail(ctx, SB200_E_INVALID, "bad arguments to rgb_to_luma");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slot[0].stream;
+    uint8_t *d_rgb = nullptr, *d_gray = nullptr;
+    const size_t rowb = (size_t)w * channels, n_px = (size_t)w * h;
+    cudaError_t e = cudaMalloc((void**)&d_rgb, rowb * h);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_gray, n_px);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_rgb, rowb, rgb, stride, rowb, h, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_luma<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(d_rgb, d_gray, n_px, (int)channels);
+        ctx->launches++;
+        e = cudaMemcpyAsync(gray, d_gray, n_px, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_rgb); cudaFree(d_gray);
+    if (e != cudaSuccess) return fail(ctx, SB200_E_CUDA, "rgb_to_luma: %s", cudaGetErrorString(e));
     return SB200_OK;
 }
 

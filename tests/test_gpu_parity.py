@@ -233,3 +233,21 @@ def test_multi_device_shards(sf, oracle):
         assert np.abs(res[i].descriptors.astype(int) - odesc.astype(int)).max(initial=0) <= 1
     if ndev < 2:
         pytest.skip("single device: multi-context gather exercised with one context only")
+
+
+@pytest.mark.parametrize("channels", [3, 4])
+def test_rgb_input(sf, oracle, channels):
+    """Input prep of the reference's callers (image::grayscale, examples/run-sift.rs:8) on the device: same luma
+    bytes as the oracle's integer formula, and sift_rgb(rgb) == sift(luma(rgb))."""
+    rng = np.random.default_rng(41)
+    base = smooth_image(210, 170, 5).astype(np.int32)
+    rgb = np.clip(base[..., None] + rng.integers(-40, 41, (170, 210, channels)), 0, 255).astype(np.uint8)
+    luma = oracle.rgb_to_luma(rgb)
+    with sf.Extractor(210, 170, 1) as ex:
+        assert np.array_equal(ex.rgb_to_luma(rgb), luma)
+        assert ex.sift_rgb(rgb) == ex.sift(luma)
+    # extremes of the integer formula
+    edge = np.array([[[255, 255, 255], [0, 0, 0], [255, 0, 0], [0, 255, 0], [0, 0, 255], [1, 1, 1], [254, 255, 253], [3, 2, 200]]], np.uint8)
+    edge = np.repeat(np.repeat(edge, 8, 0), 2, 1)
+    with sf.Extractor(16, 8, 1) as ex:
+        assert np.array_equal(ex.rgb_to_luma(edge), oracle.rgb_to_luma(edge))
