@@ -157,6 +157,24 @@ def test_batch_equals_singles(sf, oracle):
     assert np.array_equal(_bits(kp[offs[5]:offs[6]]["x"]), _bits(okp["x"]))
 
 
+def test_large_batch_equals_singles(sf):
+    """A batch big enough for the batch-wide work queues of the orientation / descriptor kernels to run in their
+    chunked, request-ahead mode (> 57k keypoints in one group) and for sift_batch to taper its first and last
+    groups: still exactly the per-image results in image order."""
+    n, w, h = 48, 640, 480
+    imgs = np.stack([noise_image(w, h, 500 + i) for i in range(n)])
+    with sf.Extractor(w, h, 1) as one:
+        singles = [one.sift(imgs[i]) for i in range(n)]
+    assert sum(len(s) for s in singles) > 57000
+    for max_batch in (n, 8):        # one group of 48; groups of 2, 8, 8, 8, 8, 8, 4, 2
+        with sf.Extractor(w, h, max_batch) as ex:
+            offs, kp, de = ex.sift_batch(imgs)
+        assert len(offs) == n + 1 and offs[-1] == len(kp)
+        for i in range(n):
+            assert np.array_equal(singles[i].keypoint_array, kp[offs[i]:offs[i + 1]]), (max_batch, i)
+            assert np.array_equal(singles[i].descriptors, de[offs[i]:offs[i + 1]]), (max_batch, i)
+
+
 def test_deterministic(sf):
     g = noise_image(640, 480, 5)
     with sf.Extractor(640, 480, 2) as ex:
