@@ -247,16 +247,20 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
         const float gws = -1.0f / (2.0f * sigma * sigma);         // :667
         const int side = 2 * radius + 1, total = side * side;
         float acc0 = 0.f, acc1 = 0.f;  // bins `lane` and `32 + lane`
-        // sample `idx` of the (2r+1)^2 window in raster order: pixel loads are issued one batch of 32 ahead
+        // sample `idx` of the (2r+1)^2 window in raster order: pixel loads are issued one batch of 32 ahead.
+        // The lane's (row, column) advance by 32 samples per batch: at most two row wraps (side >= 17), no division.
+        int yq_n = lane / side, xq_n = lane - yq_n * side;   // window coordinates of the lane's next sample
         auto fetch = [&](const int idx, int& yp, int& xp, float4& q) -> bool {
-            const int yq = idx / side;
-            yp = yq - radius; xp = idx - yq * side - radius;
+            yp = yq_n - radius; xp = xq_n - radius;
             const int yi = y + yp, xi = x + xp;
             const bool in = idx < total && yi > 0 && yi < h - 1 && xi > 0 && xi < w - 1;
             if (in) {
                 const float* c = I + (yi * pitch + xi);
                 q = make_float4(__ldg(c + 1), __ldg(c - 1), __ldg(c - pitch), __ldg(c + pitch));
             }
+            xq_n += 32;
+            if (xq_n >= side) { xq_n -= side; yq_n++; }
+            if (xq_n >= side) { xq_n -= side; yq_n++; }
             return in;
         };
         int yp_n, xp_n;
@@ -593,8 +597,13 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     const float col_rot = fx * G.cos_s - fy * G.sin_s;
     const float row_rot = fx * G.sin_s + fy * G.cos_s;
     const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
-    // src/lib.rs:834-837 (the image-bounds half of the test, :838-841, is enforced by the span construction)
-    const bool member = active & (row_bin > -0.5f) & (row_bin < 4.5f) & (col_bin > -0.5f) & (col_bin < 4.5f);
+    // The membership test of src/lib.rs:834-837, -0.5 < row_bin, col_bin < 4.5, needs no instruction of its own:
+    // it holds exactly when floor(row_bin - 0.5) and floor(col_bin - 0.5) lie in -1..3 (at the one value where the
+    // two differ, row_bin == -0.5, the sample's share of every kept cell is c1 = mag * 0 = +0), and a sample whose
+    // floors are outside that range has no valid cell below, so all of it lands in the spare cell.  Lanes without a
+    // sample carry zero pixels: their magnitude, hence every contribution, is +0.  (The image-bounds half of the
+    // test, :838-841, is enforced by the span construction.)
+    (void)active;
     const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
     const float dx = px.xp - px.xm;
     const float dy = px.ym - px.yp;
@@ -623,7 +632,7 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     const int r1 = (int)row_floor, q1 = (int)col_floor;
     const int o0 = ((int)ori_floor) & 7;           // ori_floor in [-16, 16): wrap like :926-938
     const int o1 = (o0 + 1) & 7;
-    const bool r0ok = member & ((unsigned)r1 <= 3u), r1ok = member & ((unsigned)(r1 + 1) <= 3u);
+    const bool r0ok = (unsigned)r1 <= 3u, r1ok = (unsigned)(r1 + 1) <= 3u;
     const bool q0ok = (unsigned)q1 <= 3u, q1ok = (unsigned)(q1 + 1) <= 3u;
     const int cell00 = r1 * 4 + q1;
     int cw[4];  // word offsets of the four spatial cells (k >> 1: bit 0 = column step, bit 1 = row step)
