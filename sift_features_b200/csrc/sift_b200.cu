@@ -66,6 +66,12 @@ struct Slot {
     OutKeyPoint* d_out_kps = nullptr;
     uint8_t* d_out_desc = nullptr;
     uint32_t* h_counts = nullptr;  // pinned mirror of d_counts
+    // CUDA graphs of the whole per-group kernel sequence, keyed by its launch parameters (a few shapes per slot)
+    struct PipeGraph {
+        uint32_t n, w, h, stride; uint64_t img_stride; const uint8_t* d_in;
+        cudaGraphExec_t exec; uint64_t launches, stage_launches[SB200_STAGE_COUNT]; uint64_t last_use;
+    };
+    std::vector<PipeGraph> graphs;
     // state of the group in flight
     uint32_t n_imgs = 0;
     uint64_t first_img = 0;
@@ -93,6 +99,8 @@ struct sb200_ctx {
     bool march = true;                         // SB200_BLUR=tile selects the independent-tile TMA blur (debugging aid)
     int seg_rows_override = 0;                 // SB200_SEG_ROWS: fixed segment height of the marching blur (tests)
     bool tail = true;                          // SB200_TAIL=0: per-layer launches for the small octaves too (debugging aid)
+    bool use_graphs = true;                    // SB200_GRAPHS=0: plain stream launches
+    uint64_t graph_clock = 0;
     CUtensorMap tmap_ex[2][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
     bool tmap_ok[MAX_OCT] = {false};
     void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
@@ -317,6 +325,8 @@ int alloc_slot(sb200_ctx* ctx, Slot& s) {
 }
 
 void free_slot(Slot& s) {
+    for (auto& g : s.graphs) cudaGraphExecDestroy(g.exec);
+    s.graphs.clear();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.ev_counts) cudaEventDestroy(s.ev_counts);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
@@ -722,6 +732,62 @@ int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
     return SB200_OK;
 }
 
+// The whole kernel sequence of one group (pyramid + detection) -- about fifty launches whose grids and arguments
+// depend only on (n, w, h, input pointer / strides, limit or not) -- is captured once per such shape into a CUDA graph
+// and replayed: one launch per group on the host, and no per-kernel launch latency between the many short kernels of
+// the small octaves on the device.  Stage timing (profiling) needs events between the kernels: plain launches then.
+int run_pipeline(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, uint32_t stride, uint64_t img_stride,
+                 const uint8_t* d_in, int64_t limit) {
+    if (!ctx->use_graphs || ctx->profiling) {
+        int rc = enqueue_pyramid(ctx, s, n, w, h, stride, img_stride, d_in);
+        if (rc) return rc;
+        return enqueue_detect(ctx, s, n, limit);
+    }
+    if (limit >= 0) {   // features_limit is a kernel argument (and adds the sort): run directly
+        int rc = enqueue_pyramid(ctx, s, n, w, h, stride, img_stride, d_in);
+        if (rc) return rc;
+        return enqueue_detect(ctx, s, n, limit);
+    }
+    Slot::PipeGraph* hit = nullptr;
+    for (auto& g : s.graphs)
+        if (g.n == n && g.w == w && g.h == h && g.stride == stride && g.img_stride == img_stride && g.d_in == d_in) hit = &g;
+    if (!hit) {
+        const uint64_t l0 = ctx->launches;
+        uint64_t sl0[SB200_STAGE_COUNT];
+        for (int i = 0; i < SB200_STAGE_COUNT; i++) sl0[i] = ctx->stage_launches[i];
+        CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_pyramid(ctx, s, n, w, h, stride, img_stride, d_in);
+        if (!rc) rc = enqueue_detect(ctx, s, n, limit);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(ctx, SB200_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        Slot::PipeGraph g{};
+        g.n = n; g.w = w; g.h = h; g.stride = stride; g.img_stride = img_stride; g.d_in = d_in;
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(ctx, SB200_E_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e));
+        g.launches = ctx->launches - l0;
+        for (int i = 0; i < SB200_STAGE_COUNT; i++) g.stage_launches[i] = ctx->stage_launches[i] - sl0[i];
+        // the capture itself launched nothing: undo the counts, the replay below adds them
+        ctx->launches = l0;
+        for (int i = 0; i < SB200_STAGE_COUNT; i++) ctx->stage_launches[i] = sl0[i];
+        if (s.graphs.size() >= 6) {   // evict the least recently used shape
+            size_t k = 0;
+            for (size_t i = 1; i < s.graphs.size(); i++) if (s.graphs[i].last_use < s.graphs[k].last_use) k = i;
+            cudaGraphExecDestroy(s.graphs[k].exec);
+            s.graphs.erase(s.graphs.begin() + k);
+        }
+        s.graphs.push_back(g);
+        hit = &s.graphs.back();
+    }
+    hit->last_use = ++ctx->graph_clock;
+    CU(cudaGraphLaunch(hit->exec, s.stream));
+    ctx->launches += hit->launches;
+    for (int i = 0; i < SB200_STAGE_COUNT; i++) ctx->stage_launches[i] += hit->stage_launches[i];
+    return SB200_OK;
+}
+
 bool is_device_accessible_host(const void* p) {
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -783,9 +849,7 @@ int launch_group(sb200_ctx* ctx, Slot& s, const uint8_t* img, uint32_t n, uint32
         k_luma<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(s.d_rgb, s.d_in, n_px, (int)channels);
         ctx->launches++;
     }
-    int rc = enqueue_pyramid(ctx, s, n, w, h, w, (uint64_t)w * h, s.d_in);
-    if (rc) return rc;
-    rc = enqueue_detect(ctx, s, n, limit);
+    int rc = run_pipeline(ctx, s, n, w, h, w, (uint64_t)w * h, s.d_in, limit);
     if (rc) return rc;
     CU(cudaMemcpyAsync(s.h_counts, s.d_counts, (4 * (size_t)ctx->max_batch + 1) * sizeof(uint32_t),
                        cudaMemcpyDeviceToHost, st));
@@ -937,6 +1001,8 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         {
             const char* e = getenv("SB200_BLUR");
             ctx->march = !(e && !strcmp(e, "tile"));
+            const char* gr = getenv("SB200_GRAPHS");
+            ctx->use_graphs = !(gr && !strcmp(gr, "0"));
             const char* tl = getenv("SB200_TAIL");
             ctx->tail = !(tl && !strcmp(tl, "0"));
             CU(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM));
@@ -1102,9 +1168,7 @@ int sb200_extract_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n
     Slot& s = ctx->slot[ctx->dev_rr];
     ctx->last_slot = ctx->dev_rr;
     ctx->dev_rr ^= 1;
-    rc = enqueue_pyramid(ctx, s, n, w, h, stride, image_stride, d_gray);
-    if (rc) return rc;
-    rc = enqueue_detect(ctx, s, n, features_limit);
+    rc = run_pipeline(ctx, s, n, w, h, stride, image_stride, d_gray, features_limit);
     if (rc) return rc;
     s.n_imgs = n;
     ctx->have_single = ctx->have_pyramid = (n == 1);
