@@ -39,6 +39,9 @@ const char* kStageNames[SB200_STAGE_COUNT] = {"seed", "blur", "extrema", "refine
 struct Slot {
     int index = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;       // layers 4, 5 and the extrema scan of an octave run here while the main stream
+    cudaEvent_t ev_fork = nullptr;     // already builds the next octave (which only needs layer 3)
+    cudaEvent_t ev_join = nullptr;
     cudaEvent_t ev_counts = nullptr;
     // input
     uint8_t* d_in = nullptr;
@@ -100,6 +103,7 @@ struct sb200_ctx {
     int seg_rows_override = 0;                 // SB200_SEG_ROWS: fixed segment height of the marching blur (tests)
     bool tail = true;                          // SB200_TAIL=0: per-layer launches for the small octaves too (debugging aid)
     bool use_graphs = true;                    // SB200_GRAPHS=0: plain stream launches
+    bool fork_octaves = true;                  // SB200_FORK=0: every kernel of a group on one stream
     uint64_t graph_clock = 0;
     CUtensorMap tmap_ex[2][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
     bool tmap_ok[MAX_OCT] = {false};
@@ -300,7 +304,10 @@ cudaError_t dalloc(T** p, size_t count) {
 int alloc_slot(sb200_ctx* ctx, Slot& s) {
     const size_t B = ctx->max_batch, cap = ctx->cap;
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.ev_counts, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
     s.in_cap = (size_t)ctx->max_w * ctx->max_h * B;
     CU(dalloc(&s.d_in, s.in_cap));
     CU(cudaHostAlloc((void**)&s.h_in, std::max<size_t>(s.in_cap, 1), cudaHostAllocDefault));
@@ -328,7 +335,10 @@ void free_slot(Slot& s) {
     for (auto& g : s.graphs) cudaGraphExecDestroy(g.exec);
     s.graphs.clear();
     if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.side) cudaStreamDestroy(s.side);
     if (s.ev_counts) cudaEventDestroy(s.ev_counts);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
     cudaFree(s.d_rowoff); cudaFree(s.d_counts); cudaFree(s.d_sched); cudaFreeHost(s.h_counts); cudaFree(s.d_keys);
     cudaFree(s.d_refined); cudaFree(s.d_nori); cudaFree(s.d_angles); cudaFree(s.d_kpoff); cudaFree(s.d_kps);
@@ -568,12 +578,25 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
         }
     }
     const int o_tail = tail_first_octave(ctx);
+    // Octave o+1 starts from the decimated layer 3 of octave o: layers 4 and 5 and the extrema scan of octave o are
+    // forked onto the slot's side stream so that the chain of octaves (the critical path of a small batch) does not
+    // wait for them.  Stage timing needs one stream.
+    const bool fork = ctx->fork_octaves && !ctx->profiling;
+    bool forked = false;
+    cudaStream_t const st_main = st;
     for (int o = 0; o < o_tail; o++) {
         const OctLayout& ol = L.o[o];
         if (ol.w < 1 || ol.h < 1) continue;
+        st = st_main;
         {
             StageScope sc(ctx, st, SB200_STAGE_BLUR);
             for (int l = 1; l < N_LAYERS; l++) {
+                if (fork && l == 4) {
+                    CU(cudaEventRecord(s.ev_fork, st_main));
+                    CU(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
+                    st = s.side;
+                    forked = true;
+                }
                 BlurParams p{};
                 p.src = s.d_gauss + ol.off + (long long)(l - 1) * ol.layer_stride;
                 p.dst = s.d_gauss + ol.off + (long long)l * ol.layer_stride;
@@ -642,6 +665,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             count_launch(ctx, SB200_STAGE_EXTREMA);
         }
     }
+    st = st_main;
     if (o_tail < L.n_oct && L.o[o_tail].w >= 1 && L.o[o_tail].h >= 1) {
         // blurs + decimation + extrema of all the remaining (small) octaves: one CTA per image, one launch
         StageScope sc(ctx, st, SB200_STAGE_BLUR);
@@ -650,6 +674,10 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
         t.gauss = s.d_gauss; t.mask = s.d_mask; t.rows = s.d_rows;
         k_tail<false><<<n, TAIL_THREADS, TAIL_SMEM, st>>>(t);
         count_launch(ctx, SB200_STAGE_BLUR);
+    }
+    if (forked) {   // join: the candidate scan needs every octave's mask
+        CU(cudaEventRecord(s.ev_join, s.side));
+        CU(cudaStreamWaitEvent(st_main, s.ev_join, 0));
     }
     CU(cudaGetLastError());
     return SB200_OK;
@@ -1001,6 +1029,8 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         {
             const char* e = getenv("SB200_BLUR");
             ctx->march = !(e && !strcmp(e, "tile"));
+            const char* fk = getenv("SB200_FORK");
+            ctx->fork_octaves = !(fk && !strcmp(fk, "0"));
             const char* gr = getenv("SB200_GRAPHS");
             ctx->use_graphs = !(gr && !strcmp(gr, "0"));
             const char* tl = getenv("SB200_TAIL");
