@@ -1198,6 +1198,18 @@ int sb200_extract_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n
     Slot& s = ctx->slot[ctx->dev_rr];
     ctx->last_slot = ctx->dev_rr;
     ctx->dev_rr ^= 1;
+    if (ctx->use_graphs && !ctx->profiling && features_limit < 0 && d_gray != s.d_in) {
+        // pack the group into the slot's own input buffer (1 B/px against ~370 B/px of pyramid traffic) so that the
+        // captured graph does not depend on the caller's pointer and strides
+        if (image_stride == (uint64_t)stride * h) {
+            CU(cudaMemcpy2DAsync(s.d_in, w, d_gray, stride, w, (size_t)h * n, cudaMemcpyDeviceToDevice, s.stream));
+        } else {
+            for (uint32_t i = 0; i < n; i++)
+                CU(cudaMemcpy2DAsync(s.d_in + (size_t)i * w * h, w, d_gray + i * image_stride, stride, w, h,
+                                     cudaMemcpyDeviceToDevice, s.stream));
+        }
+        d_gray = s.d_in; stride = w; image_stride = (uint64_t)w * h;
+    }
     rc = run_pipeline(ctx, s, n, w, h, stride, image_stride, d_gray, features_limit);
     if (rc) return rc;
     s.n_imgs = n;
