@@ -701,24 +701,39 @@ __global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM
             float2 c[C::PY + 2 * R];
 #pragma unroll
             for (int j = 0; j < C::PY + 2 * R; j++) c[j] = *reinterpret_cast<const float2*>(base + j * C::IPITCH);
-            float* q = qband;
-            const bool fast = x_full && gy0 + C::PY <= yb;
+            // all PY outputs first (PY independent FADD2 -> FFMA2 chains the scheduler can interleave), stores after
+            float2 out[C::PY];
 #pragma unroll
             for (int j = 0; j < C::PY; j++) {
                 float2 acc = mul2(c[j + R], c_taps2[L][R]);
 #pragma unroll
                 for (int i = 1; i <= R; i++) acc = fma2(add2(c[j + R + i], c[j + R - i]), c_taps2[L][R + i], acc);
-                if (fast) {
-                    *reinterpret_cast<float2*>(q) = acc;
-                } else if (gy0 + j < yb) {
-                    if (x_full) *reinterpret_cast<float2*>(q) = acc;
-                    else q[0] = acc.x;
+                out[j] = acc;
+            }
+            float* q = qband;
+            if (x_full && gy0 + C::PY <= yb) {
+#pragma unroll
+                for (int j = 0; j < C::PY; j++) {
+                    *reinterpret_cast<float2*>(q) = out[j];
+                    q += p.pitch;
                 }
-                if (DECIMATE && !(j & 1)) {   // ya, y0 and gx are even: output row gy0 + j is even
-                    const int dy = (gy0 + j) >> 1, dx = gx >> 1;
-                    if (gy0 + j < yb && dy < p.dec_h && dx < p.dec_w) dband[(long long)(j >> 1) * p.dec_pitch] = acc.x;
+            } else {
+#pragma unroll
+                for (int j = 0; j < C::PY; j++) {
+                    if (gy0 + j < yb) {
+                        if (x_full) *reinterpret_cast<float2*>(q) = out[j];
+                        else q[0] = out[j].x;
+                    }
+                    q += p.pitch;
                 }
-                q += p.pitch;
+            }
+            if (DECIMATE) {   // ya, y0 and gx are even: output row gy0 + j is even for even j
+                const int dx = gx >> 1;
+#pragma unroll
+                for (int j = 0; j < C::PY; j += 2) {
+                    const int dy = (gy0 + j) >> 1;
+                    if (gy0 + j < yb && dy < p.dec_h && dx < p.dec_w) dband[(long long)(j >> 1) * p.dec_pitch] = out[j].x;
+                }
             }
         }
         qband += (long long)C::BH * p.pitch;
