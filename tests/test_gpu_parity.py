@@ -73,6 +73,15 @@ def test_noise_images(sf, oracle, w, h, seed):
     _check_image(sf, oracle, noise_image(w, h, seed))
 
 
+@pytest.mark.parametrize("w,h", [(60, 34), (61, 35), (64, 64), (65, 51), (90, 68), (120, 17), (128, 96), (129, 33),
+                                 (30, 128), (33, 257), (255, 16), (512, 9)])
+def test_boundary_sizes(sf, oracle, w, h):
+    """Sizes whose 2x seed image / octaves land on and next to the kernels' internal boundaries: 60-column extrema
+    strips, 64- and 128-column blur strips, 32-row bands, 34-row extrema blocks, the 32-pixel TMA threshold and the
+    64x36 tail threshold."""
+    _check_image(sf, oracle, noise_image(w, h, 1000 + w * 7 + h))
+
+
 @pytest.mark.parametrize("w,h,seed", [(400, 300, 11), (333, 222, 12)])
 def test_smooth_images(sf, oracle, w, h, seed):
     _check_image(sf, oracle, smooth_image(w, h, seed))
