@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsift_b200.so")
+# SB200_LIB: an alternative build of the same library (development A/B runs); the default is the in-tree build
+LIB_PATH = os.environ.get("SB200_LIB") or os.path.join(_HERE, "libsift_b200.so")
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_STATE = 0, 1, 2, 3, 4
 DESC_SIZE = 128

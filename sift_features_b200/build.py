@@ -45,7 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     extra = os.environ.get("SB200_NVCC_EXTRA", "").split()   # development knob, e.g. -DSB_MARCH_TW(l)=64
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    out = os.environ.get("SB200_BUILD_OUT", LIB)              # development knob: build a variant next to the real one
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

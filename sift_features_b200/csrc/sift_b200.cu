@@ -34,6 +34,12 @@ static_assert(sizeof(MatchOut) == sizeof(sb200_dmatch), "match layout");
 
 namespace {
 
+// groups in flight per context: upload / pyramid / keypoint stages of consecutive groups overlap across slots
+#ifndef SB_SLOTS
+#define SB_SLOTS 2
+#endif
+constexpr int N_SLOTS = SB_SLOTS;
+
 const char* kStageNames[SB200_STAGE_COUNT] = {"seed", "blur", "extrema", "refine", "orient", "descriptor", "top_blur"};
 
 struct Slot {
@@ -92,20 +98,20 @@ struct sb200_ctx {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0, cap = 0;
     std::string err;
-    Slot slot[2];
+    Slot slot[N_SLOTS];
     // layout of the current image size
     PyrLayout L{};
     uint32_t cur_w = 0, cur_h = 0;
     // TMA descriptors of the Gaussian arenas: [slot][octave][destination layer 1..5]
-    CUtensorMap tmap[2][MAX_OCT][N_LAYERS];
-    CUtensorMap tmap_m[2][MAX_OCT][N_LAYERS];  // marching blur: (BW x 32) boxes
+    CUtensorMap tmap[N_SLOTS][MAX_OCT][N_LAYERS];
+    CUtensorMap tmap_m[N_SLOTS][MAX_OCT][N_LAYERS];  // marching blur: (BW x 32) boxes
     bool march = true;                         // SB200_BLUR=tile selects the independent-tile TMA blur (debugging aid)
     int seg_rows_override = 0;                 // SB200_SEG_ROWS: fixed segment height of the marching blur (tests)
     bool tail = true;                          // SB200_TAIL=0: per-layer launches for the small octaves too (debugging aid)
     bool use_graphs = true;                    // SB200_GRAPHS=0: plain stream launches
     bool fork_octaves = true;                  // SB200_FORK=0: every kernel of a group on one stream
     uint64_t graph_clock = 0;
-    CUtensorMap tmap_ex[2][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
+    CUtensorMap tmap_ex[N_SLOTS][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
     bool tmap_ok[MAX_OCT] = {false};
     void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
     // capacities the arenas were sized for
@@ -438,7 +444,7 @@ int build_tensor_maps(sb200_ctx* ctx) {
     for (int o = 0; o < ctx->L.n_oct; o++) {
         const OctLayout& ol = ctx->L.o[o];
         if (ol.w < TMA_MIN_DIM || ol.h < TMA_MIN_DIM) continue;
-        for (int sl = 0; sl < 2; sl++) {
+        for (int sl = 0; sl < N_SLOTS; sl++) {
             int r;
             if ((o == 0 && (r = encode_one<0>(ctx, sl, o))) || (r = encode_one<1>(ctx, sl, o)) || (r = encode_one<2>(ctx, sl, o)) || (r = encode_one<3>(ctx, sl, o)) ||
                 (r = encode_one<4>(ctx, sl, o)) || (r = encode_one<5>(ctx, sl, o)) || (r = encode_extrema(ctx, sl, o)) ||
@@ -1076,7 +1082,7 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
             else
                 return fail(ctx, SB200_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
         }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < N_SLOTS; i++) {
             ctx->slot[i].index = i;
             if ((r = alloc_slot(ctx, ctx->slot[i]))) return r;
         }
@@ -1140,17 +1146,21 @@ static int extract_batch_impl(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, u
     uint32_t g = 0;
     uint64_t first = 0;
     for (; g < sizes.size(); first += sizes[g], g++) {
-        Slot& s = ctx->slot[g & 1];
-        // groups complete in order: the slot's previous group (g-2) was collected before group g-1 launched
+        Slot& s = ctx->slot[g % N_SLOTS];
+        // groups complete in launch order; the slot's previous group was collected before this launch (below)
         rc = launch_group(ctx, s, gray + first * image_stride, sizes[g], w, h, stride, image_stride, features_limit, first, channels);
         if (rc) return rc;
-        if (g >= 1) {
-            rc = collect_group(ctx, ctx->slot[(g - 1) & 1]);
+        // the slot the NEXT group will use must be free again: collect the group that ran in it
+        if (g + 1 >= (uint32_t)N_SLOTS) {
+            rc = collect_group(ctx, ctx->slot[(g + 1) % N_SLOTS]);
             if (rc) return rc;
         }
     }
-    rc = collect_group(ctx, ctx->slot[(g - 1) & 1]);
-    if (rc) return rc;
+    // remaining groups in launch order (collect_group is a no-op for idle slots)
+    for (uint32_t k = 0; k < (uint32_t)N_SLOTS; k++) {
+        rc = collect_group(ctx, ctx->slot[(g + k) % N_SLOTS]);
+        if (rc) return rc;
+    }
     rc = finish_all(ctx);
     if (rc) return rc;
     ctx->have_single = (n == 1);
@@ -1212,7 +1222,7 @@ int sb200_extract_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n
     // (small octaves, keypoint kernels) overlaps the head of the next
     Slot& s = ctx->slot[ctx->dev_rr];
     ctx->last_slot = ctx->dev_rr;
-    ctx->dev_rr ^= 1;
+    ctx->dev_rr = (ctx->dev_rr + 1) % N_SLOTS;
     if (ctx->use_graphs && !ctx->profiling && features_limit < 0 && d_gray != s.d_in) {
         // pack the group into the slot's own input buffer (1 B/px against ~370 B/px of pyramid traffic) so that the
         // captured graph does not depend on the caller's pointer and strides
@@ -1680,17 +1690,19 @@ int sb200_timer_start(sb200_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     // the timer lives on slot 0's stream; slot 1 is ordered behind it through a dependency event
     CU(cudaEventRecord(ctx->t0, ctx->slot[0].stream));
-    CU(cudaStreamWaitEvent(ctx->slot[1].stream, ctx->t0, 0));
+    for (int i = 1; i < N_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].stream, ctx->t0, 0));
     return SB200_OK;
 }
 
 int sb200_timer_stop(sb200_ctx* ctx) {
     if (!ctx) return SB200_E_INVALID;
     CU(cudaSetDevice(ctx->device));
-    cudaEvent_t j = get_event(ctx);
-    CU(cudaEventRecord(j, ctx->slot[1].stream));
-    CU(cudaStreamWaitEvent(ctx->slot[0].stream, j, 0));
-    ctx->ev_pool.push_back(j);
+    for (int i = 1; i < N_SLOTS; i++) {
+        cudaEvent_t j = get_event(ctx);
+        CU(cudaEventRecord(j, ctx->slot[i].stream));
+        CU(cudaStreamWaitEvent(ctx->slot[0].stream, j, 0));
+        ctx->ev_pool.push_back(j);
+    }
     CU(cudaEventRecord(ctx->t1, ctx->slot[0].stream));
     return SB200_OK;
 }

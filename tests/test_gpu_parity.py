@@ -106,6 +106,15 @@ def test_blur_segment_heights(sf, oracle, monkeypatch, seg_rows):
     _check_image(sf, oracle, noise_image(700, 650, 21))
 
 
+@pytest.mark.parametrize("env", [{"SB200_BLUR": "tile"}, {"SB200_TAIL": "0"}, {"SB200_GRAPHS": "0", "SB200_FORK": "0"}])
+def test_alternative_paths(sf, oracle, monkeypatch, env):
+    """The debugging switches select older / simpler code paths (independent-tile TMA blur, per-layer launches for
+    the small octaves, plain single-stream launches without graph capture): same bit-exact results."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _check_image(sf, oracle, noise_image(520, 390, 77))
+
+
 def test_flat_regions(sf, oracle):
     """Saturated / constant blocks: every pixel of such a block passes the reference's extremum test with
     ties (src/lib.rs:437-506) and dies in interpolate_extremum; the candidate list must still be the reference's."""
