@@ -377,6 +377,19 @@ def run_b200(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": 1, "kind": "port",
                                     "sample": f"{n_cpu} of the step's images, single thread (the crate is "
                                               "single-threaded); oracle C port of src/lib.rs"}
+            # the reference's own second bench (benches/sift.rs:99-113, `opencv_sift`): OpenCV's SIFT on one image
+            try:
+                import cv2
+                cv2.setNumThreads(1)
+                im = np.ascontiguousarray(sets_h[0][1][0])
+                sift = cv2.SIFT_create()
+                t0 = time.perf_counter()
+                kps, _ = sift.detectAndCompute(im, None)
+                dt = time.perf_counter() - t0
+                line["opencv_sift_cpu"] = {"value": 1.0 / dt, "unit": "images/s", "cores": 1, "keypoints": len(kps),
+                                           "sample": "cv2.SIFT_create().detectAndCompute on 1 image, cv2.setNumThreads(1)"}
+            except Exception as e:   # informational only
+                line["opencv_sift_cpu"] = {"unavailable": str(e)[:80]}
         print(json.dumps(line), flush=True)
     ex.close()
     dist.close()
