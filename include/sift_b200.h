@@ -45,7 +45,8 @@ extern "C" {
 #define SB200_OK 0
 #define SB200_E_INVALID 1   /* bad argument (null pointer, zero size, image larger than the context) */
 #define SB200_E_CUDA 2      /* CUDA runtime / driver error, no device, out of memory */
-#define SB200_E_CAPACITY 3  /* more candidates/keypoints than the context was sized for */
+#define SB200_E_CAPACITY 3  /* an output buffer / the device-resident result is too small (the host entry points grow
+                               the context's own per-candidate arrays transparently and never return this) */
 #define SB200_E_STATE 4     /* call needs a prior sb200_precompute / extract on this context */
 
 typedef struct sb200_ctx sb200_ctx;

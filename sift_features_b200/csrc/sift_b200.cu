@@ -84,6 +84,7 @@ struct Slot {
     // state of the group in flight
     uint32_t n_imgs = 0;
     uint64_t first_img = 0;
+    int64_t limit = -1;
     bool busy = false;
 };
 
@@ -307,6 +308,29 @@ cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
 }
 
+// per-candidate / per-keypoint arrays of a slot, sized by the context's current capacity
+int alloc_cand_arrays(sb200_ctx* ctx, Slot& s) {
+    const size_t B = ctx->max_batch, cap = ctx->cap;
+    CU(dalloc(&s.d_keys, cap * B));
+    CU(dalloc(&s.d_refined, cap * B));
+    CU(dalloc(&s.d_nori, cap * B));
+    CU(dalloc(&s.d_angles, cap * B * MAX_ORI));
+    CU(dalloc(&s.d_kpoff, cap * B));
+    CU(dalloc(&s.d_kps, cap * B));
+    CU(dalloc(&s.d_sort, 4 * cap * B));
+    CU(dalloc(&s.d_order, cap * B));
+    CU(dalloc(&s.d_out_kps, cap * B));
+    CU(dalloc(&s.d_out_desc, cap * B * DESC_SIZE));
+    return SB200_OK;
+}
+
+void free_cand_arrays(Slot& s) {
+    cudaFree(s.d_keys); cudaFree(s.d_refined); cudaFree(s.d_nori); cudaFree(s.d_angles); cudaFree(s.d_kpoff);
+    cudaFree(s.d_kps); cudaFree(s.d_sort); cudaFree(s.d_order); cudaFree(s.d_out_kps); cudaFree(s.d_out_desc);
+    s.d_keys = nullptr; s.d_refined = nullptr; s.d_nori = nullptr; s.d_angles = nullptr; s.d_kpoff = nullptr;
+    s.d_kps = nullptr; s.d_sort = nullptr; s.d_order = nullptr; s.d_out_kps = nullptr; s.d_out_desc = nullptr;
+}
+
 int alloc_slot(sb200_ctx* ctx, Slot& s) {
     const size_t B = ctx->max_batch, cap = ctx->cap;
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -324,17 +348,7 @@ int alloc_slot(sb200_ctx* ctx, Slot& s) {
     CU(dalloc(&s.d_counts, 4 * B + 1));
     CU(dalloc(&s.d_sched, 2 * B + 5));
     CU(cudaHostAlloc((void**)&s.h_counts, (4 * B + 1) * sizeof(uint32_t), cudaHostAllocDefault));
-    CU(dalloc(&s.d_keys, cap * B));
-    CU(dalloc(&s.d_refined, cap * B));
-    CU(dalloc(&s.d_nori, cap * B));
-    CU(dalloc(&s.d_angles, cap * B * MAX_ORI));
-    CU(dalloc(&s.d_kpoff, cap * B));
-    CU(dalloc(&s.d_kps, cap * B));
-    CU(dalloc(&s.d_sort, 4 * cap * B));
-    CU(dalloc(&s.d_order, cap * B));
-    CU(dalloc(&s.d_out_kps, cap * B));
-    CU(dalloc(&s.d_out_desc, cap * B * DESC_SIZE));
-    return SB200_OK;
+    return alloc_cand_arrays(ctx, s);
 }
 
 void free_slot(Slot& s) {
@@ -346,9 +360,8 @@ void free_slot(Slot& s) {
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
-    cudaFree(s.d_rowoff); cudaFree(s.d_counts); cudaFree(s.d_sched); cudaFreeHost(s.h_counts); cudaFree(s.d_keys);
-    cudaFree(s.d_refined); cudaFree(s.d_nori); cudaFree(s.d_angles); cudaFree(s.d_kpoff); cudaFree(s.d_kps);
-    cudaFree(s.d_sort); cudaFree(s.d_order); cudaFree(s.d_out_kps); cudaFree(s.d_out_desc);
+    cudaFree(s.d_rowoff); cudaFree(s.d_counts); cudaFree(s.d_sched); cudaFreeHost(s.h_counts);
+    free_cand_arrays(s);
     s = Slot{};
 }
 
@@ -905,25 +918,55 @@ int launch_group(sb200_ctx* ctx, Slot& s, const uint8_t* img, uint32_t n, uint32
     CU(cudaEventRecord(s.ev_counts, st));
     s.n_imgs = n;
     s.first_img = first_img;
+    s.limit = limit;
     s.busy = true;
     return SB200_OK;
 }
 
 // waits for the group's counts, appends its results to the context's result arrays
+// An image with more candidates / keypoints than the context was sized for (exact ramps and the like: every pixel
+// ties) does not fail the call: the per-candidate arrays of all slots are re-allocated larger and the detection
+// stages are run again on the pyramids and extrema masks still resident in the slots.
+int grow_capacity(sb200_ctx* ctx, uint32_t need) {
+    for (auto& t : ctx->slot) {
+        CU(cudaStreamSynchronize(t.stream));
+        CU(cudaStreamSynchronize(t.side));
+    }
+    const uint64_t nc = std::max<uint64_t>((uint64_t)need + need / 4 + 1024, (uint64_t)ctx->cap * 2);
+    if (nc > 0x3fffffffull) return fail(ctx, SB200_E_CAPACITY, "%u candidates per image exceed the supported maximum", need);
+    ctx->cap = (uint32_t)nc;
+    for (auto& t : ctx->slot) {
+        for (auto& g : t.graphs) cudaGraphExecDestroy(g.exec);   // the graphs hold the old pointers and capacity
+        t.graphs.clear();
+        free_cand_arrays(t);
+        int rc = alloc_cand_arrays(ctx, t);
+        if (rc) return rc;
+    }
+    return SB200_OK;
+}
+
 int collect_group(sb200_ctx* ctx, Slot& s) {
     if (!s.busy) return SB200_OK;
-    CU(cudaEventSynchronize(s.ev_counts));
-    s.busy = false;
     const uint32_t B = ctx->max_batch, n = s.n_imgs;
     const uint32_t* cand = s.h_counts;
     const uint32_t* kpc = s.h_counts + B;
     const uint32_t* outoff = s.h_counts + 3 * B;
-    for (uint32_t i = 0; i < n; i++) {
-        if (cand[i] > ctx->cap || kpc[i] > ctx->cap)
-            return fail(ctx, SB200_E_CAPACITY,
-                        "image %llu: %u candidates / %u keypoints exceed the context capacity %u",
-                        (unsigned long long)(s.first_img + i), cand[i], kpc[i], ctx->cap);
+    for (;;) {
+        CU(cudaEventSynchronize(s.ev_counts));
+        uint32_t need = 0;
+        for (uint32_t i = 0; i < n; i++) need = std::max(need, std::max(cand[i], kpc[i]));
+        if (need <= ctx->cap) break;
+        int rc = grow_capacity(ctx, need);
+        if (rc) return rc;
+        for (auto& t : ctx->slot) {   // every group in flight lost its candidate arrays: detect again
+            if (!t.busy) continue;
+            rc = enqueue_detect(ctx, t, t.n_imgs, t.limit);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(t.h_counts, t.d_counts, (4 * (size_t)B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, t.stream));
+            CU(cudaEventRecord(t.ev_counts, t.stream));
+        }
     }
+    s.busy = false;
     const uint64_t total = outoff[n];
     int rc = ensure_result_capacity(ctx, ctx->res_n + total, s.first_img + n);
     if (rc) return rc;
@@ -1300,7 +1343,7 @@ int sb200_extract_precomputed(sb200_ctx* ctx, int64_t features_limit, sb200_resu
     CU(cudaMemcpyAsync(s.h_counts, s.d_counts, (4 * (size_t)ctx->max_batch + 1) * sizeof(uint32_t),
                        cudaMemcpyDeviceToHost, s.stream));
     CU(cudaEventRecord(s.ev_counts, s.stream));
-    s.n_imgs = 1; s.first_img = 0; s.busy = true;
+    s.n_imgs = 1; s.first_img = 0; s.limit = features_limit; s.busy = true;
     rc = collect_group(ctx, s);
     if (rc) return rc;
     rc = finish_all(ctx);

@@ -115,6 +115,25 @@ def test_alternative_paths(sf, oracle, monkeypatch, env):
     _check_image(sf, oracle, noise_image(520, 390, 77))
 
 
+@pytest.mark.parametrize("kind", ["ramp", "checker", "stripes", "impulses"])
+def test_structured_images(sf, oracle, kind):
+    """Synthetic structure that white noise and photographs never show: exact ramps (DoG = rounding noise, masses of
+    ties), a checkerboard and 1-pixel stripes (periodic ties, saturated steps), isolated impulses on black."""
+    h, w = 192, 256
+    yy, xx = np.mgrid[0:h, 0:w]
+    if kind == "ramp":
+        g = ((xx + yy) // 2 % 256).astype(np.uint8)
+    elif kind == "checker":
+        g = (((xx // 8) + (yy // 8)) % 2 * 255).astype(np.uint8)
+    elif kind == "stripes":
+        g = ((xx % 2) * 200 + 20).astype(np.uint8)
+    else:
+        g = np.zeros((h, w), np.uint8)
+        g[16::32, 16::32] = 255
+        g[40, 70] = 90
+    _check_image(sf, oracle, g)
+
+
 def test_flat_regions(sf, oracle):
     """Saturated / constant blocks: every pixel of such a block passes the reference's extremum test with
     ties (src/lib.rs:437-506) and dies in interpolate_extremum; the candidate list must still be the reference's."""
@@ -231,10 +250,26 @@ def test_errors(sf):
         with pytest.raises(sf.SiftError) as e:
             ex.sift_with_precomputed()                      # no pyramid resident
         assert e.value.status == _ffi.E_STATE
+
+
+def test_capacity_grows(sf, oracle):
+    """More candidates / keypoints than the context was sized for is not an error (the reference never fails): the
+    library re-allocates its per-candidate arrays and runs the detection stages again on the resident pyramids --
+    for a single image, and in the middle of a pipelined batch."""
+    img = noise_image(160, 120, 3)
+    with sf.Extractor(160, 120, 1) as ex:
+        ref = ex.sift(img)
+    assert len(ref) > 64
     with sf.Extractor(160, 120, 1, max_keypoints_per_image=16) as ex:
-        with pytest.raises(sf.SiftError) as e:
-            ex.sift(noise_image(160, 120, 3))               # more keypoints than the context was sized for
-        assert e.value.status == _ffi.E_CAPACITY
+        assert ex.sift(img) == ref
+        assert ex.sift(img) == ref                          # and stays usable
+    imgs = np.stack([noise_image(160, 120, 3 + (i % 3)) for i in range(9)])
+    with sf.Extractor(160, 120, 2, max_keypoints_per_image=16) as ex:
+        offs, kp, de = ex.sift_batch(imgs)
+    with sf.Extractor(160, 120, 2) as ex:
+        offs2, kp2, de2 = ex.sift_batch(imgs)
+    assert np.array_equal(offs, offs2) and np.array_equal(kp, kp2) and np.array_equal(de, de2)
+    assert np.array_equal(kp[offs[0]:offs[1]], ref.keypoint_array)
 
 
 def test_opencv_cross_match(sf):
