@@ -98,6 +98,12 @@ def test_1080p_noise_full_size(sf, oracle):
     assert 6000 < len(res) < 12000
 
 
+def test_maximum_size(sf, oracle):
+    """SB200_MAX_DIM: 4096 x 4096 (8192-pixel seed image, 12 octaves, 13-bit candidate coordinates at their limit)."""
+    res = _check_image(sf, oracle, noise_image(4096, 4096, 1234), pyramid=False)
+    assert len(res) > 50000
+
+
 @pytest.mark.parametrize("seg_rows", [512, 96])
 def test_blur_segment_heights(sf, oracle, monkeypatch, seg_rows):
     """The marching blur cuts an octave into vertical segments whose height depends on the batch; a large batch
