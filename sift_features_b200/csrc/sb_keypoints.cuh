@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
                     // f32 atan2 decides unless the scaled angle is close to a rounding
                     // boundary; then the f64 evaluation the reference uses decides.
                     float raw = bin_angle_step * fast_atan2_rad(dy, dx);   // |error| < 4e-7 rad => < 3e-6 bins
-                    if (fabsf(fabsf(raw - truncf(raw)) - 0.5f) < 1e-3f)
+                    if (fabsf(fabsf(raw - truncf(raw)) - 0.5f) < 1e-4f)   // > 25x the approximation error
                         raw = bin_angle_step * (float)atan2((double)dy, (double)dx);
                     bin = (int)roundf(raw);
                     if (bin >= ORI_BINS) bin -= ORI_BINS;

@@ -533,8 +533,9 @@ int march_seg_rows(const sb200_ctx* ctx, int w, int h, uint32_t n, int tile_w, i
     const long long slots = (long long)ctas_per_sm * ctx->sm_count;
     const long long S = strips * n;
     // plenty of strips (large batches): the other slot's kernels fill any tail, only the per-CTA overhead counts --
-    // tall segments (measured: flat from ~540 rows up; ~3 % better than 256-row segments at 32 images of 1080p)
-    const long long segs_tall = (h + 767) / 768;
+    // tall segments (measured at 32 images of 1080p: throughput flat from ~540 rows up, ~3 % above 256-row
+    // segments, while the launch on its own -- no other slot filling its tail -- is best around 400-550 rows)
+    const long long segs_tall = (h + 575) / 576;
     if (S * segs_tall >= 2 * slots) return (int)(((h + segs_tall - 1) / segs_tall + 31) / 32 * 32);
     // few strips (single images): the launch is alone on the machine, wave quantisation decides
     int best_rows = 64;
