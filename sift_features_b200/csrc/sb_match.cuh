@@ -36,7 +36,8 @@ struct MatchParams {
     const uint32_t* norm_a;        // [n_a] |a|^2
     const uint32_t* nbp;           // [ceil(n_b / MT_N) * MT_N]  (|b|^2 << 8) | (j & 255), zero beyond n_b
     uint32_t n_a, n_b;
-    unsigned long long* best;      // [n_a]  (distance^2 << 32) | argmin j
+    uint32_t tiles_per_cta;        // train tiles per CTA: blockIdx.y selects the range (the ranges are merged by atomicMin)
+    unsigned long long* best;      // [n_a]  (distance^2 << 32) | argmin j; all-ones before the launch
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -81,7 +82,11 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_nn(const __grid_constan
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * MT_M;
-    const int n_tiles = (int)((p.n_b + MT_N - 1) / MT_N);
+    // this CTA's train tiles: [t_first, t_first + n_tiles)
+    const int all_tiles = (int)((p.n_b + MT_N - 1) / MT_N);
+    const int t_first = (int)(blockIdx.y * p.tiles_per_cta);
+    const int n_tiles = min((int)p.tiles_per_cta, all_tiles - t_first);
+    if (n_tiles <= 0) return;   // block-uniform, before any barrier / TMEM use
     if (tid == 0) {
         mbar_init(&full_a, 1);
         for (int s = 0; s < MT_STAGES; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_nn(const __grid_constan
                 const int s = t % MT_STAGES;
                 if (t >= MT_STAGES) mbar_wait(&empty_b[s], (uint32_t)((t / MT_STAGES) - 1) & 1u);
                 mbar_expect_tx(&full_b[s], MT_B_BYTES);
-                tma_load_2d(sB + (size_t)s * MT_B_BYTES, &tm_b, 0, t * MT_N, &full_b[s]);
+                tma_load_2d(sB + (size_t)s * MT_B_BYTES, &tm_b, 0, (t_first + t) * MT_N, &full_b[s]);
             }
         }
     } else if (warp == 1) {
@@ -148,9 +153,10 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_nn(const __grid_constan
             mbar_wait(&tmem_full[acc], (uint32_t)(t >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * MT_N;
-            const uint32_t* nbp = p.nbp + (size_t)t * MT_N;
-            const int valid = min(MT_N, (int)p.n_b - t * MT_N);
-            uint32_t tile_min = 0xffffffffu;   // (distance^2 << 8) | column
+            const int tg = t_first + t;   // global tile index
+            const uint32_t* nbp = p.nbp + (size_t)tg * MT_N;
+            const int valid = min(MT_N, (int)p.n_b - tg * MT_N);
+            uint32_t tmin[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // (distance^2 << 8) | column, four chains
 #pragma unroll 1
             for (int c0 = 0; c0 < MT_N; c0 += 32) {
                 uint32_t v[32];
@@ -166,20 +172,22 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_nn(const __grid_constan
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (c0 + 32 <= valid) {
 #pragma unroll
-                    for (int k = 0; k < 32; k++) tile_min = min(tile_min, __ldg(nbp + c0 + k) + na256 - 512u * v[k]);
+                    for (int k = 0; k < 32; k++) tmin[k & 3] = min(tmin[k & 3], __ldg(nbp + c0 + k) + na256 - 512u * v[k]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 32; k++)
-                        if (c0 + k < valid) tile_min = min(tile_min, __ldg(nbp + c0 + k) + na256 - 512u * v[k]);
+                        if (c0 + k < valid) tmin[k & 3] = min(tmin[k & 3], __ldg(nbp + c0 + k) + na256 - 512u * v[k]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            const uint32_t tile_min = min(min(tmin[0], tmin[1]), min(tmin[2], tmin[3]));
             const uint32_t d2 = tile_min >> 8;
-            if (tile_min != 0xffffffffu && d2 < best_d2) { best_d2 = d2; best_j = (uint32_t)(t * MT_N) + (tile_min & 255u); }
+            if (tile_min != 0xffffffffu && d2 < best_d2) { best_d2 = d2; best_j = (uint32_t)(tg * MT_N) + (tile_min & 255u); }
         }
-        if (row < (int)p.n_a) p.best[row] = ((unsigned long long)best_d2 << 32) | best_j;
+        // merge with the other tile ranges of this row: smaller distance first, then smaller index
+        if (row < (int)p.n_a && best_d2 != 0xffffffffu) atomicMin(p.best + row, ((unsigned long long)best_d2 << 32) | best_j);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -1632,7 +1632,14 @@ int sb200_match_descriptors_device(sb200_ctx* ctx, const uint8_t* d_query, uint6
         mp.norm_a = ctx->d_mnorm[a]; mp.nbp = ctx->d_mnbp[b];
         mp.n_a = (uint32_t)n[a]; mp.n_b = (uint32_t)n[b];
         mp.best = ctx->d_mbest[a];
-        k_match_nn<<<(unsigned)((n[a] + MT_M - 1) / MT_M), MT_THREADS, MT_SMEM, st>>>(tm_a, tm_b, mp);
+        // one CTA per 128 query rows and per range of train tiles: enough CTAs for two per SM-slot (one CTA holds
+        // all of an SM's tensor memory), ranges of at least four tiles
+        const uint32_t row_ctas = (uint32_t)((n[a] + MT_M - 1) / MT_M), tiles = (uint32_t)((n[b] + MT_N - 1) / MT_N);
+        uint32_t splits = std::max<uint32_t>(1, std::min<uint32_t>((2u * ctx->sm_count + row_ctas - 1) / row_ctas, (tiles + 3) / 4));
+        mp.tiles_per_cta = (tiles + splits - 1) / splits;
+        splits = (tiles + mp.tiles_per_cta - 1) / mp.tiles_per_cta;
+        CU(cudaMemsetAsync(ctx->d_mbest[a], 0xff, n[a] * sizeof(unsigned long long), st));
+        k_match_nn<<<dim3(row_ctas, splits), MT_THREADS, MT_SMEM, st>>>(tm_a, tm_b, mp);
         ctx->launches++;
     }
     k_match_cross<<<1, 1024, 0, st>>>(ctx->d_mbest[0], ctx->d_mbest[1], (uint32_t)n_query, (uint32_t)n_train, ctx->d_mout,
