@@ -517,6 +517,12 @@ __global__ void __launch_bounds__(256, TmaCfg<L>::CTAS_PER_SM) k_blur_tma(const 
 __host__ __device__ constexpr int march_tile_w(int l) { return SB_MARCH_TW(l); }
 // consecutive outputs per row-pass task: 16 (eight independent FMA chains per lane, one task per warp and band)
 // measured 4-7 % faster than 8 on every tap set
+#ifndef SB_MARCH_PY
+#define SB_MARCH_PY(l) 8
+#endif
+#ifndef SB_MARCH_CTAS
+#define SB_MARCH_CTAS(l) 0   // resident CTAs per SM the kernel is compiled for; 0: 512 threads' worth
+#endif
 #ifndef SB_MARCH_SEG
 #define SB_MARCH_SEG(l) 16
 #endif
@@ -535,9 +541,9 @@ struct MarchCfg {
     static constexpr int BW4 = (BW_MIN + 3) / 4;
     static constexpr int BW = 4 * ((BW4 % 2) ? BW4 : BW4 + 1);   // BW/4 odd: conflict-free LDS.128 with lanes <-> rows
     static constexpr int IPITCH = TW + 4;        // == 4 (mod 32)
-    static constexpr int PY = 8;                 // output rows per column-pass thread (which owns two adjacent columns)
+    static constexpr int PY = SB_MARCH_PY(L);    // output rows per column-pass thread (which owns two adjacent columns)
     static constexpr int THREADS = (TW / 2) * (BH / PY);   // one column-pass task per thread
-    static constexpr int CTAS_PER_SM = 512 / THREADS;
+    static constexpr int CTAS_PER_SM = SB_MARCH_CTAS(L) ? SB_MARCH_CTAS(L) : 512 / THREADS;
     // stage buffers (bands in flight + the one being filtered): the narrow tap sets are memory-bound and need two
     // bands in flight per CTA to hide the TMA latency behind their short steps; the wide ones have no room for a
     // third buffer next to two resident CTAs and do not need it
