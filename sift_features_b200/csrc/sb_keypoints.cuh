@@ -580,8 +580,9 @@ __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const uin
     DescPix q{0.f, 0.f, 0.f, 0.f};
     if (active) {
         const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
-        const float* c = G.img + ((G.y + yw) * G.pitch + (G.x + xw));   // a layer holds < 2^31 floats: 32-bit offsets
-        q.xp = __ldg(c + 1); q.xm = __ldg(c - 1); q.ym = __ldg(c - G.pitch); q.yp = __ldg(c + G.pitch);
+        const int i = (G.y + yw) * G.pitch + (G.x + xw);   // a layer holds < 2^31 floats: 32-bit offsets
+        q.xp = __ldg(G.img + (i + 1)); q.xm = __ldg(G.img + (i - 1));
+        q.ym = __ldg(G.img + (i - G.pitch)); q.yp = __ldg(G.img + (i + G.pitch));
     }
     return q;
 }
