@@ -517,6 +517,9 @@ __global__ void __launch_bounds__(256, TmaCfg<L>::CTAS_PER_SM) k_blur_tma(const 
 __host__ __device__ constexpr int march_tile_w(int l) { return SB_MARCH_TW(l); }
 // consecutive outputs per row-pass task: 16 (eight independent FMA chains per lane, one task per warp and band)
 // measured 4-7 % faster than 8 on every tap set
+#ifndef SB_MARCH_BH
+#define SB_MARCH_BH(l) 32
+#endif
 #ifndef SB_MARCH_PY
 #define SB_MARCH_PY(l) 8
 #endif
@@ -532,7 +535,7 @@ struct MarchCfg {
     static constexpr int R = blur_radius(L);
     static constexpr int RA = (R + 3) / 4 * 4;   // left halo of the box: a TMA box starts on a 16-byte boundary
     static constexpr int XO = RA - R;            // box column of the first element the filter needs
-    static constexpr int TW = march_tile_w(L), BH = 32;
+    static constexpr int TW = march_tile_w(L), BH = SB_MARCH_BH(L);   // strip width, rows per band
     static constexpr int SW = TW + 2 * R;
     static constexpr int SEG = SB_MARCH_SEG(L);  // consecutive outputs of one row-pass task (one lane): SEG / 2 FMA chains
     static constexpr int WIN = XO + SEG + 2 * R; // box floats read for them (aligned start)
@@ -547,7 +550,7 @@ struct MarchCfg {
     // stage buffers (bands in flight + the one being filtered): the narrow tap sets are memory-bound and need two
     // bands in flight per CTA to hide the TMA latency behind their short steps; the wide ones have no room for a
     // third buffer next to two resident CTAs and do not need it
-    static constexpr int NSTG = (L <= 2) ? 3 : 2;
+    static constexpr int NSTG = (L <= 2 && BH == 32) ? 3 : 2;
     static constexpr int RING_ROWS = 3 * BH + 2 * R;   // three band slots + a mirror of the first 2R rows of slot 0
     static constexpr uint32_t BAND_BYTES = (uint32_t)BH * BW * sizeof(float);
 #ifndef SB_MARCH_PAD
@@ -556,7 +559,7 @@ struct MarchCfg {
     static constexpr size_t SMEM = (size_t)NSTG * BAND_BYTES + (size_t)RING_ROWS * IPITCH * sizeof(float) + SB_MARCH_PAD;
     static_assert(BW >= XO + SW && (BW / 4) % 2 == 1 && TW - SEG + 4 * NV4 <= BW && BW <= 256, "box width");
     static_assert(BAND_BYTES % 128 == 0, "128-byte aligned stage buffers");
-    static_assert(2 * R + 1 <= BH && PY + 2 * R <= 2 * BH, "window spans at most two bands");
+    static_assert(2 * R + 1 <= BH && PY + 2 * R <= 2 * BH && BH % 32 == 0, "window spans at most two bands");
     static_assert((TW / 2) * (BH / PY) == THREADS, "one column-pass task per thread");
 };
 
@@ -629,19 +632,21 @@ __global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM
         float* const ib = inter + slot * SLOT_FLOATS;
         const bool vedge = band_y0 < 0 || band_y0 + C::BH > h;                      // block-uniform
         const int rows_needed = yb + R - band_y0;   // >= BH except in the last band
-        const int row = lane;
-        if (row >= rows_needed) return;
-        int srow = row;         // stage row this lane filters
-        bool copy_prev = false; // the mirrored row belongs to the previous band: copy its row-pass result from the ring
-        if (vedge) {
-            const int yy = reflect101(band_y0 + row, h);
-            srow = yy - band_y0;
-            copy_prev = srow < 0;
-        }
-        const float* const srcrow = st + srow * C::BW;
-        float* const dstrow = ib + row * C::IPITCH;
+        constexpr int NSEG = C::TW / C::SEG;
 #pragma unroll 1
-        for (int seg = warp; seg < C::TW / C::SEG; seg += C::THREADS / 32) {
+        for (int task = warp; task < NSEG * (C::BH / 32); task += C::THREADS / 32) {   // task = 32 rows x one segment
+            const int seg = task % NSEG;
+            const int row = (task / NSEG) * 32 + lane;
+            if (row >= rows_needed) continue;
+            int srow = row;         // stage row this lane filters
+            bool copy_prev = false; // the mirrored row belongs to the previous band: copy its row-pass result from the ring
+            if (vedge) {
+                const int yy = reflect101(band_y0 + row, h);
+                srow = yy - band_y0;
+                copy_prev = srow < 0;
+            }
+            const float* const srcrow = st + srow * C::BW;
+            float* const dstrow = ib + row * C::IPITCH;
             float4 o[C::SEG / 4];
             if (copy_prev) {
                 const int pslot = slot == 0 ? 2 : slot - 1;
