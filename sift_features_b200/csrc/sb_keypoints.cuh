@@ -663,8 +663,7 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
 __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /* smem [DESC_SMEM_WORDS] */, int lane,
                                                 uint8_t* out /* 128 B */) {
     float* hist = wsm;
-    uint16_t* row_cnt = reinterpret_cast<uint16_t*>(wsm + DESC_HIST_WORDS);              // [DESC_MAXROWS] running sample count
-    uint8_t* row_x0 = reinterpret_cast<uint8_t*>(wsm + DESC_HIST_WORDS + DESC_MAXROWS / 2);  // [DESC_MAXROWS] xlo + radius
+    uint16_t* row_tab = reinterpret_cast<uint16_t*>(wsm + DESC_HIST_WORDS);   // [DESC_MAXROWS] (span length << 8) | (xlo + radius)
     {
         float4* h4 = reinterpret_cast<float4*>(hist);
         for (int k = lane; k < DESC_HIST_WORDS / 4; k += 32) h4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -688,9 +687,8 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     const int xw_min = max(-G.radius, 1 - G.x), xw_max = min(G.radius, G.w - 2 - G.x);
     const uint32_t lt = (1u << lane) - 1u;
     // ---- row table: lanes take window rows in parallel.  Entry k describes the k-th non-empty row (the
-    //      non-empty rows are consecutive: convex square, convex image): running sample count (inclusive)
-    //      and first column.  At most a couple of samples per row fail the exact test, which the sample
-    //      step repeats. ----
+    //      non-empty rows are consecutive: convex square, convex image): span length and first column.  At
+    //      most a couple of samples per row fail the exact test, which the sample step repeats. ----
     uint32_t n_rows = 0, total = 0, yq_first = 0;  // warp-uniform
     const int nwin = 2 * G.radius + 1;
     for (int rb = 0; rb < nwin; rb += 32) {
@@ -722,29 +720,25 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
         }
         if (len > 0) {
             const uint32_t k = n_rows + __popc(ne & lt);
-            row_cnt[k] = (uint16_t)(total + incl);
-            row_x0[k] = (uint8_t)(xlo + G.radius);
+            row_tab[k] = (uint16_t)((len << 8) | (xlo + G.radius));
         }
         if (n_rows == 0 && ne) yq_first = rb + __ffs(ne) - 1;
         n_rows += __popc(ne);
         total += __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
-    // ---- samples, 32 at a time: sample i lives in the table row whose running count first exceeds i ----
-    uint32_t r_cur = 0;  // first table row with samples at or after the current batch (warp-uniform)
-    auto lookup = [&](const uint32_t base, uint32_t& packed) -> bool {
-        const uint32_t cj = (r_cur + lane < n_rows) ? row_cnt[r_cur + lane] : 0xffffu;
-        const uint32_t last = cj - base - 1u;           // batch position of the row's last sample
-        const uint32_t ends = __reduce_or_sync(0xffffffffu, last < 32u ? 1u << last : 0u);
-        const uint32_t k = r_cur + __popc(ends & lt);    // rows that end before this lane's sample
-        const uint32_t i = base + lane;
-        const bool active = i < total;
-        packed = 0;
-        if (active) {
-            const uint32_t before = k ? row_cnt[k - 1] : 0u;
-            packed = ((yq_first + k) << 8) | ((uint32_t)row_x0[k] + (i - before));
+    // ---- samples, 32 at a time: every lane walks the table with its own cursor (row k, offset xo in the row),
+    //      32 samples forward per batch -- one or two short rows at most, no search ----
+    uint32_t cur_k = 0, cur_xo = lane, cur_w = n_rows ? row_tab[0] : 0u;
+    auto lookup = [&](const uint32_t advance, uint32_t& packed) -> bool {
+        cur_xo += advance;
+        while (cur_k < n_rows && cur_xo >= (cur_w >> 8)) {
+            cur_xo -= cur_w >> 8;
+            cur_k++;
+            cur_w = cur_k < n_rows ? row_tab[cur_k] : 0u;
         }
-        r_cur += __popc(ends);
+        const bool active = cur_k < n_rows;
+        packed = active ? (((yq_first + cur_k) << 8) | ((cur_w & 255u) + cur_xo)) : 0u;
         return active;
     };
     if (total) {
@@ -756,7 +750,7 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
             const bool a = a_next;
             const DescPix px = p_next;
             if (base + 32 < total) {
-                a_next = lookup(base + 32, e_next);
+                a_next = lookup(32, e_next);
                 p_next = descriptor_fetch(G, e_next, a_next);
             }
             descriptor_sample(G, e, a, px, hist, lane);
