@@ -2,7 +2,7 @@
 """bench.py -- throughput of the SIFT extraction hot path on B200 (BASELINE.json metric:
 "1080p images/sec at 1/2/4/8 B200; descriptors/sec; % of HBM roofline").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k|vga|desc] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k|vga|desc|match|jpeg] [--impl b200|reference]
 
 One "step" = one pass of the whole hot path (seed, pyramid, DoG/extrema, refinement, orientation,
 descriptors) over one batch of synthetic gray images per GPU.  Prints ONE JSON line on rank 0.
@@ -538,29 +538,84 @@ def run_match(args, rank, local_rank, world):
     dist.close()
 
 
+def run_jpeg(args, rank, local_rank, world):
+    """JPEG input: 1080p bitstreams in host memory -> nvJPEG decode + luma on the device ->
+    the extraction path -> keypoints and descriptors in host memory.  The CPU leg beside it is what the reference's
+    callers do first: a libjpeg-turbo decode (cv2.imdecode) on one core."""
+    import cv2
+    import sift_features_b200 as sf
+    dist = Dist(rank, local_rank, world)
+    w, h, B, G = WORKLOADS["1080p"]
+    B = args.batch or B
+    G = args.groups or G
+    bird = np.load(os.path.join(ROOT, "tests", "golden", "bird_gray.npy"))
+    tile = np.tile(bird, (h // bird.shape[0] + 1, w // bird.shape[1] + 1))[:h, :w]
+    jpegs = []
+    for i in range(B * G):
+        img = np.roll(tile, (37 * (i + 1 + rank * 1000)) % w, 1)
+        if args.jpeg_colour:
+            img = np.stack([img, np.roll(img, 5, 0), np.roll(img, 9, 1)], -1)
+        jpegs.append(cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes())
+    ex = sf.Extractor(w, h, B, device=local_rank)
+    for _ in range(args.warmup):
+        offs, kp, _d = ex.sift_jpeg(jpegs)
+    dist.barrier()
+    l0 = ex.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        offs, kp, _d = ex.sift_jpeg(jpegs)
+    t = dist.reduce(time.perf_counter() - t0, "max")
+    launches = ex.launch_count - l0
+    if rank == 0:
+        n = len(jpegs)
+        line = {"metric": "1080p JPEG images/sec (decode + luma + extraction, host bitstreams -> host results)",
+                "value": args.steps * n * world / t, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8 -> f32", "data": "synthetic",
+                "config": {"workload": f"jpeg: {n} x 1920x1080 {'colour 4:2:0' if args.jpeg_colour else 'gray'} JPEGs "
+                                       f"(quality 90, tiled bird fixture), groups of {B}",
+                           "jpeg_backend": ex.jpeg_backend, "keypoints_per_image": float(len(kp)) / n},
+                "e2e": {"value": args.steps * n * world / t, "unit": "images/s",
+                        "h2d_bytes_per_step": int(sum(len(j) for j in jpegs)),
+                        "d2h_bytes_per_step": int(len(kp)) * (20 + 128)},
+                "gpu_launches": int(launches)}
+        if world == 1 and not args.no_cpu:
+            t0 = time.perf_counter()
+            for j in jpegs[:16]:
+                cv2.imdecode(np.frombuffer(j, np.uint8), cv2.IMREAD_GRAYSCALE)
+            line["cpu_baseline"] = {"value": 16 / (time.perf_counter() - t0), "unit": "images/s", "cores": 1, "kind": "port",
+                                    "sample": "decode only (cv2.imdecode, libjpeg-turbo) of 16 of the bitstreams"}
+        print(json.dumps(line), flush=True)
+    ex.close()
+    dist.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS) + ["desc", "match"])
+    ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS) + ["desc", "match", "jpeg"])
     ap.add_argument("--batch", type=int, default=0, help="images per group (context max_batch)")
     ap.add_argument("--groups", type=int, default=0, help="groups per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--jpeg-colour", action="store_true", help="jpeg workload: three-component 4:2:0 streams")
     ap.add_argument("--no-profile-stages", dest="profile_stages", action="store_false",
                     help="do not bracket stages with CUDA events during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
-        if args.workload in ("desc", "match"):
+        if args.workload in ("desc", "match", "jpeg"):
             args.workload = "1080p"
         return run_reference(args, rank, world)
     if args.workload == "desc":
         return run_desc(args, rank, local_rank, world)
     if args.workload == "match":
         return run_match(args, rank, local_rank, world)
+    if args.workload == "jpeg":
+        return run_jpeg(args, rank, local_rank, world)
     return run_b200(args, rank, local_rank, world)
 
 

@@ -48,6 +48,7 @@ extern "C" {
 #define SB200_E_CAPACITY 3  /* an output buffer / the device-resident result is too small (the host entry points grow
                                the context's own per-candidate arrays transparently and never return this) */
 #define SB200_E_STATE 4     /* call needs a prior sb200_precompute / extract on this context */
+#define SB200_E_UNSUPPORTED 5 /* an optional component is missing on this machine (nvJPEG for the JPEG entry points) */
 
 typedef struct sb200_ctx sb200_ctx;
 
@@ -167,6 +168,23 @@ int sb200_extract_batch_rgb(sb200_ctx* ctx, const uint8_t* rgb, uint32_t n, uint
 /* the conversion alone (parity view): gray receives w x h bytes */
 int sb200_rgb_to_luma(sb200_ctx* ctx, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t stride, uint32_t channels,
                       uint8_t* gray);
+
+/* JPEG input: what `image::open(path)?.grayscale()` + sift() do in examples/run-sift.rs:8-19 and
+ * `image::load_from_memory(..).grayscale()` in src/lib.rs:1012, with the decode on the device (nvJPEG batched decode;
+ * hardware engines, then GPU Huffman, then nvJPEG's default backend) followed by the same integer luma; a one-component
+ * JPEG is its Y plane, as the `image` crate returns it.  Only the compressed bytes cross the host/device boundary.
+ * All n streams of one call must have the same frame size (like sb200_extract_batch); lengths in bytes.
+ * Decoded pixels are the decoder's: nvJPEG, libjpeg-turbo and the crate's zune-jpeg differ by a grey level or two on
+ * the same stream (IDCT rounding, chroma upsampling), so parity through this entry point is a tolerance, and exact only
+ * against sb200_decode_jpeg_luma's own pixels.  SB200_E_UNSUPPORTED when libnvjpeg cannot be loaded. */
+int sb200_extract_batch_jpeg(sb200_ctx* ctx, const uint8_t* const* jpegs, const uint64_t* lengths, uint32_t n,
+                             int64_t features_limit, sb200_result* out);
+/* frame size and component count from the header */
+int sb200_jpeg_info(sb200_ctx* ctx, const uint8_t* jpeg, uint64_t length, uint32_t* w, uint32_t* h, uint32_t* components);
+/* the decode + luma step alone (parity view): gray receives w x h bytes, capacity = size of the buffer */
+int sb200_decode_jpeg_luma(sb200_ctx* ctx, const uint8_t* jpeg, uint64_t length, uint8_t* gray, uint64_t capacity);
+/* nvJPEG backend that decoded the last group: "hardware", "gpu", "default", or "none" */
+const char* sb200_jpeg_backend(const sb200_ctx* ctx);
 
 /* ---- descriptor matching: the step after the path in the reference's examples ----
  * examples/sift-match.rs:30-35 and examples/opencv-cross-match.rs:34-43 hand the (N,128) u8 descriptor

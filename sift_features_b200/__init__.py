@@ -232,6 +232,39 @@ class Extractor:
                                                 out.ctypes.data))
         return out
 
+    def sift_jpeg(self, jpegs, features_limit: Optional[int] = None):
+        """JPEG bitstreams (bytes-like objects, one frame size) -> (offsets[n+1], keypoints, descriptors): nvJPEG decode
+        and the integer luma on the device, then sift() -- `image::open(..).grayscale()` + sift of examples/run-sift.rs:8-19
+        without host pixels."""
+        bufs = [np.frombuffer(j, np.uint8) for j in jpegs]
+        if not bufs:
+            raise ValueError("no images")
+        ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+        lens = (C.c_uint64 * len(bufs))(*[b.size for b in bufs])
+        res = _ffi.Result()
+        self._retry_capacity(lambda: self._lib.sb200_extract_batch_jpeg(
+            self._h, ptrs, lens, len(bufs), -1 if features_limit is None else int(features_limit), C.byref(res)))
+        return self._take(res)
+
+    def jpeg_info(self, jpeg):
+        """(width, height, components) from the JPEG header."""
+        b = np.frombuffer(jpeg, np.uint8)
+        w, h, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.sb200_jpeg_info(self._h, b.ctypes.data, b.size, C.byref(w), C.byref(h), C.byref(c)))
+        return w.value, h.value, c.value
+
+    def decode_jpeg_luma(self, jpeg) -> np.ndarray:
+        """The device-side decode + luma step alone: the GrayImage sift_jpeg() runs on."""
+        b = np.frombuffer(jpeg, np.uint8)
+        w, h, _ = self.jpeg_info(jpeg)
+        out = np.zeros((h, w), np.uint8)
+        self._check(self._lib.sb200_decode_jpeg_luma(self._h, b.ctypes.data, b.size, out.ctypes.data, out.size))
+        return out
+
+    @property
+    def jpeg_backend(self) -> str:
+        return self._lib.sb200_jpeg_backend(self._h).decode()
+
     def precompute_images(self, img) -> "PrecomputedImages":
         """precompute_images::<OpenCVProcessing> (src/lib.rs:131-143); the pyramid stays on the device."""
         a = _as_gray(img)

@@ -28,7 +28,8 @@ SYMBOLS = [
     "sb200_reset_stats", "sb200_launch_count", "sb200_stage_name", "sb200_algorithmic_bytes", "sb200_timer_start",
     "sb200_timer_stop", "sb200_timer_elapsed_ms", "sb200_host_alloc", "sb200_host_free", "sb200_device_alloc",
     "sb200_device_free", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_flush_l2", "sb200_match_descriptors", "sb200_match_descriptors_device",
-    "sb200_extract_batch_rgb", "sb200_rgb_to_luma",
+    "sb200_extract_batch_rgb", "sb200_rgb_to_luma", "sb200_extract_batch_jpeg", "sb200_jpeg_info", "sb200_decode_jpeg_luma",
+    "sb200_jpeg_backend",
 ]
 
 
@@ -72,6 +73,10 @@ def load() -> C.CDLL:
         "sb200_compute_descriptors_device": (C.c_int, [vp, vp, u32, u32, u32, vp, u64, vp]),
         "sb200_extract_batch_rgb": (C.c_int, [vp, u8p, u32, u32, u32, u32, u64, u32, i64, C.POINTER(Result)]),
         "sb200_rgb_to_luma": (C.c_int, [vp, u8p, u32, u32, u32, u32, vp]),
+        "sb200_extract_batch_jpeg": (C.c_int, [vp, C.POINTER(vp), C.POINTER(u64), u32, i64, C.POINTER(Result)]),
+        "sb200_jpeg_info": (C.c_int, [vp, vp, u64, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+        "sb200_decode_jpeg_luma": (C.c_int, [vp, vp, u64, vp, u64]),
+        "sb200_jpeg_backend": (C.c_char_p, [vp]),
         "sb200_match_descriptors": (C.c_int, [vp, vp, u64, vp, u64, vp, u64, C.POINTER(u64)]),
         "sb200_match_descriptors_device": (C.c_int, [vp, vp, u64, vp, u64, vp, u64, C.POINTER(u64)]),
         "sb200_extract_batch_multi": (C.c_int, [C.POINTER(vp), u32, u8p, u32, u32, u32, u32, u64, i64,

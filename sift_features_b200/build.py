@@ -16,12 +16,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsift_b200.so")
 SOURCES = ["sift_b200.cu"]
-HEADERS = ["sb_common.cuh", "sb_math.cuh", "sb_pyramid.cuh", "sb_keypoints.cuh"]
+HEADERS = ["sb_common.cuh", "sb_math.cuh", "sb_pyramid.cuh", "sb_keypoints.cuh", "sb_match.cuh", "sb_jpeg.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",          # every FMA in the kernels is explicit (bit-exact arithmetic contract)
     "-Xcompiler", "-fPIC", "-shared",
+    "-ldl",                  # nvJPEG is opened with dlopen on first use of the JPEG entry points (sb_jpeg.h)
 ]
 
 

@@ -22,6 +22,7 @@
 
 #include "../../include/sift_b200.h"
 #include "sb_common.cuh"
+#include "sb_jpeg.h"
 #include "sb_keypoints.cuh"
 #include "sb_match.cuh"
 #include "sb_pyramid.cuh"
@@ -88,6 +89,15 @@ struct Slot {
     bool busy = false;
 };
 
+// stage buffer of the JPEG entry points: decoded pixels (Y or interleaved RGB) of one chunk of bitstreams
+struct JpegStage {
+    uint8_t* d = nullptr;
+    size_t cap = 0;
+    cudaEvent_t decoded = nullptr;          // recorded on the decode stream after the chunk
+    cudaEvent_t read[SB_SLOTS] = {nullptr};  // recorded on a slot's stream after it read its group out of the buffer
+    bool read_valid[SB_SLOTS] = {false};
+};
+
 struct StageEvents {
     cudaEvent_t a, b;
     int stage;
@@ -137,6 +147,12 @@ struct sb200_ctx {
     DescIn* d_dkps = nullptr;
     uint8_t* d_ddesc = nullptr;
     size_t dkps_cap = 0;
+    // JPEG input (nvJPEG, loaded on first use): bitstreams are decoded a chunk at a time on their own stream into one of
+    // two stage buffers, so that the decode of chunk c+1 overlaps the extraction of chunk c
+    JpegDecoder jpeg;
+    JpegStage jstage[2];
+    cudaStream_t jstream = nullptr;
+    uint32_t jpeg_chunk = 128;   // SB200_JPEG_CHUNK; nvJPEG decodes Huffman on the GPU for batches of >= 100 streams
     // matcher scratch (grow-only)
     uint8_t* d_mdesc[2] = {nullptr, nullptr};        // query / train descriptors
     uint32_t* d_mnorm[2] = {nullptr, nullptr};
@@ -870,47 +886,141 @@ __global__ void __launch_bounds__(256) k_luma(const uint8_t* __restrict__ rgb, u
     gray[i] = (uint8_t)((2126u * p[0] + 7152u * p[1] + 722u * p[2]) / 10000u);
 }
 
-// upload + full pipeline + async read-back of the counts for one group; channels = 1 (gray) or 3 / 4 (RGB / RGBA,
-// converted to luma on the device)
-int launch_group(sb200_ctx* ctx, Slot& s, const uint8_t* img, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
-                 uint64_t image_stride, int64_t limit, uint64_t first_img, uint32_t channels = 1) {
-    cudaStream_t st = s.stream;
-    const size_t rowb = (size_t)w * channels;   // bytes per packed row
-    if (channels > 1 && s.rgb_cap < rowb * h * ctx->max_batch) {
-        CU(cudaStreamSynchronize(st));
-        cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb);
-        s.d_rgb = nullptr; s.h_rgb = nullptr; s.rgb_cap = 0;
-        const size_t cap = (size_t)ctx->max_w * ctx->max_h * 4 * ctx->max_batch;
-        CU(dalloc(&s.d_rgb, cap));
-        CU(cudaHostAlloc((void**)&s.h_rgb, cap, cudaHostAllocDefault));
-        s.rgb_cap = cap;
-    }
-    uint8_t* const d_up = channels > 1 ? s.d_rgb : s.d_in;
-    uint8_t* const h_up = channels > 1 ? s.h_rgb : s.h_in;
-    const bool contiguous = (image_stride == (uint64_t)stride * h);
-    if (is_device_accessible_host(img)) {
-        if (contiguous) {
-            CU(cudaMemcpy2DAsync(d_up, rowb, img, stride, rowb, (size_t)h * n, cudaMemcpyHostToDevice, st));
-        } else {
-            for (uint32_t i = 0; i < n; i++)
-                CU(cudaMemcpy2DAsync(d_up + (size_t)i * rowb * h, rowb, img + i * image_stride, stride, rowb, h,
-                                     cudaMemcpyHostToDevice, st));
+// staging buffers of the colour entry points, allocated on first use
+int ensure_rgb(sb200_ctx* ctx, Slot& s, size_t bytes) {
+    if (s.rgb_cap >= bytes) return SB200_OK;
+    CU(cudaStreamSynchronize(s.stream));
+    cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb);
+    s.d_rgb = nullptr; s.h_rgb = nullptr; s.rgb_cap = 0;
+    const size_t cap = (size_t)ctx->max_w * ctx->max_h * 4 * ctx->max_batch;
+    CU(dalloc(&s.d_rgb, cap));
+    CU(cudaHostAlloc((void**)&s.h_rgb, cap, cudaHostAllocDefault));
+    s.rgb_cap = cap;
+    return SB200_OK;
+}
+
+// where the pixels of a call come from: packed host / pinned images (gray, RGB, RGBA) or JPEG bitstreams
+struct Source {
+    const uint8_t* img = nullptr;
+    uint32_t stride = 0;
+    uint64_t image_stride = 0;
+    uint32_t channels = 1;
+    const uint8_t* const* jpeg = nullptr;   // non-null: n bitstreams, all of the same frame size
+    const size_t* jpeg_len = nullptr;
+    bool jpeg_rgb = false;                  // some stream has three components: decode to RGB, then luma
+    uint32_t n = 0;                         // images of the call
+    uint32_t chunk = 0;                     // bitstreams per decode batch (groups never straddle chunks)
+};
+
+int jpeg_stage_ready(sb200_ctx* ctx, size_t bytes) {
+    if (!ctx->jstream) CU(cudaStreamCreateWithFlags(&ctx->jstream, cudaStreamNonBlocking));
+    for (auto& g : ctx->jstage) {
+        if (!g.decoded) {
+            CU(cudaEventCreateWithFlags(&g.decoded, cudaEventDisableTiming));
+            for (auto& e : g.read) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
-    } else {
-        // pageable memory: pack into the pinned staging buffer, then one async copy
-        CU(cudaStreamSynchronize(st));  // staging buffer may still feed the previous upload
-        for (uint32_t i = 0; i < n; i++) {
-            const uint8_t* src = img + i * image_stride;
-            uint8_t* dst = h_up + (size_t)i * rowb * h;
-            if (stride == rowb) memcpy(dst, src, rowb * h);
-            else for (uint32_t y = 0; y < h; y++) memcpy(dst + (size_t)y * rowb, src + (size_t)y * stride, rowb);
+        if (g.cap < bytes) {
+            CU(cudaStreamSynchronize(ctx->jstream));
+            for (auto& t : ctx->slot) CU(cudaStreamSynchronize(t.stream));
+            cudaFree(g.d); g.d = nullptr; g.cap = 0;
+            CU(dalloc(&g.d, bytes));
+            g.cap = bytes;
         }
-        CU(cudaMemcpyAsync(d_up, h_up, rowb * h * n, cudaMemcpyHostToDevice, st));
     }
-    if (channels > 1) {
-        const size_t n_px = (size_t)w * h * n;
-        k_luma<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(s.d_rgb, s.d_in, n_px, (int)channels);
+    return SB200_OK;
+}
+
+// decodes chunk c of the call's bitstreams into stage buffer c % 2 on the decode stream (device-side decode: only the
+// compressed bytes cross the host/device boundary)
+int decode_chunk(sb200_ctx* ctx, const Source& src, uint32_t c, uint32_t w, uint32_t h) {
+    JpegStage& g = ctx->jstage[c & 1];
+    const uint32_t first = c * src.chunk, n = std::min(src.chunk, src.n - first);
+    const size_t bpp = src.jpeg_rgb ? 3 : 1, img_bytes = (size_t)w * h * bpp;
+    for (int k = 0; k < N_SLOTS; k++)   // groups of the chunk that used this buffer before have to be done with it
+        if (g.read_valid[k]) { CU(cudaStreamWaitEvent(ctx->jstream, g.read[k], 0)); g.read_valid[k] = false; }
+    std::vector<uint8_t*> dst(n);
+    for (uint32_t i = 0; i < n; i++) dst[i] = g.d + i * img_bytes;
+    std::string err;
+    if (!ctx->jpeg.decode((int)(c & 1), src.jpeg + first, src.jpeg_len + first, n, src.jpeg_rgb, dst.data(), (size_t)w * bpp,
+                          ctx->jstream, err))
+        return fail(ctx, SB200_E_INVALID, "%s", err.c_str());
+    CU(cudaEventRecord(g.decoded, ctx->jstream));
+    return SB200_OK;
+}
+
+// a group's pixels out of the stage buffer into the slot's input buffer (luma on the way for colour streams)
+int fetch_decoded(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img, uint32_t n, uint32_t w, uint32_t h) {
+    const uint32_t c = (uint32_t)(first_img / src.chunk);
+    if (first_img % src.chunk == 0) {
+        // first group of a chunk: the chunk itself if nothing decoded it yet, and the next one so that it decodes
+        // while this chunk's groups run
+        int rc = c == 0 ? decode_chunk(ctx, src, 0, w, h) : SB200_OK;
+        if (rc) return rc;
+        if ((uint64_t)(c + 1) * src.chunk < src.n) {
+            rc = decode_chunk(ctx, src, c + 1, w, h);
+            if (rc) return rc;
+        }
+    }
+    JpegStage& g = ctx->jstage[c & 1];
+    const size_t px = (size_t)w * h, bpp = src.jpeg_rgb ? 3 : 1;
+    const uint8_t* from = g.d + (first_img - (uint64_t)c * src.chunk) * px * bpp;
+    CU(cudaStreamWaitEvent(s.stream, g.decoded, 0));
+    if (src.jpeg_rgb) {
+        k_luma<<<(unsigned)((px * n + 255) / 256), 256, 0, s.stream>>>(from, s.d_in, px * n, 3);
         ctx->launches++;
+    } else {
+        CU(cudaMemcpyAsync(s.d_in, from, px * n, cudaMemcpyDeviceToDevice, s.stream));
+    }
+    const int k = (int)(&s - ctx->slot);
+    CU(cudaEventRecord(g.read[k], s.stream));
+    g.read_valid[k] = true;
+    return SB200_OK;
+}
+
+// upload (or decode) + full pipeline + async read-back of the counts for one group; channels = 1 (gray) or 3 / 4
+// (RGB / RGBA, converted to luma on the device)
+int launch_group(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img, uint32_t n, uint32_t w, uint32_t h,
+                 int64_t limit) {
+    cudaStream_t st = s.stream;
+    if (src.jpeg) {
+        int rc = fetch_decoded(ctx, s, src, first_img, n, w, h);
+        if (rc) return rc;
+    } else {
+        const uint32_t channels = src.channels, stride = src.stride;
+        const uint64_t image_stride = src.image_stride;
+        const uint8_t* img = src.img + first_img * image_stride;
+        const size_t rowb = (size_t)w * channels;   // bytes per packed row
+        if (channels > 1) {
+            int rc = ensure_rgb(ctx, s, rowb * h * ctx->max_batch);
+            if (rc) return rc;
+        }
+        uint8_t* const d_up = channels > 1 ? s.d_rgb : s.d_in;
+        uint8_t* const h_up = channels > 1 ? s.h_rgb : s.h_in;
+        const bool contiguous = (image_stride == (uint64_t)stride * h);
+        if (is_device_accessible_host(img)) {
+            if (contiguous) {
+                CU(cudaMemcpy2DAsync(d_up, rowb, img, stride, rowb, (size_t)h * n, cudaMemcpyHostToDevice, st));
+            } else {
+                for (uint32_t i = 0; i < n; i++)
+                    CU(cudaMemcpy2DAsync(d_up + (size_t)i * rowb * h, rowb, img + i * image_stride, stride, rowb, h,
+                                         cudaMemcpyHostToDevice, st));
+            }
+        } else {
+            // pageable memory: pack into the pinned staging buffer, then one async copy
+            CU(cudaStreamSynchronize(st));  // staging buffer may still feed the previous upload
+            for (uint32_t i = 0; i < n; i++) {
+                const uint8_t* from = img + i * image_stride;
+                uint8_t* to = h_up + (size_t)i * rowb * h;
+                if (stride == rowb) memcpy(to, from, rowb * h);
+                else for (uint32_t y = 0; y < h; y++) memcpy(to + (size_t)y * rowb, from + (size_t)y * stride, rowb);
+            }
+            CU(cudaMemcpyAsync(d_up, h_up, rowb * h * n, cudaMemcpyHostToDevice, st));
+        }
+        if (channels > 1) {
+            const size_t n_px = (size_t)w * h * n;
+            k_luma<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(s.d_rgb, s.d_in, n_px, (int)channels);
+            ctx->launches++;
+        }
     }
     int rc = run_pipeline(ctx, s, n, w, h, w, (uint64_t)w * h, s.d_in, limit);
     if (rc) return rc;
@@ -1011,6 +1121,7 @@ const char* sb200_status_string(int status) {
         case SB200_E_CUDA: return "CUDA error";
         case SB200_E_CAPACITY: return "capacity exceeded";
         case SB200_E_STATE: return "invalid state";
+        case SB200_E_UNSUPPORTED: return "unsupported on this machine";
         default: return "unknown status";
     }
 }
@@ -1098,6 +1209,8 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
             ctx->fork_octaves = !(fk && !strcmp(fk, "0"));
             const char* gr = getenv("SB200_GRAPHS");
             ctx->use_graphs = !(gr && !strcmp(gr, "0"));
+            const char* jc = getenv("SB200_JPEG_CHUNK");
+            if (jc && atoi(jc) >= 1) ctx->jpeg_chunk = (uint32_t)atoi(jc);
             const char* tl = getenv("SB200_TAIL");
             ctx->tail = !(tl && !strcmp(tl, "0"));
             CU(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM));
@@ -1147,6 +1260,14 @@ void sb200_destroy(sb200_ctx* ctx) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         free_slot(s);
     }
+    if (ctx->jstream) cudaStreamSynchronize(ctx->jstream);
+    ctx->jpeg.release();   // before the stream and the buffers its states may still reference
+    for (auto& g : ctx->jstage) {
+        cudaFree(g.d);
+        if (g.decoded) cudaEventDestroy(g.decoded);
+        for (auto e : g.read) if (e) cudaEventDestroy(e);
+    }
+    if (ctx->jstream) cudaStreamDestroy(ctx->jstream);
     for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -1158,10 +1279,12 @@ void sb200_destroy(sb200_ctx* ctx) {
     delete ctx;
 }
 
-static int extract_batch_impl(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
-                              uint64_t image_stride, int64_t features_limit, sb200_result* out, uint32_t channels) {
+static int extract_batch_impl(sb200_ctx* ctx, const Source& src, uint32_t n, uint32_t w, uint32_t h, int64_t features_limit,
+                              sb200_result* out) {
     if (!ctx) return SB200_E_INVALID;
-    if (!gray || !out || n == 0 || (uint64_t)stride < (uint64_t)w * channels || (channels != 1 && channels != 3 && channels != 4))
+    if (!out || n == 0) return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch");
+    if (!src.jpeg && (!src.img || (uint64_t)src.stride < (uint64_t)w * src.channels ||
+                      (src.channels != 1 && src.channels != 3 && src.channels != 4)))
         return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch");
     CU(cudaSetDevice(ctx->device));
     int rc = set_image_size(ctx, w, h);
@@ -1175,7 +1298,14 @@ static int extract_batch_impl(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, u
     // group sizes: full groups of B images, but a long batch starts and ends with a quarter-size group so that the
     // upload of the first group and the download of the last one -- the two copies nothing can overlap -- are short
     std::vector<uint32_t> sizes;
-    {
+    if (src.jpeg) {
+        // bitstreams: groups never straddle the chunks they are decoded in
+        for (uint64_t c0 = 0; c0 < n; c0 += src.chunk)
+            for (uint64_t rem = std::min<uint64_t>(src.chunk, n - c0); rem;) {
+                const uint32_t c = (uint32_t)std::min<uint64_t>(B, rem);
+                sizes.push_back(c); rem -= c;
+            }
+    } else {
         uint64_t rem = n;
         const uint32_t q = std::max<uint32_t>(1, B / 4);
         if (n >= 2ull * B && B >= 4) {
@@ -1192,7 +1322,7 @@ static int extract_batch_impl(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, u
     for (; g < sizes.size(); first += sizes[g], g++) {
         Slot& s = ctx->slot[g % N_SLOTS];
         // groups complete in launch order; the slot's previous group was collected before this launch (below)
-        rc = launch_group(ctx, s, gray + first * image_stride, sizes[g], w, h, stride, image_stride, features_limit, first, channels);
+        rc = launch_group(ctx, s, src, first, sizes[g], w, h, features_limit);
         if (rc) return rc;
         // the slot the NEXT group will use must be free again: collect the group that ran in it
         if (g + 1 >= (uint32_t)N_SLOTS) {
@@ -1217,14 +1347,116 @@ static int extract_batch_impl(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, u
 
 int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
                         uint64_t image_stride, int64_t features_limit, sb200_result* out) {
-    return extract_batch_impl(ctx, gray, n, w, h, stride, image_stride, features_limit, out, 1);
+    Source src;
+    src.img = gray; src.stride = stride; src.image_stride = image_stride; src.channels = 1;
+    return extract_batch_impl(ctx, src, n, w, h, features_limit, out);
 }
 
 int sb200_extract_batch_rgb(sb200_ctx* ctx, const uint8_t* rgb, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
                             uint64_t image_stride, uint32_t channels, int64_t features_limit, sb200_result* out) {
     if (ctx && channels != 3 && channels != 4) return fail(ctx, SB200_E_INVALID, "channels must be 3 (RGB) or 4 (RGBA)");
-    return extract_batch_impl(ctx, rgb, n, w, h, stride, image_stride, features_limit, out, channels);
+    Source src;
+    src.img = rgb; src.stride = stride; src.image_stride = image_stride; src.channels = channels;
+    return extract_batch_impl(ctx, src, n, w, h, features_limit, out);
 }
+
+// ---- JPEG input ----
+static_assert(sizeof(size_t) == sizeof(uint64_t), "lengths are passed to nvJPEG as size_t");
+
+static int jpeg_ready(sb200_ctx* ctx) {
+    std::string err;
+    if (!ctx->jpeg.init(N_SLOTS, err)) return fail(ctx, SB200_E_UNSUPPORTED, "%s", err.c_str());
+    return SB200_OK;
+}
+
+int sb200_jpeg_info(sb200_ctx* ctx, const uint8_t* jpeg, uint64_t length, uint32_t* w, uint32_t* h, uint32_t* components) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!jpeg || length == 0) return fail(ctx, SB200_E_INVALID, "bad arguments to jpeg_info");
+    CU(cudaSetDevice(ctx->device));
+    int rc = jpeg_ready(ctx);
+    if (rc) return rc;
+    JpegDecoder::Info inf;
+    std::string err;
+    if (!ctx->jpeg.info(jpeg, (size_t)length, inf, err)) return fail(ctx, SB200_E_INVALID, "%s", err.c_str());
+    if (w) *w = inf.w;
+    if (h) *h = inf.h;
+    if (components) *components = inf.components;
+    return SB200_OK;
+}
+
+// headers of all streams: one frame size for the whole call; *rgb = some stream carries colour
+static int jpeg_batch_info(sb200_ctx* ctx, const uint8_t* const* jpegs, const uint64_t* lengths, uint32_t n, uint32_t* w,
+                           uint32_t* h, bool* rgb) {
+    *rgb = false;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!jpegs[i] || lengths[i] == 0) return fail(ctx, SB200_E_INVALID, "JPEG %u is empty", i);
+        JpegDecoder::Info inf;
+        std::string err;
+        if (!ctx->jpeg.info(jpegs[i], (size_t)lengths[i], inf, err)) return fail(ctx, SB200_E_INVALID, "JPEG %u: %s", i, err.c_str());
+        if (i == 0) { *w = inf.w; *h = inf.h; }
+        else if (inf.w != *w || inf.h != *h)
+            return fail(ctx, SB200_E_INVALID, "JPEG %u is %ux%u, the batch is %ux%u (one size per call)", i, inf.w, inf.h, *w, *h);
+        if (inf.components == 3) *rgb = true;
+    }
+    return SB200_OK;
+}
+
+int sb200_extract_batch_jpeg(sb200_ctx* ctx, const uint8_t* const* jpegs, const uint64_t* lengths, uint32_t n,
+                             int64_t features_limit, sb200_result* out) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!jpegs || !lengths || !out || n == 0) return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch_jpeg");
+    CU(cudaSetDevice(ctx->device));
+    int rc = jpeg_ready(ctx);
+    if (rc) return rc;
+    uint32_t w = 0, h = 0;
+    Source src;
+    rc = jpeg_batch_info(ctx, jpegs, lengths, n, &w, &h, &src.jpeg_rgb);
+    if (rc) return rc;
+    if (w > ctx->max_w || h > ctx->max_h)
+        return fail(ctx, SB200_E_INVALID, "image %ux%u larger than the context's %ux%u", w, h, ctx->max_w, ctx->max_h);
+    src.jpeg = jpegs;
+    src.jpeg_len = reinterpret_cast<const size_t*>(lengths);
+    src.n = n;
+    // chunks of about jpeg_chunk streams, equal in size (a short last chunk would fall back to Huffman decoding on the
+    // host inside nvJPEG), a multiple of the group size
+    const uint32_t B = ctx->max_batch;
+    const uint32_t n_chunks = std::max<uint32_t>(1, n / std::max<uint32_t>(ctx->jpeg_chunk, 1));
+    src.chunk = std::max<uint32_t>(1, ((n + n_chunks - 1) / n_chunks + B - 1) / B * B);
+    rc = jpeg_stage_ready(ctx, (size_t)std::min(src.chunk, n) * w * h * (src.jpeg_rgb ? 3 : 1));
+    if (rc) return rc;
+    return extract_batch_impl(ctx, src, n, w, h, features_limit, out);
+}
+
+int sb200_decode_jpeg_luma(sb200_ctx* ctx, const uint8_t* jpeg, uint64_t length, uint8_t* gray, uint64_t capacity) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!jpeg || length == 0 || !gray) return fail(ctx, SB200_E_INVALID, "bad arguments to decode_jpeg_luma");
+    CU(cudaSetDevice(ctx->device));
+    int rc = jpeg_ready(ctx);
+    if (rc) return rc;
+    uint32_t w = 0, h = 0;
+    bool rgb = false;
+    rc = jpeg_batch_info(ctx, &jpeg, &length, 1, &w, &h, &rgb);
+    if (rc) return rc;
+    if ((uint64_t)w * h > capacity) return fail(ctx, SB200_E_CAPACITY, "output buffer holds %llu bytes, the image has %llu",
+                                                (unsigned long long)capacity, (unsigned long long)w * h);
+    if (w > ctx->max_w || h > ctx->max_h)
+        return fail(ctx, SB200_E_INVALID, "image %ux%u larger than the context's %ux%u", w, h, ctx->max_w, ctx->max_h);
+    Slot& s = ctx->slot[0];
+    CU(cudaStreamSynchronize(s.stream));
+    Source src;
+    const size_t len = (size_t)length;
+    src.jpeg = &jpeg; src.jpeg_len = &len; src.jpeg_rgb = rgb; src.n = 1; src.chunk = 1;
+    rc = jpeg_stage_ready(ctx, (size_t)w * h * (rgb ? 3 : 1));
+    if (rc) return rc;
+    rc = fetch_decoded(ctx, s, src, 0, 1, w, h);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(gray, s.d_in, (size_t)w * h, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    ctx->have_pyramid = ctx->have_single = false;   // the slot's input buffer no longer matches its pyramid
+    return SB200_OK;
+}
+
+const char* sb200_jpeg_backend(const sb200_ctx* ctx) { return ctx ? ctx->jpeg.backend() : "none"; }
 
 int sb200_rgb_to_luma(sb200_ctx* ctx, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t stride, uint32_t channels,
                       uint8_t* gray) {
