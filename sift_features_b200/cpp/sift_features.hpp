@@ -6,6 +6,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sift_b200.h"
@@ -64,6 +65,20 @@ public:
                                   features_limit ? (int64_t)*features_limit : -1, &r));
         std::vector<SiftResult> out;
         for (uint32_t i = 0; i < n; i++) out.push_back(take(r, i));
+        return out;
+    }
+    // image::open(..).grayscale() + sift(), examples/run-sift.rs:8-19: JPEG bitstreams of one frame size, decoded
+    // (nvJPEG) and converted to luma on the device
+    std::vector<SiftResult> sift_jpeg(const std::vector<std::pair<const uint8_t*, uint64_t>>& jpegs,
+                                      std::optional<size_t> features_limit = std::nullopt) {
+        std::vector<const uint8_t*> ptr;
+        std::vector<uint64_t> len;
+        for (auto& j : jpegs) { ptr.push_back(j.first); len.push_back(j.second); }
+        sb200_result r{};
+        check(sb200_extract_batch_jpeg(ctx_, ptr.data(), len.data(), (uint32_t)ptr.size(),
+                                       features_limit ? (int64_t)*features_limit : -1, &r));
+        std::vector<SiftResult> out;
+        for (uint32_t i = 0; i < ptr.size(); i++) out.push_back(take(r, i));
         return out;
     }
     // precompute_images, src/lib.rs:131-143 (the pyramid stays on the device)

@@ -53,6 +53,9 @@ extern "C" {
     fn sb200_extract_precomputed(ctx: *mut Sb200Ctx, limit: i64, out: *mut Sb200Result) -> c_int;
     fn sb200_compute_descriptors(ctx: *mut Sb200Ctx, img: *const f32, w: u32, h: u32, stride: u32,
                                  kps: *const Sb200DescIn, n: u64, out: *mut u8) -> c_int;
+    fn sb200_jpeg_info(ctx: *mut Sb200Ctx, jpeg: *const u8, length: u64, w: *mut u32, h: *mut u32, components: *mut u32) -> c_int;
+    fn sb200_extract_batch_jpeg(ctx: *mut Sb200Ctx, jpegs: *const *const u8, lengths: *const u64, n: u32, limit: i64,
+                                out: *mut Sb200Result) -> c_int;
     fn sb200_match_descriptors(ctx: *mut Sb200Ctx, query: *const u8, n_query: u64, train: *const u8, n_train: u64,
                                out: *mut DMatch, cap: u64, n_out: *mut u64) -> c_int;
 }
@@ -78,6 +81,20 @@ pub fn match_descriptors(query: &Array2<u8>, train: &Array2<u8>) -> Vec<DMatch> 
     ctx.check(st);
     unsafe { out.set_len(n as usize) };
     out
+}
+
+/// `image::load_from_memory(bytes)?.grayscale()` + `sift()` (`src/lib.rs:1012-1019`, `examples/run-sift.rs:8-19`) with
+/// the JPEG decode and the luma conversion on the device.
+pub fn sift_jpeg(jpeg: &[u8], features_limit: Option<usize>) -> SiftResult {
+    let probe = Context::new(8, 8);
+    let (mut w, mut h, mut c) = (0u32, 0u32, 0u32);
+    probe.check(unsafe { sb200_jpeg_info(probe.0, jpeg.as_ptr(), jpeg.len() as u64, &mut w, &mut h, &mut c) });
+    let ctx = Context::new(w, h);
+    let mut r = std::mem::MaybeUninit::<Sb200Result>::zeroed();
+    let (ptr, len) = (jpeg.as_ptr(), jpeg.len() as u64);
+    let st = unsafe { sb200_extract_batch_jpeg(ctx.0, &ptr, &len, 1, features_limit.map_or(-1, |l| l as i64), r.as_mut_ptr()) };
+    ctx.check(st);
+    Context::take(unsafe { &r.assume_init() })
 }
 
 /// One context per (thread, device); owns the device arenas.
