@@ -368,6 +368,15 @@ def run_b200(args, rank, local_rank, world):
                 "pyramid_dog": {"algorithmic_bytes_per_image": tot, "ms_per_image": pyr_ms / imgs_rank,
                                 "achieved": tot * imgs_rank / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else None,
                                 "frac": tot * imgs_rank / (pyr_ms * 1e-3) / 1e9 / peak if pyr_ms > 0 else None},
+                # the other two heavy stages, for the record: the extrema scan streams the six layers (24 B/px) and sits
+                # at the HBM roof; the keypoint stages work on L2-resident patches (8.24 KB per keypoint at the bench
+                # shape) and are issue / shared-memory bound, so their HBM fraction is low
+                "extrema_stage": {"algorithmic_bytes_per_image": a_ext, "ms_per_image": stats["extrema"]["ms"] / imgs_rank,
+                                  "frac": a_ext * imgs_rank / (stats["extrema"]["ms"] * 1e-3) / 1e9 / peak
+                                  if stats["extrema"]["ms"] > 0 else None},
+                "descriptor_stage": {"bound": "issue (ncu: 86 % of SM peak, LSU pipe 52 %)",
+                                     "ms_per_image": stats["descriptor"]["ms"] / imgs_rank,
+                                     "ns_per_keypoint": 1e6 * stats["descriptor"]["ms"] / imgs_rank / max(kp_per_group / B, 1)},
             }
             line["stages_ms_per_image"] = {k: v["ms"] / imgs_rank for k, v in stats.items()}
             line["whole_path_frac_of_hbm_roofline"] = tot * value / world / 1e9 / peak

@@ -520,8 +520,14 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 //     exp / atan2 / trilinear part always runs with 32 active lanes.
 //   * The four pixel loads of the next 32 samples are issued before the arithmetic of the current 32.
 // ---------------------------------------------------------------------------
-constexpr int DESC_WARPS = 8;
-constexpr int DESC_COPIES = 16;
+#ifndef SB_DESC_WARPS
+#define SB_DESC_WARPS 8
+#endif
+#ifndef SB_DESC_COPIES
+#define SB_DESC_COPIES 16
+#endif
+constexpr int DESC_WARPS = SB_DESC_WARPS;
+constexpr int DESC_COPIES = SB_DESC_COPIES;
 constexpr int DESC_MAXROWS = 256;  // window rows: 2 * radius + 1 with radius <= 127
 constexpr int DESC_CELL_WORDS = 8 * DESC_COPIES;               // one spatial cell: 8 orientation bins x copies
 constexpr int DESC_HIST_WORDS = 17 * DESC_CELL_WORDS;          // 16 cells + one that swallows out-of-grid parts

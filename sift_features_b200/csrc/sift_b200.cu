@@ -1289,7 +1289,10 @@ static int extract_batch_impl(sb200_ctx* ctx, const Source& src, uint32_t n, uin
     CU(cudaSetDevice(ctx->device));
     int rc = set_image_size(ctx, w, h);
     if (rc) return rc;
-    for (auto& s : ctx->slot) CU(cudaStreamSynchronize(s.stream));  // results of the previous call are released
+    for (auto& s : ctx->slot) {
+        CU(cudaStreamSynchronize(s.stream));  // results of the previous call are released
+        s.busy = false;                        // groups a failed call left behind are dropped, not collected
+    }
     ctx->res_n = 0;
     ctx->have_pyramid = false;
     rc = ensure_result_capacity(ctx, 0, n);
@@ -1566,7 +1569,10 @@ int sb200_extract_precomputed(sb200_ctx* ctx, int64_t features_limit, sb200_resu
     if (!ctx->have_pyramid) return fail(ctx, SB200_E_STATE, "no pyramid resident: call sb200_precompute first");
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slot[ctx->last_slot];
-    for (auto& sl : ctx->slot) CU(cudaStreamSynchronize(sl.stream));
+    for (auto& sl : ctx->slot) {
+        CU(cudaStreamSynchronize(sl.stream));
+        sl.busy = false;
+    }
     ctx->res_n = 0;
     int rc = ensure_result_capacity(ctx, 0, 1);
     if (rc) return rc;
