@@ -89,6 +89,15 @@ struct Slot {
     bool busy = false;
 };
 
+// chunks of bitstreams in flight: JPEG_AHEAD chunks are decoding (round-robin over JPEG_STREAMS streams, so that
+// nvJPEG's latency-bound Huffman kernels of consecutive chunks overlap) while the groups of an earlier chunk run
+#ifndef SB_JPEG_AHEAD
+#define SB_JPEG_AHEAD 3
+#endif
+constexpr int JPEG_AHEAD = SB_JPEG_AHEAD;
+constexpr int JPEG_STREAMS = JPEG_AHEAD;
+constexpr int JPEG_STAGES = JPEG_AHEAD + 1;
+
 // stage buffer of the JPEG entry points: decoded pixels (Y or interleaved RGB) of one chunk of bitstreams
 struct JpegStage {
     uint8_t* d = nullptr;
@@ -147,11 +156,11 @@ struct sb200_ctx {
     DescIn* d_dkps = nullptr;
     uint8_t* d_ddesc = nullptr;
     size_t dkps_cap = 0;
-    // JPEG input (nvJPEG, loaded on first use): bitstreams are decoded a chunk at a time on their own stream into one of
-    // two stage buffers, so that the decode of chunk c+1 overlaps the extraction of chunk c
+    // JPEG input (nvJPEG, loaded on first use): bitstreams are decoded a chunk at a time on their own streams into
+    // stage buffers, so that the decode of the next chunks overlaps the extraction of chunk c
     JpegDecoder jpeg;
-    JpegStage jstage[2];
-    cudaStream_t jstream = nullptr;
+    JpegStage jstage[JPEG_STAGES];
+    cudaStream_t jstream[JPEG_STREAMS] = {nullptr};
     uint32_t jpeg_chunk = 128;   // SB200_JPEG_CHUNK; nvJPEG decodes Huffman on the GPU for batches of >= 100 streams
     // matcher scratch (grow-only)
     uint8_t* d_mdesc[2] = {nullptr, nullptr};        // query / train descriptors
@@ -913,14 +922,15 @@ struct Source {
 };
 
 int jpeg_stage_ready(sb200_ctx* ctx, size_t bytes) {
-    if (!ctx->jstream) CU(cudaStreamCreateWithFlags(&ctx->jstream, cudaStreamNonBlocking));
+    for (auto& js : ctx->jstream)
+        if (!js) CU(cudaStreamCreateWithFlags(&js, cudaStreamNonBlocking));
     for (auto& g : ctx->jstage) {
         if (!g.decoded) {
             CU(cudaEventCreateWithFlags(&g.decoded, cudaEventDisableTiming));
             for (auto& e : g.read) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         if (g.cap < bytes) {
-            CU(cudaStreamSynchronize(ctx->jstream));
+            for (auto& js : ctx->jstream) CU(cudaStreamSynchronize(js));
             for (auto& t : ctx->slot) CU(cudaStreamSynchronize(t.stream));
             cudaFree(g.d); g.d = nullptr; g.cap = 0;
             CU(dalloc(&g.d, bytes));
@@ -930,21 +940,22 @@ int jpeg_stage_ready(sb200_ctx* ctx, size_t bytes) {
     return SB200_OK;
 }
 
-// decodes chunk c of the call's bitstreams into stage buffer c % 2 on the decode stream (device-side decode: only the
-// compressed bytes cross the host/device boundary)
+// decodes chunk c of the call's bitstreams into stage buffer c % JPEG_STAGES on decode stream c % JPEG_STREAMS
+// (device-side decode: only the compressed bytes cross the host/device boundary)
 int decode_chunk(sb200_ctx* ctx, const Source& src, uint32_t c, uint32_t w, uint32_t h) {
-    JpegStage& g = ctx->jstage[c & 1];
+    JpegStage& g = ctx->jstage[c % JPEG_STAGES];
+    cudaStream_t js = ctx->jstream[c % JPEG_STREAMS];
     const uint32_t first = c * src.chunk, n = std::min(src.chunk, src.n - first);
     const size_t bpp = src.jpeg_rgb ? 3 : 1, img_bytes = (size_t)w * h * bpp;
     for (int k = 0; k < N_SLOTS; k++)   // groups of the chunk that used this buffer before have to be done with it
-        if (g.read_valid[k]) { CU(cudaStreamWaitEvent(ctx->jstream, g.read[k], 0)); g.read_valid[k] = false; }
+        if (g.read_valid[k]) { CU(cudaStreamWaitEvent(js, g.read[k], 0)); g.read_valid[k] = false; }
     std::vector<uint8_t*> dst(n);
     for (uint32_t i = 0; i < n; i++) dst[i] = g.d + i * img_bytes;
     std::string err;
-    if (!ctx->jpeg.decode((int)(c & 1), src.jpeg + first, src.jpeg_len + first, n, src.jpeg_rgb, dst.data(), (size_t)w * bpp,
-                          ctx->jstream, err))
+    if (!ctx->jpeg.decode((int)(c % JPEG_STAGES), src.jpeg + first, src.jpeg_len + first, n, src.jpeg_rgb, dst.data(),
+                          (size_t)w * bpp, js, err))
         return fail(ctx, SB200_E_INVALID, "%s", err.c_str());
-    CU(cudaEventRecord(g.decoded, ctx->jstream));
+    CU(cudaEventRecord(g.decoded, js));
     return SB200_OK;
 }
 
@@ -952,16 +963,15 @@ int decode_chunk(sb200_ctx* ctx, const Source& src, uint32_t c, uint32_t w, uint
 int fetch_decoded(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img, uint32_t n, uint32_t w, uint32_t h) {
     const uint32_t c = (uint32_t)(first_img / src.chunk);
     if (first_img % src.chunk == 0) {
-        // first group of a chunk: the chunk itself if nothing decoded it yet, and the next one so that it decodes
-        // while this chunk's groups run
-        int rc = c == 0 ? decode_chunk(ctx, src, 0, w, h) : SB200_OK;
-        if (rc) return rc;
-        if ((uint64_t)(c + 1) * src.chunk < src.n) {
-            rc = decode_chunk(ctx, src, c + 1, w, h);
+        // first group of a chunk: keep JPEG_AHEAD chunks decoding beyond this one (at the start of the call, this
+        // chunk and the ones after it) while this chunk's groups run
+        for (uint32_t d = (c == 0 ? 0 : c + JPEG_AHEAD); d <= c + JPEG_AHEAD; d++) {
+            if (d != 0 && (uint64_t)d * src.chunk >= src.n) break;
+            int rc = decode_chunk(ctx, src, d, w, h);
             if (rc) return rc;
         }
     }
-    JpegStage& g = ctx->jstage[c & 1];
+    JpegStage& g = ctx->jstage[c % JPEG_STAGES];
     const size_t px = (size_t)w * h, bpp = src.jpeg_rgb ? 3 : 1;
     const uint8_t* from = g.d + (first_img - (uint64_t)c * src.chunk) * px * bpp;
     CU(cudaStreamWaitEvent(s.stream, g.decoded, 0));
@@ -1260,14 +1270,14 @@ void sb200_destroy(sb200_ctx* ctx) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         free_slot(s);
     }
-    if (ctx->jstream) cudaStreamSynchronize(ctx->jstream);
+    for (auto js : ctx->jstream) if (js) cudaStreamSynchronize(js);
     ctx->jpeg.release();   // before the stream and the buffers its states may still reference
     for (auto& g : ctx->jstage) {
         cudaFree(g.d);
         if (g.decoded) cudaEventDestroy(g.decoded);
         for (auto e : g.read) if (e) cudaEventDestroy(e);
     }
-    if (ctx->jstream) cudaStreamDestroy(ctx->jstream);
+    for (auto js : ctx->jstream) if (js) cudaStreamDestroy(js);
     for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -1368,7 +1378,7 @@ static_assert(sizeof(size_t) == sizeof(uint64_t), "lengths are passed to nvJPEG 
 
 static int jpeg_ready(sb200_ctx* ctx) {
     std::string err;
-    if (!ctx->jpeg.init(N_SLOTS, err)) return fail(ctx, SB200_E_UNSUPPORTED, "%s", err.c_str());
+    if (!ctx->jpeg.init(JPEG_STAGES, err)) return fail(ctx, SB200_E_UNSUPPORTED, "%s", err.c_str());
     return SB200_OK;
 }
 
