@@ -1236,8 +1236,13 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         {
             int per_sm = 0;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_descriptor, 32 * DESC_WARPS, DESC_SMEM_BYTES));
+            // SB200_DESC_CTAS / SB200_ORI_CTAS (per SM) leave room on every SM for the other slot's kernels (experiments)
+            const char* dc = getenv("SB200_DESC_CTAS");
+            if (dc && atoi(dc) >= 1) per_sm = std::min(per_sm, atoi(dc));
             ctx->desc_ctas = std::max(1, per_sm) * ctx->sm_count;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orient, 32 * ORI_WARPS, 0));
+            const char* oc = getenv("SB200_ORI_CTAS");
+            if (oc && atoi(oc) >= 1) per_sm = std::min(per_sm, atoi(oc));
             ctx->ori_ctas = std::max(1, per_sm) * ctx->sm_count;
         }
         {
