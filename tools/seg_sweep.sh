@@ -1,7 +1,7 @@
 #!/bin/bash
-# sweeps the marching-blur segment height at the bench's batch size (development aid)
+# sweeps the marching-blur segment height at the bench's batch size (development aid): [WORKLOAD=vga] seg_sweep.sh rows...
 for r in "$@"; do
-  SB200_SEG_ROWS=$r python bench.py --no-cpu --steps 6 2>/dev/null > /tmp/segsweep.json
+  SB200_SEG_ROWS=$r python bench.py --workload ${WORKLOAD:-1080p} --no-cpu --steps 6 2>/dev/null > /tmp/segsweep.json
   python - "$r" <<'P'
 import json, sys
 d = json.loads(open('/tmp/segsweep.json').read().strip().splitlines()[-1])
