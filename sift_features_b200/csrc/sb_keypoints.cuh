@@ -587,8 +587,13 @@ __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const uin
     if (active) {
         const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
         const int i = (G.y + yw) * G.pitch + (G.x + xw);   // a layer holds < 2^31 floats: 32-bit offsets
-        q.xp = __ldg(G.img + (i + 1)); q.xm = __ldg(G.img + (i - 1));
-        q.ym = __ldg(G.img + (i - G.pitch)); q.yp = __ldg(G.img + (i + G.pitch));
+        // one 64-bit address, kept opaque so that the neighbours are pointer +- pitch (two adds each) instead of
+        // three more base + 64-bit index computations
+        const float* pc = G.img + i;
+        asm volatile("" : "+l"(pc));
+        const ptrdiff_t pitch = G.pitch;
+        q.xp = __ldg(pc + 1); q.xm = __ldg(pc - 1);
+        q.ym = __ldg(pc - pitch); q.yp = __ldg(pc + pitch);
     }
     return q;
 }
@@ -675,7 +680,9 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
         for (int k = lane; k < DESC_HIST_WORDS / 4; k += 32) h4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     DescGeom G;
-    G.img = t.img; G.w = t.w; G.h = t.h; G.pitch = t.pitch; G.orientation = t.orientation;
+    G.img = t.img;
+    asm volatile("" : "+l"(G.img));   // a plain 64-bit pointer from here on (not base + layer offset re-derived per use)
+    G.w = t.w; G.h = t.h; G.pitch = t.pitch; G.orientation = t.orientation;
     // `x.round() as usize` (src/lib.rs:796-797): saturating, negative -> 0
     const float xr = roundf(t.x), yr = roundf(t.y);
     G.x = xr > 0.f ? (int)fminf(xr, 1e9f) : 0;

@@ -247,6 +247,14 @@ def test_fuzz_sizes(sf, oracle):
         _check_image(sf, oracle, g, pyramid=(case % 6 == 0))
 
 
+@pytest.mark.parametrize("w,h", [(4096, 10), (10, 4096), (2000, 16), (16, 2000), (4096, 1), (1, 4096), (3000, 33), (33, 3000)])
+def test_extreme_aspect(sf, oracle, w, h):
+    """Strips and ribbons up to the maximum dimension: octaves that run out of rows or columns long before the other
+    dimension does (TMA boxes wider / taller than the layer, single-row layers, the fused tail on 1-pixel-wide octaves)."""
+    _check_image(sf, oracle, smooth_image(w, h, w + h), pyramid=False)
+    _check_image(sf, oracle, noise_image(w, h, w * 7 + h), pyramid=(w * h < 50000))
+
+
 def test_concurrent_contexts(sf):
     """The crate's functions are re-entrant: here one context per thread; four threads on one
     device at once give what each gives alone."""
