@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
         const int o = r.octave_scale >> 8, layer = r.octave_scale & 255;
         const OctLayout& ol = P.L.o[o];
         const float* I = gimg + ol.off + (long long)layer * ol.layer_stride;
+        asm volatile("" : "+l"(I));   // a plain 64-bit pointer from here on (not base + layer offset re-derived per load)
         const int w = ol.w, h = ol.h, pitch = ol.pitch;
         const int x = r.px, y = r.py;
         const int radius = (int)roundf(3.f * 1.5f * r.kp_scale);  // src/lib.rs:380
@@ -256,7 +257,9 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
             const bool in = idx < total && yi > 0 && yi < h - 1 && xi > 0 && xi < w - 1;
             if (in) {
                 const float* c = I + (yi * pitch + xi);
-                q = make_float4(__ldg(c + 1), __ldg(c - 1), __ldg(c - pitch), __ldg(c + pitch));
+                asm volatile("" : "+l"(c));   // one address; the neighbours are pointer +- pitch
+                const ptrdiff_t dp = pitch;
+                q = make_float4(__ldg(c + 1), __ldg(c - 1), __ldg(c - dp), __ldg(c + dp));
             }
             xq_n += 32;
             if (xq_n >= side) { xq_n -= side; yq_n++; }
