@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 //     arithmetic).
 //   * Window samples that fall outside the rotated 4x4 grid (about half) are never visited: the lanes
 //     compute, in parallel, the column span of every window row that can intersect the grid and a running
-//     sample count (one packed word per non-empty row in shared memory); sample i of the keypoint is then
-//     found from that table with one warp-wide OR-reduction per 32 samples, so the expensive gradient /
+//     sample count (one packed word per non-empty row in shared memory); every lane then walks that table with
+//     its own cursor, 32 samples forward per step, so the expensive gradient /
 //     exp / atan2 / trilinear part always runs with 32 active lanes.
 //   * The four pixel loads of the next 32 samples are issued before the arithmetic of the current 32.
 // ---------------------------------------------------------------------------
@@ -533,7 +533,7 @@ constexpr int DESC_WARPS = SB_DESC_WARPS;
 constexpr int DESC_COPIES = SB_DESC_COPIES;
 constexpr int DESC_MAXROWS = 256;  // window rows: 2 * radius + 1 with radius <= 127
 constexpr int DESC_CELL_WORDS = 8 * DESC_COPIES;               // one spatial cell: 8 orientation bins x copies
-constexpr int DESC_HIST_WORDS = 17 * DESC_CELL_WORDS;          // 16 cells + one that swallows out-of-grid parts
+constexpr int DESC_HIST_WORDS = 16 * DESC_CELL_WORDS;          // the 4x4 cells the crop at :951 keeps
 // per warp: histogram copies, row table (running count u16[256], first column u8[256])
 constexpr int DESC_SMEM_WORDS = DESC_HIST_WORDS + DESC_MAXROWS / 2 + DESC_MAXROWS / 4;
 constexpr size_t DESC_SMEM_BYTES = 256 + (size_t)DESC_WARPS * DESC_SMEM_WORDS * sizeof(float);
@@ -548,6 +548,7 @@ struct DescGeom {
     const float* img;
     int w, h, pitch, x, y, radius;
     float sin_s, cos_s, orientation;
+    float ori_bins;   // orientation in histogram bins (8 per turn)
 };
 
 // single-instruction SFU approximations (flush-to-zero: no denormal rescaling sequences around the MUFU)
@@ -555,31 +556,30 @@ __device__ __forceinline__ float rcp_approx(const float x) { float r; asm("rcp.a
 __device__ __forceinline__ float rsqrt_approx(const float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float ex2_approx(const float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// atan2(y, x) in degrees, [0, 360): minimax polynomial of atan on [0,1] (|error| < 3.3e-7 rad) plus octant
-// folding.  The reference's f64 atan2 only feeds the trilinear orientation weights here (continuous in the
-// angle), so a 2e-5 degree error is far below the u8 quantisation step of the descriptor.
-__device__ __forceinline__ float fast_atan2_deg(const float y, const float x) {
+// atan2(y, x) in orientation-bin units (8 bins per turn), [0, 8]: minimax polynomial of atan on [0,1]
+// (|error| < 3.3e-7 rad, coefficients pre-multiplied by 8 / 2pi) plus octant folding.  The reference's f64 atan2
+// only feeds the trilinear orientation weights here (continuous in the angle, taken modulo 8 bins by the caller), so
+// a 5e-7 bin error is far below the u8 quantisation step of the descriptor.
+__device__ __forceinline__ float fast_atan2_bins(const float y, const float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    // the flush-to-zero reciprocal needs a normal operand: gradients deep inside constant regions are denormal
-    // (scaling numerator and denominator by 2^64 is exact)
-    const float sc = mx < 1e-30f ? 0x1p64f : 1.0f;
-    const float a = (mx > 0.f) ? (mn * sc) * rcp_approx(mx * sc) : 0.f;
+    // the flush-to-zero reciprocal needs a normal operand: gradients deep inside constant regions are denormal.
+    // Scaling numerator and denominator by 2^64 is exact and makes every nonzero gradient normal (|gradient| <= 1, so
+    // nothing overflows); the floor keeps the reciprocal finite at 0 / 0, where the quotient is then 0 * finite = 0
+    const float a = (mn * 0x1p64f) * rcp_approx(fmaxf(mx * 0x1p64f, 1e-30f));
     const float s = a * a;
-    float p = 0x1.be6ae0p-8f;
-    p = fmaf(p, s, -0x1.134924p-5f);
-    p = fmaf(p, s, 0x1.462378p-4f);
-    p = fmaf(p, s, -0x1.0f04d4p-3f);
-    p = fmaf(p, s, 0x1.95aa00p-3f);
-    p = fmaf(p, s, -0x1.552b7cp-2f);
-    p = fmaf(p, s, 0x1.ffff7ep-1f);
-    float r = p * a;                                   // [0, pi/4]
-    if (ay > ax) r = 1.57079632679489661923f - r;      // [0, pi/2]
-    if (x < 0.f) r = 3.14159265358979323846f - r;      // [0, pi]
-    if (y < 0.f) r = 6.28318530717958647692f - r;      // (pi, 2pi]
-    float deg = r * 57.29577951308232f;
-    if (deg >= 360.0f) deg -= 360.0f;
-    return deg;
+    float p = 0x1.1c32bcp-7f;
+    p = fmaf(p, s, -0x1.5e8130p-5f);
+    p = fmaf(p, s, 0x1.9f40a4p-4f);
+    p = fmaf(p, s, -0x1.59126ap-3f);
+    p = fmaf(p, s, 0x1.0240f6p-2f);
+    p = fmaf(p, s, -0x1.b26416p-2f);
+    p = fmaf(p, s, 0x1.45f2b4p+0f);
+    float r = p * a;                 // [0, 1]: one bin is pi/4
+    if (ay > ax) r = 2.0f - r;       // [0, 2]
+    if (x < 0.f) r = 4.0f - r;       // [0, 4]
+    if (y < 0.f) r = 8.0f - r;       // (4, 8]
+    return r;
 }
 
 // one queued sample per active lane: gradient, weight, angle, trilinear split, accumulation
@@ -602,8 +602,9 @@ __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const uin
 }
 
 // one sample per lane: gradient, weight, angle, trilinear split, accumulation.  Branch-free up to the
-// accumulation: lanes without a sample (or whose sample fails the exact membership test) and the parts of a
-// sample that fall outside the 4x4 grid are steered into the spare 17th cell instead of being predicated off.
+// accumulation; the parts of a sample that fall outside the 4x4 grid (all of it for a sample that fails the exact
+// membership test) are predicated off read-modify-write by read-modify-write, and the four cells sit at constant
+// offsets from one base address per orientation bin.
 __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint32_t packed, const bool active,
                                                   const DescPix px, float* hist, const int lane) {
     // geometry: the reference's f32 operations, so the membership test, cell indices and fractions are its values
@@ -615,7 +616,7 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     // The membership test of src/lib.rs:834-837, -0.5 < row_bin, col_bin < 4.5, needs no instruction of its own:
     // it holds exactly when floor(row_bin - 0.5) and floor(col_bin - 0.5) lie in -1..3 (at the one value where the
     // two differ, row_bin == -0.5, the sample's share of every kept cell is c1 = mag * 0 = +0), and a sample whose
-    // floors are outside that range has no valid cell below, so all of it lands in the spare cell.  Lanes without a
+    // floors are outside that range has no valid cell below, so none of it is accumulated.  Lanes without a
     // sample carry zero pixels: their magnitude, hence every contribution, is +0.  (The image-bounds half of the
     // test, :838-841, is enforced by the span construction.)
     (void)active;
@@ -625,12 +626,12 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     // magnitude, Gaussian weight and angle: fast approximations (relative error ~1e-6), see header comment
     const float d2 = fmaf(dx, dx, dy * dy);
     const float wgt = fmaf(col_rot, col_rot, row_rot * row_rot);
-    // sqrt(d2) = d2 * rsqrt(d2); a denormal d2 (constant image regions) is scaled into the normal range first
-    const float d2s = d2 < 1e-30f ? d2 * 0x1p64f : d2;
-    const float root = (d2 > 0.f ? d2s * rsqrt_approx(d2s) : 0.f) * (d2 < 1e-30f ? 0x1p-32f : 1.0f);
+    // sqrt(d2) = d2 * rsqrt(d2) = d2 * (rsqrt(d2 * 2^64) * 2^32): the scaling (exact) gives the flush-to-zero rsqrt a
+    // normal operand for every nonzero d2, denormal ones (constant image regions) included; the floor keeps it
+    // finite at d2 = 0, where the product is 0
+    const float root = d2 * (rsqrt_approx(fmaxf(d2 * 0x1p64f, 1e-30f)) * 0x1p32f);
     const float mag = root * ex2_approx(wgt * (-0.125f * 1.44269504088896341f));  // exp(-2/4^2 * wgt), :859
-    const float orient = fast_atan2_deg(dy, dx) - G.orientation;                   // :871
-    const float obin = orient * (8.0f / 360.0f);
+    const float obin = fast_atan2_bins(dy, dx) - G.ori_bins;                       // :871, in bins; in [-8, 8]
     const float row_floor = floorf(rb), col_floor = floorf(cbn), ori_floor = floorf(obin);
     const float row_frac = rb - row_floor, col_frac = cbn - col_floor, ori_frac = obin - ori_floor;
     // trilinear split exactly as src/lib.rs:906-919
@@ -650,25 +651,24 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     const bool r0ok = (unsigned)r1 <= 3u, r1ok = (unsigned)(r1 + 1) <= 3u;
     const bool q0ok = (unsigned)q1 <= 3u, q1ok = (unsigned)(q1 + 1) <= 3u;
     const int cell00 = r1 * 4 + q1;
-    int cw[4];  // word offsets of the four spatial cells (k >> 1: bit 0 = column step, bit 1 = row step)
-    cw[0] = ((r0ok & q0ok) ? cell00 : 16) * DESC_CELL_WORDS;
-    cw[1] = ((r0ok & q1ok) ? cell00 + 1 : 16) * DESC_CELL_WORDS;
-    cw[2] = ((r1ok & q0ok) ? cell00 + 4 : 16) * DESC_CELL_WORDS;
-    cw[3] = ((r1ok & q1ok) ? cell00 + 5 : 16) * DESC_CELL_WORDS;
-    float* const m0 = hist + (lane & (DESC_COPIES - 1)) + o0 * DESC_COPIES;
-    float* const m1 = hist + (lane & (DESC_COPIES - 1)) + o1 * DESC_COPIES;
-    float* pk[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) pk[k] = ((k & 1) ? m1 : m0) + cw[k >> 1];
+    // the four spatial cells (k >> 1: bit 0 = column step, bit 1 = row step) sit at constant offsets from cell
+    // (r1, q1); parts that fall outside the 4x4 grid are predicated off (the base may then point outside the
+    // histogram -- it is only dereferenced for cells inside the grid)
+    const bool ok[4] = {r0ok & q0ok, r0ok & q1ok, r1ok & q0ok, r1ok & q1ok};
+    constexpr int CO[4] = {0, DESC_CELL_WORDS, 4 * DESC_CELL_WORDS, 5 * DESC_CELL_WORDS};
+    float* const b0 = hist + (lane & (DESC_COPIES - 1)) + o0 * DESC_COPIES + cell00 * DESC_CELL_WORDS;
+    float* const b1 = b0 + (o1 - o0) * DESC_COPIES;
     // lanes l and l + DESC_COPIES share a copy: two phases
 #pragma unroll
     for (int phase = 0; phase < 32 / DESC_COPIES; phase++) {
         if ((lane / DESC_COPIES) == phase) {
             float old[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) old[k] = *pk[k];
+            for (int k = 0; k < 8; k++)
+                if (ok[k >> 1]) old[k] = ((k & 1) ? b1 : b0)[CO[k >> 1]];   // (left unset for parts outside the grid)
 #pragma unroll
-            for (int k = 0; k < 8; k++) *pk[k] = old[k] + cv[k];
+            for (int k = 0; k < 8; k++)
+                if (ok[k >> 1]) ((k & 1) ? b1 : b0)[CO[k >> 1]] = old[k] + cv[k];
         }
         __syncwarp();
     }
@@ -686,6 +686,7 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     G.img = t.img;
     asm volatile("" : "+l"(G.img));   // a plain 64-bit pointer from here on (not base + layer offset re-derived per use)
     G.w = t.w; G.h = t.h; G.pitch = t.pitch; G.orientation = t.orientation;
+    G.ori_bins = t.orientation * (8.0f / 360.0f);
     // `x.round() as usize` (src/lib.rs:796-797): saturating, negative -> 0
     const float xr = roundf(t.x), yr = roundf(t.y);
     G.x = xr > 0.f ? (int)fminf(xr, 1e9f) : 0;
