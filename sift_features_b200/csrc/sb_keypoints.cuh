@@ -585,19 +585,22 @@ __device__ __forceinline__ float fast_atan2_bins(const float y, const float x) {
 // one queued sample per active lane: gradient, weight, angle, trilinear split, accumulation
 struct DescPix { float xp, xm, ym, yp; };  // I[y][x+1], I[y][x-1], I[y-1][x], I[y+1][x]
 
-__device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const uint32_t packed, const bool active) {
-    DescPix q{0.f, 0.f, 0.f, 0.f};
-    if (active) {
-        const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
-        const int i = (G.y + yw) * G.pitch + (G.x + xw);   // a layer holds < 2^31 floats: 32-bit offsets
-        // one 64-bit address, kept opaque so that the neighbours are pointer +- pitch (two adds each) instead of
-        // three more base + 64-bit index computations
-        const float* pc = G.img + i;
-        asm volatile("" : "+l"(pc));
-        const ptrdiff_t pitch = G.pitch;
-        q.xp = __ldg(pc + 1); q.xm = __ldg(pc - 1);
-        q.ym = __ldg(pc - pitch); q.yp = __ldg(pc + pitch);
-    }
+struct DescAt { int yw, xw; };              // window coordinates of a lane's sample (relative to the keypoint pixel)
+
+// A lane without a sample is parked on the window corner (-radius, -radius): its rotated coordinates are >= 3.4
+// cells from the centre in one direction, outside the 4x4 grid, so nothing of it is accumulated whatever pixels it
+// carries -- it loads the keypoint's own pixel neighbourhood (always inside the image) instead of branching.
+__device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const DescAt at, const bool active) {
+    const int i = active ? (G.y + at.yw) * G.pitch + (G.x + at.xw)   // a layer holds < 2^31 floats: 32-bit offsets
+                         : G.y * G.pitch + G.x;
+    // one 64-bit address, kept opaque so that the neighbours are pointer +- pitch (two adds each) instead of
+    // three more base + 64-bit index computations
+    const float* pc = G.img + i;
+    asm volatile("" : "+l"(pc));
+    const ptrdiff_t pitch = G.pitch;
+    DescPix q;
+    q.xp = __ldg(pc + 1); q.xm = __ldg(pc - 1);
+    q.ym = __ldg(pc - pitch); q.yp = __ldg(pc + pitch);
     return q;
 }
 
@@ -605,10 +608,10 @@ __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const uin
 // accumulation; the parts of a sample that fall outside the 4x4 grid (all of it for a sample that fails the exact
 // membership test) are predicated off read-modify-write by read-modify-write, and the four cells sit at constant
 // offsets from one base address per orientation bin.
-__device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint32_t packed, const bool active,
-                                                  const DescPix px, float* hist, const int lane) {
+__device__ __forceinline__ void descriptor_sample(const DescGeom& G, const DescAt at, const DescPix px, float* hist,
+                                                  const int lane) {
     // geometry: the reference's f32 operations, so the membership test, cell indices and fractions are its values
-    const int yw = (int)(packed >> 8) - G.radius, xw = (int)(packed & 255u) - G.radius;
+    const int yw = at.yw, xw = at.xw;
     const float fx = (float)xw, fy = (float)yw;
     const float col_rot = fx * G.cos_s - fy * G.sin_s;
     const float row_rot = fx * G.sin_s + fy * G.cos_s;
@@ -616,10 +619,9 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const uint3
     // The membership test of src/lib.rs:834-837, -0.5 < row_bin, col_bin < 4.5, needs no instruction of its own:
     // it holds exactly when floor(row_bin - 0.5) and floor(col_bin - 0.5) lie in -1..3 (at the one value where the
     // two differ, row_bin == -0.5, the sample's share of every kept cell is c1 = mag * 0 = +0), and a sample whose
-    // floors are outside that range has no valid cell below, so none of it is accumulated.  Lanes without a
-    // sample carry zero pixels: their magnitude, hence every contribution, is +0.  (The image-bounds half of the
-    // test, :838-841, is enforced by the span construction.)
-    (void)active;
+    // floors are outside that range has no valid cell below, so none of it is accumulated -- which is also what
+    // happens to lanes without a sample (parked on the window corner).  (The image-bounds half of the test,
+    // :838-841, is enforced by the span construction.)
     const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
     const float dx = px.xp - px.xm;
     const float dy = px.ym - px.yp;
@@ -747,7 +749,8 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     // ---- samples, 32 at a time: every lane walks the table with its own cursor (row k, offset xo in the row),
     //      32 samples forward per batch -- one or two short rows at most, no search ----
     uint32_t cur_k = 0, cur_xo = lane, cur_w = n_rows ? row_tab[0] : 0u;
-    auto lookup = [&](const uint32_t advance, uint32_t& packed) -> bool {
+    const int y_first_w = (int)yq_first - G.radius;
+    auto lookup = [&](const uint32_t advance, DescAt& at) -> bool {
         cur_xo += advance;
         while (cur_k < n_rows && cur_xo >= (cur_w >> 8)) {
             cur_xo -= cur_w >> 8;
@@ -755,22 +758,22 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
             cur_w = cur_k < n_rows ? row_tab[cur_k] : 0u;
         }
         const bool active = cur_k < n_rows;
-        packed = active ? (((yq_first + cur_k) << 8) | ((cur_w & 255u) + cur_xo)) : 0u;
+        at.yw = active ? y_first_w + (int)cur_k : -G.radius;
+        at.xw = active ? (int)((cur_w & 255u) + cur_xo) - G.radius : -G.radius;
         return active;
     };
     if (total) {
-        uint32_t e_next;
-        bool a_next = lookup(0, e_next);
-        DescPix p_next = descriptor_fetch(G, e_next, a_next);
+        DescAt at_next;
+        bool a_next = lookup(0, at_next);
+        DescPix p_next = descriptor_fetch(G, at_next, a_next);
         for (uint32_t base = 0; base < total; base += 32) {
-            const uint32_t e = e_next;
-            const bool a = a_next;
+            const DescAt at = at_next;
             const DescPix px = p_next;
             if (base + 32 < total) {
-                a_next = lookup(32, e_next);
-                p_next = descriptor_fetch(G, e_next, a_next);
+                a_next = lookup(32, at_next);
+                p_next = descriptor_fetch(G, at_next, a_next);
             }
-            descriptor_sample(G, e, a, px, hist, lane);
+            descriptor_sample(G, at, px, hist, lane);
         }
     }
     __syncwarp();
