@@ -213,7 +213,6 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
                                                             const int n_img, uint32_t* __restrict__ work) {
     __shared__ uint64_t s_tab[32];
     __shared__ float s_val[ORI_WARPS][32];
-    __shared__ uint32_t s_msk[ORI_WARPS][40];
     __shared__ float s_raw[ORI_WARPS][40];
     __shared__ float s_hist[ORI_WARPS][ORI_BINS];
     if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
@@ -247,7 +246,9 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
         const float sigma = 1.5f * r.kp_scale;                    // LAMBDA_ORI * kp_scale, :386
         const float gws = -1.0f / (2.0f * sigma * sigma);         // :667
         const int side = 2 * radius + 1, total = side * side;
-        float acc0 = 0.f, acc1 = 0.f;  // bins `lane` and `32 + lane`
+        // the raw histogram accumulates in shared memory (s_raw[2 .. 2 + ORI_BINS), the layout the smoothing reads)
+        s_raw[warp][lane + 2] = 0.f;
+        if (lane < ORI_BINS - 32) s_raw[warp][32 + lane + 2] = 0.f;
         // sample `idx` of the (2r+1)^2 window in raster order: pixel loads are issued one batch of 32 ahead.
         // The lane's (row, column) advance by 32 samples per batch: at most two row wraps (side >= 17), no division.
         int yq_n = lane / side, xq_n = lane - yq_n * side;   // window coordinates of the lane's next sample
@@ -295,24 +296,20 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
                     val = weight * mag;
                 }
             }
-            // ordered accumulation: publish values, group lanes by bin, owners add in lane order
-            s_msk[warp][lane] = 0u;
-            if (lane < 8) s_msk[warp][32 + lane] = 0u;
+            // ordered accumulation: publish values, group lanes by bin; the lowest lane of every group adds the
+            // group's values to the bin in lane order (= the reference's raster order), groups have distinct bins
             s_val[warp][lane] = val;
             __syncwarp();
             const uint32_t grp = __match_any_sync(0xffffffffu, bin);
-            if (bin >= 0 && lane == __ffs(grp) - 1) s_msk[warp][bin] = grp;
-            __syncwarp();
-            uint32_t m0 = s_msk[warp][lane];
-            while (m0) { const int j = __ffs(m0) - 1; m0 &= m0 - 1; acc0 += s_val[warp][j]; }
-            uint32_t m1 = (lane < ORI_BINS - 32) ? s_msk[warp][32 + lane] : 0u;
-            while (m1) { const int j = __ffs(m1) - 1; m1 &= m1 - 1; acc1 += s_val[warp][j]; }
+            if (bin >= 0 && lane == __ffs(grp) - 1) {
+                float hsum = s_raw[warp][bin + 2];
+                uint32_t m = grp;
+                while (m) { const int j = __ffs(m) - 1; m &= m - 1; hsum += s_val[warp][j]; }
+                s_raw[warp][bin + 2] = hsum;
+            }
             __syncwarp();
         }
         // raw_hist with 2-bin circular padding, src/lib.rs:742-749
-        s_raw[warp][lane + 2] = acc0;
-        if (lane < ORI_BINS - 32) s_raw[warp][32 + lane + 2] = acc1;
-        __syncwarp();
         if (lane == 0) {
             s_raw[warp][1] = s_raw[warp][ORI_BINS + 1];
             s_raw[warp][0] = s_raw[warp][ORI_BINS];
