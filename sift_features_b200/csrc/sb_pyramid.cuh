@@ -260,17 +260,24 @@ struct UpsampleParams {
     int pitch;
 };
 
+constexpr int UPS_ROWS = 8;   // input row pairs per CTA (amortises the table set-up and the CTA launch)
+
 __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
     // v / 255 for the 256 possible pixel values (the IEEE division itself, done once per CTA instead of 8x per thread)
     __shared__ float s_norm[256];
     s_norm[threadIdx.x] = (float)threadIdx.x / 255.0f;
     __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;      // output columns 4k .. 4k+3
-    const int y = (int)blockIdx.y - 1;                        // input row pair (y, y+1); y = -1 yields output row 0
     const long long img = blockIdx.z;
     const int W = p.in_w, H = p.in_h;
     if (4 * k >= 2 * W) return;
     const uint8_t* in = p.in + img * p.in_img_stride;
+    float* dst = p.dst + img * p.img_stride;
+    const bool full = (4 * k + 3) < 2 * W;
+#pragma unroll 2
+  for (int yy = 0; yy < UPS_ROWS; yy++) {
+    const int y = (int)blockIdx.y * UPS_ROWS + yy - 1;        // input row pair (y, y+1); y = -1 yields output row 0
+    if (y >= H) break;
     const int y0 = max(y, 0), y1 = min(y + 1, H - 1);
     float a[2][4];
 #pragma unroll
@@ -290,8 +297,6 @@ __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
     }
     // the reference clamps the source index and zeroes the weight at the borders (column 0 and 2W-1)
     if (k == 0) { hrow[0][0] = a[0][1]; hrow[1][0] = a[1][1]; }   // 2k-1 < 0: both taps are column 0
-    float* dst = p.dst + img * p.img_stride;
-    const bool full = (4 * k + 3) < 2 * W;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const int Y = 2 * y + 1 + r;
@@ -304,6 +309,7 @@ __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
         if (full) *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
         else for (int c = 0; c < 4 && 4 * k + c < 2 * W; c++) q[c] = o[c];
     }
+  }
 }
 
 // ---------------------------------------------------------------------------

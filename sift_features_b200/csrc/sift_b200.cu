@@ -627,7 +627,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             u.in_w = (int)w; u.in_h = (int)h; u.in_stride = (int)in_stride;
             u.dst = s.d_gauss + L.o[0].off + 5 * L.o[0].layer_stride;
             u.img_stride = L.img_floats; u.pitch = L.o[0].pitch;
-            dim3 grid((((int)w + 1) / 2 + 255) / 256, h + 1, n);
+            dim3 grid((((int)w + 1) / 2 + 255) / 256, (h + 1 + UPS_ROWS - 1) / UPS_ROWS, n);
             k_upsample2x<<<grid, 256, 0, st>>>(u);
             if (ctx->march) launch_blur_march<0, false>(ctx, st, ctx->tmap_m[s.index][0][0], p, n, 5);
             else launch_blur_tma<0, false>(st, ctx->tmap[s.index][0][0], p, n, 5);
