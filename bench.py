@@ -374,7 +374,7 @@ def run_b200(args, rank, local_rank, world):
                 "extrema_stage": {"algorithmic_bytes_per_image": a_ext, "ms_per_image": stats["extrema"]["ms"] / imgs_rank,
                                   "frac": a_ext * imgs_rank / (stats["extrema"]["ms"] * 1e-3) / 1e9 / peak
                                   if stats["extrema"]["ms"] > 0 else None},
-                "descriptor_stage": {"bound": "issue (ncu: 86 % of SM peak, LSU pipe 52 %)",
+                "descriptor_stage": {"bound": "issue (ncu: 85 % of the SM issue peak, profiles/r01_ncu_full_1080p_b32.txt)",
                                      "ms_per_image": stats["descriptor"]["ms"] / imgs_rank,
                                      "ns_per_keypoint": 1e6 * stats["descriptor"]["ms"] / imgs_rank / max(kp_per_group / B, 1)},
             }
