@@ -344,6 +344,7 @@ def run_b200(args, rank, local_rank, world):
             # dominant kernel: the 27-tap blur of octave 0 (k_blur_march<5>), one launch per group of B images;
             # algorithmic bytes = read 4 B + write 4 B per pixel of the 2W x 2H layer
             top_ms, top_n = stats["top_blur"]["ms"], max(1, stats["top_blur"]["launches"])
+            sm_mhz = (clocks or {}).get("sm_mhz")
             top_bytes = 8.0 * (2 * w) * (2 * h) * B
             ach = top_bytes / (top_ms / top_n * 1e-3) / 1e9 if top_ms > 0 else None
             traffic = None
@@ -363,6 +364,14 @@ def run_b200(args, rank, local_rank, world):
                             "timed steps (one group in flight)",
                 "algorithmic_bytes_per_launch": top_bytes, "avg_launch_us": 1e3 * top_ms / top_n,
                 "note": "54 FMA-pipe ops per pixel at 27 taps: this layer is FP32-issue bound below the HBM roof",
+                # the bound that actually binds this launch: FP32 lane-operations the oracle's arithmetic fixes (27 row-pass
+                # FMAs + 14 FMAs and 13 adds of the folded column pass per pixel, + ~1.4 of normalisation / addressing
+                # measured in SASS = 55.4) against 148 SMs x 128 FP32 lanes at the SM clock sampled during the run
+                "fp32_pipe": {"lane_ops_per_pixel": 55.4,
+                              "achieved_tops": 55.4 * (2 * w) * (2 * h) * B / (top_ms / top_n * 1e-3) / 1e12 if top_ms > 0 else None,
+                              "peak_tops": 148 * 128 * sm_mhz * 1e6 / 1e12 if sm_mhz else None,
+                              "frac": (55.4 * (2 * w) * (2 * h) * B / (top_ms / top_n * 1e-3)) /
+                                      (148 * 128 * sm_mhz * 1e6) if top_ms > 0 and sm_mhz else None},
                 "blur_stage": {"algorithmic_bytes_per_image": a_blur, "ms_per_image": blur_ms / imgs_rank,
                                "frac": a_blur * imgs_rank / (blur_ms * 1e-3) / 1e9 / peak if blur_ms > 0 else None},
                 "pyramid_dog": {"algorithmic_bytes_per_image": tot, "ms_per_image": pyr_ms / imgs_rank,
