@@ -677,14 +677,17 @@ __global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM
 #pragma unroll
                     for (int i = 0; i <= 2 * R; i++) {
                         const int sidx = C::XO + 2 * jp + i;
+                        // the kernel is symmetric (tap i == tap 2R - i, bit for bit): naming every tap by its upper-half
+                        // index keeps the set of constants the row and the column pass touch to R + 1 values
+                        const int ti = i < R ? 2 * R - i : i;
                         if ((sidx & 1) == 0) {
                             const float2 in = make_float2(win[sidx], win[sidx + 1]);
-                            acc[jp] = (i == 0) ? mul2(in, c_taps2[L][0]) : fma2(in, c_taps2[L][i], acc[jp]);
+                            acc[jp] = (i == 0) ? mul2(in, c_taps2[L][ti]) : fma2(in, c_taps2[L][ti], acc[jp]);
                         } else if (i == 0) {
-                            acc[jp] = make_float2(win[sidx] * c_taps[L][0], win[sidx + 1] * c_taps[L][0]);
+                            acc[jp] = make_float2(win[sidx] * c_taps[L][ti], win[sidx + 1] * c_taps[L][ti]);
                         } else {
-                            acc[jp].x = fmaf(win[sidx], c_taps[L][i], acc[jp].x);
-                            acc[jp].y = fmaf(win[sidx + 1], c_taps[L][i], acc[jp].y);
+                            acc[jp].x = fmaf(win[sidx], c_taps[L][ti], acc[jp].x);
+                            acc[jp].y = fmaf(win[sidx + 1], c_taps[L][ti], acc[jp].y);
                         }
                     }
                 }
