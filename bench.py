@@ -38,7 +38,7 @@ WORKLOADS = {
     # name: (width, height, images per group (= context max_batch), groups per step)
     "1080p": (1920, 1080, 32, 4),  # BASELINE.json configs[1] shape, batched
     "4k": (3840, 2160, 8, 2),      # configs[2]
-    "vga": (640, 480, 128, 4),      # configs[3] shape (8192 images = 32 such steps)
+    "vga": (640, 480, 128, 4),      # configs[3] shape (8192 images = 16 such steps)
 }
 
 
