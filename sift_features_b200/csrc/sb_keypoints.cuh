@@ -511,8 +511,9 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 //     copy k at word bin*DESC_COPIES + k, so a half-warp's read-modify-writes always hit 16 distinct
 //     banks; lanes l and l+16 share a copy and update it in two phases.  The copies are summed
 //     at the end (f32 sums in a different order than the reference's raster order: the +-1 byte
-//     tolerance of the north star covers it; everything up to the accumulation is the reference's
-//     arithmetic).
+//     tolerance of the north star covers it).  The sample geometry (rotation, bins, cell indices, fractions)
+//     is the reference's f32 arithmetic; magnitude, Gaussian weight and gradient angle use single-instruction
+//     SFU approximations (relative error ~1e-6), far below the u8 quantisation step.
 //   * Window samples that fall outside the rotated 4x4 grid (about half) are never visited: the lanes
 //     compute, in parallel, the column span of every window row that can intersect the grid and a running
 //     sample count (one packed word per non-empty row in shared memory); every lane then walks that table with
@@ -531,7 +532,7 @@ constexpr int DESC_COPIES = SB_DESC_COPIES;
 constexpr int DESC_MAXROWS = 256;  // window rows: 2 * radius + 1 with radius <= 127
 constexpr int DESC_CELL_WORDS = 8 * DESC_COPIES;               // one spatial cell: 8 orientation bins x copies
 constexpr int DESC_HIST_WORDS = 16 * DESC_CELL_WORDS;          // the 4x4 cells the crop at :951 keeps
-// per warp: histogram copies, row table (running count u16[256], first column u8[256])
+// per warp: histogram copies, row table u16[256] = (span length << 8) | first column  (+ 64 words of slack)
 constexpr int DESC_SMEM_WORDS = DESC_HIST_WORDS + DESC_MAXROWS / 2 + DESC_MAXROWS / 4;
 constexpr size_t DESC_SMEM_BYTES = 256 + (size_t)DESC_WARPS * DESC_SMEM_WORDS * sizeof(float);
 
