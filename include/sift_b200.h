@@ -223,6 +223,12 @@ int sb200_set_profiling(sb200_ctx* ctx, int on);
 /* accumulated device milliseconds and kernel launches per stage since the last reset */
 int sb200_stage_stats(sb200_ctx* ctx, double* ms, uint64_t* launches, uint32_t cap);
 int sb200_reset_stats(sb200_ctx* ctx);
+/* per-launch view of the pyramid stages, accumulated like the stage stats while profiling is on: slot
+ * octave * 8 + k, where k = 0 is the 2x upsample + seed blur (octave 0 only), k = 1..5 the blur that writes
+ * Gaussian layer k, k = 6 the DoG/extrema scan of the octave and k = 7 the fused launch for all the small
+ * octaves (filed under the first octave it covers). */
+#define SB200_FINE_SLOTS (SB200_MAX_OCTAVES * 8)
+int sb200_launch_stats(sb200_ctx* ctx, double* ms, uint64_t* launches, uint32_t cap);
 /* total kernel launches issued by this context since creation */
 uint64_t sb200_launch_count(const sb200_ctx* ctx);
 const char* sb200_stage_name(uint32_t stage);

@@ -334,6 +334,16 @@ class Extractor:
     def reset_stats(self):
         self._check(self._lib.sb200_reset_stats(self._h))
 
+    def launch_stats(self):
+        """Per-launch view of the pyramid stages while profiling is on: {(octave, kind): (ms, launches)} with kind in
+        "seed", "blur1".."blur5", "extrema", "tail" (sb200_launch_stats)."""
+        n = _ffi.FINE_SLOTS
+        ms = (C.c_double * n)()
+        ln = (C.c_uint64 * n)()
+        self._check(self._lib.sb200_launch_stats(self._h, ms, ln, n))
+        kinds = ("seed", "blur1", "blur2", "blur3", "blur4", "blur5", "extrema", "tail")
+        return {(i // 8, kinds[i % 8]): (ms[i], int(ln[i])) for i in range(n) if ln[i]}
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.sb200_launch_count(self._h))

@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("SB200_LIB") or os.path.join(_HERE, "libsift_b200.so")
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_STATE = 0, 1, 2, 3, 4
 DESC_SIZE = 128
 STAGE_COUNT = 7
+FINE_SLOTS = 128
 
 # every symbol include/sift_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -25,7 +26,7 @@ SYMBOLS = [
     "sb200_precompute", "sb200_extract_precomputed", "sb200_pyramid_info", "sb200_pyramid_layer",
     "sb200_pyramid_dog", "sb200_last_candidates", "sb200_last_sift_keypoints", "sb200_compute_descriptors",
     "sb200_compute_descriptors_device", "sb200_extract_batch_multi", "sb200_set_profiling", "sb200_stage_stats",
-    "sb200_reset_stats", "sb200_launch_count", "sb200_stage_name", "sb200_algorithmic_bytes", "sb200_timer_start",
+    "sb200_reset_stats", "sb200_launch_stats", "sb200_launch_count", "sb200_stage_name", "sb200_algorithmic_bytes", "sb200_timer_start",
     "sb200_timer_stop", "sb200_timer_elapsed_ms", "sb200_host_alloc", "sb200_host_free", "sb200_device_alloc",
     "sb200_device_free", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_flush_l2", "sb200_match_descriptors", "sb200_match_descriptors_device",
     "sb200_extract_batch_rgb", "sb200_rgb_to_luma", "sb200_extract_batch_jpeg", "sb200_jpeg_info", "sb200_decode_jpeg_luma",
@@ -84,6 +85,7 @@ def load() -> C.CDLL:
         "sb200_set_profiling": (C.c_int, [vp, C.c_int]),
         "sb200_stage_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(u64), u32]),
         "sb200_reset_stats": (C.c_int, [vp]),
+        "sb200_launch_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(u64), u32]),
         "sb200_launch_count": (u64, [vp]),
         "sb200_stage_name": (C.c_char_p, [u32]),
         "sb200_algorithmic_bytes": (u64, [u32, u32, C.POINTER(u64), u32]),

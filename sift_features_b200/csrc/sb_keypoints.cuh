@@ -507,9 +507,12 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 // One warp per keypoint.
 //   * Only the inner 4x4 cells of the reference's (6,6,8) histogram survive the crop at :951, so
 //     only those 128 bins are accumulated.
-//   * No atomics: the warp keeps DESC_COPIES lane-private copies of the 128 bins in shared memory,
+//   * No atomics: the warp keeps DESC_COPIES = 16 lane-private copies of the 128 bins in shared memory,
 //     copy k at word bin*DESC_COPIES + k, so a half-warp's read-modify-writes always hit 16 distinct
-//     banks; lanes l and l+16 share a copy and update it in two phases.  The copies are summed
+//     banks.  Lanes l and l+16 share a copy WITHOUT ever touching the same word in the same instruction:
+//     a sample feeds two adjacent orientation bins, one even and one odd; the lower half-warp adds its
+//     even-bin parts first and its odd-bin parts second, the upper half-warp the other way round, so all 32
+//     lanes are active in all eight read-modify-writes of a sample.  The copies are summed
 //     at the end (f32 sums in a different order than the reference's raster order: the +-1 byte
 //     tolerance of the north star covers it).  The sample geometry (rotation, bins, cell indices, fractions)
 //     is the reference's f32 arithmetic; magnitude, Gaussian weight and gradient angle use single-instruction
@@ -527,9 +530,13 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 #ifndef SB_DESC_COPIES
 #define SB_DESC_COPIES 16
 #endif
+#ifndef SB_DESC_EXACT_GEOM
+#define SB_DESC_EXACT_GEOM 0
+#endif
 constexpr int DESC_WARPS = SB_DESC_WARPS;
 constexpr int DESC_COPIES = SB_DESC_COPIES;
-constexpr int DESC_MAXROWS = 256;  // window rows: 2 * radius + 1 with radius <= 127
+constexpr int DESC_MAXROWS = 256;  // window rows: 2 * radius + 1 with radius <= 127 (+ the sentinel entry)
+static_assert(DESC_COPIES == 16, "the parity-split scatter pairs lanes l and l + 16 on one copy");
 constexpr int DESC_CELL_WORDS = 8 * DESC_COPIES;               // one spatial cell: 8 orientation bins x copies
 constexpr int DESC_HIST_WORDS = 16 * DESC_CELL_WORDS;          // the 4x4 cells the crop at :951 keeps
 // per warp: histogram copies, row table u16[256] = (span length << 8) | first column  (+ 64 words of slack)
@@ -547,6 +554,7 @@ struct DescGeom {
     int w, h, pitch, x, y, radius;
     float sin_s, cos_s, orientation;
     float ori_bins;   // orientation in histogram bins (8 per turn)
+    float wscale;     // -(1/8) log2(e) / hist_width^2: exponent of the Gaussian weight per squared window distance
 };
 
 // single-instruction SFU approximations (flush-to-zero: no denormal rescaling sequences around the MUFU)
@@ -561,10 +569,10 @@ __device__ __forceinline__ float ex2_approx(const float x) { float r; asm("ex2.a
 __device__ __forceinline__ float fast_atan2_bins(const float y, const float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    // the flush-to-zero reciprocal needs a normal operand: gradients deep inside constant regions are denormal.
-    // Scaling numerator and denominator by 2^64 is exact and makes every nonzero gradient normal (|gradient| <= 1, so
-    // nothing overflows); the floor keeps the reciprocal finite at 0 / 0, where the quotient is then 0 * finite = 0
-    const float a = (mn * 0x1p64f) * rcp_approx(fmaxf(mx * 0x1p64f, 1e-30f));
+    // the floor keeps the flush-to-zero reciprocal finite at 0 / 0 (quotient 0 * finite = 0) and for denormal gradients
+    // (deep inside constant regions), whose direction is then arbitrary -- their magnitude, < 1e-30 against the
+    // >= 1e-3 of any keypoint's neighbourhood, cannot move a descriptor byte
+    const float a = mn * rcp_approx(fmaxf(mx, 1e-30f));
     const float s = a * a;
     float p = 0x1.1c32bcp-7f;
     p = fmaf(p, s, -0x1.5e8130p-5f);
@@ -585,9 +593,10 @@ struct DescPix { float xp, xm, ym, yp; };  // I[y][x+1], I[y][x-1], I[y-1][x], I
 
 struct DescAt { int yw, xw; };              // window coordinates of a lane's sample (relative to the keypoint pixel)
 
-// A lane without a sample is parked on the window corner (-radius, -radius): its rotated coordinates are >= 3.4
-// cells from the centre in one direction, outside the 4x4 grid, so nothing of it is accumulated whatever pixels it
-// carries -- it loads the keypoint's own pixel neighbourhood (always inside the image) instead of branching.
+// A lane without a sample is parked in the row table's sentinel entry: window columns >= 255 - radius, which are
+// outside the rotated 4x4 grid for every orientation (|column| > radius = 2.5 sqrt(2) cells), so nothing of it is
+// accumulated whatever pixels it carries -- it loads the keypoint's own pixel neighbourhood (always inside the image)
+// instead of branching.
 __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const DescAt at, const bool active) {
     const int i = active ? (G.y + at.yw) * G.pitch + (G.x + at.xw)   // a layer holds < 2^31 floats: 32-bit offsets
                          : G.y * G.pitch + G.x;
@@ -608,73 +617,92 @@ __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const Des
 // offsets from one base address per orientation bin.
 __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const DescAt at, const DescPix px, float* hist,
                                                   const int lane) {
-    // geometry: the reference's f32 operations, so the membership test, cell indices and fractions are its values
+    // geometry (src/lib.rs:818-833): row_bin - 0.5 and col_bin - 0.5 of the rotated, scaled sample position.
+    // SB_DESC_EXACT_GEOM = 1 keeps the reference's operation sequence (mul, mul, add, + 2, - 0.5); the default
+    // contracts it into two FMAs per coordinate (results within one rounding of the reference's; the trilinear
+    // weights are continuous across cell boundaries, so a sample that lands an ulp on the other side of one moves
+    // 1e-7 of its magnitude between two cells).
     const int yw = at.yw, xw = at.xw;
     const float fx = (float)xw, fy = (float)yw;
+#if SB_DESC_EXACT_GEOM
     const float col_rot = fx * G.cos_s - fy * G.sin_s;
     const float row_rot = fx * G.sin_s + fy * G.cos_s;
-    const float row_bin = row_rot + 2.0f, col_bin = col_rot + 2.0f;
+    const float rb = (row_rot + 2.0f) - 0.5f, cbn = (col_rot + 2.0f) - 0.5f;
+    const float wexp = fmaf(col_rot, col_rot, row_rot * row_rot) * (-0.125f * 1.44269504088896341f);   // exp(-2/4^2 * ..), :859
+#else
+    const float rb = fmaf(fx, G.sin_s, fmaf(fy, G.cos_s, 1.5f));
+    const float cbn = fmaf(fx, G.cos_s, fmaf(fy, -G.sin_s, 1.5f));
+    const float wexp = fmaf(fx, fx, fy * fy) * G.wscale;   // |rotated position|^2 = (x^2 + y^2) / hist_width^2
+#endif
     // The membership test of src/lib.rs:834-837, -0.5 < row_bin, col_bin < 4.5, needs no instruction of its own:
     // it holds exactly when floor(row_bin - 0.5) and floor(col_bin - 0.5) lie in -1..3 (at the one value where the
     // two differ, row_bin == -0.5, the sample's share of every kept cell is c1 = mag * 0 = +0), and a sample whose
     // floors are outside that range has no valid cell below, so none of it is accumulated -- which is also what
-    // happens to lanes without a sample (parked on the window corner).  (The image-bounds half of the test,
+    // happens to lanes without a sample (parked in the sentinel row).  (The image-bounds half of the test,
     // :838-841, is enforced by the span construction.)
-    const float rb = row_bin - 0.5f, cbn = col_bin - 0.5f;
     const float dx = px.xp - px.xm;
     const float dy = px.ym - px.yp;
     // magnitude, Gaussian weight and angle: fast approximations (relative error ~1e-6), see header comment
     const float d2 = fmaf(dx, dx, dy * dy);
-    const float wgt = fmaf(col_rot, col_rot, row_rot * row_rot);
-    // sqrt(d2) = d2 * rsqrt(d2) = d2 * (rsqrt(d2 * 2^64) * 2^32): the scaling (exact) gives the flush-to-zero rsqrt a
-    // normal operand for every nonzero d2, denormal ones (constant image regions) included; the floor keeps it
-    // finite at d2 = 0, where the product is 0
-    const float root = d2 * (rsqrt_approx(fmaxf(d2 * 0x1p64f, 1e-30f)) * 0x1p32f);
-    const float mag = root * ex2_approx(wgt * (-0.125f * 1.44269504088896341f));  // exp(-2/4^2 * wgt), :859
+    // sqrt(d2) = d2 * rsqrt(d2); the floor keeps the flush-to-zero rsqrt finite at d2 = 0 (product 0) and for
+    // gradients below 1e-18, which weigh nothing next to a keypoint's neighbourhood
+    const float root = d2 * rsqrt_approx(fmaxf(d2, 1e-36f));
+    const float mag = root * ex2_approx(wexp);
     const float obin = fast_atan2_bins(dy, dx) - G.ori_bins;                       // :871, in bins; in [-8, 8]
     const float row_floor = floorf(rb), col_floor = floorf(cbn), ori_floor = floorf(obin);
     const float row_frac = rb - row_floor, col_frac = cbn - col_floor, ori_frac = obin - ori_floor;
-    // trilinear split exactly as src/lib.rs:906-919
-    float cv[8];
+    // spatial half of the trilinear split exactly as src/lib.rs:906-913
     const float c1 = mag * row_frac, c0 = mag - c1;
-    const float c11 = c1 * col_frac, c10 = c1 - c11;
-    const float c01 = c0 * col_frac, c00 = c0 - c01;
-    cv[7] = c11 * ori_frac; cv[6] = c11 - cv[7];   // c111, c110
-    cv[5] = c10 * ori_frac; cv[4] = c10 - cv[5];   // c101, c100
-    cv[3] = c01 * ori_frac; cv[2] = c01 - cv[3];   // c011, c010
-    cv[1] = c00 * ori_frac; cv[0] = c00 - cv[1];   // c001, c000
+    float sp[4];                                    // cells (r1, q1), (r1, q1+1), (r1+1, q1), (r1+1, q1+1)
+    sp[3] = c1 * col_frac; sp[2] = c1 - sp[3];      // c11, c10
+    sp[1] = c0 * col_frac; sp[0] = c0 - sp[1];      // c01, c00
     // the reference adds into cells (row_floor+1 .. +2, col_floor+1 .. +2) of its 6x6 grid and keeps
     // cells 1..4 (:951): in inner-grid terms the first cell is (r1, q1) in -1..3
     const int r1 = (int)row_floor, q1 = (int)col_floor;
-    const int o0 = ((int)ori_floor) & 7;           // ori_floor in [-16, 16): wrap like :926-938
-    const int o1 = (o0 + 1) & 7;
-    const bool r0ok = (unsigned)r1 <= 3u, r1ok = (unsigned)(r1 + 1) <= 3u;
-    const bool q0ok = (unsigned)q1 <= 3u, q1ok = (unsigned)(q1 + 1) <= 3u;
-    const int cell00 = r1 * 4 + q1;
-    // the four spatial cells (k >> 1: bit 0 = column step, bit 1 = row step) sit at constant offsets from cell
-    // (r1, q1); parts that fall outside the 4x4 grid are predicated off (the base may then point outside the
-    // histogram -- it is only dereferenced for cells inside the grid)
-    const bool ok[4] = {r0ok & q0ok, r0ok & q1ok, r1ok & q0ok, r1ok & q1ok};
+    const int oi = (int)ori_floor;                  // in [-16, 16): orientation bins o0 = oi mod 8 and o0 + 1 mod 8 (:926-938)
+    // Orientation half (:914-919): bin o0 gets c - c * ori_frac, bin o0 + 1 gets c * ori_frac.  One of the two bins is
+    // even, the other odd: E = (oi + 1) & 6, O = (oi & 7) | 1.  Lanes 0-15 (hl = 0) add to E first and O second,
+    // lanes 16-31 (hl = 1) to O first and E second, so the two lanes that share a histogram copy never touch the same
+    // word in the same instruction.  The first bin is o0 exactly when hl == (oi & 1); its weight is then 1 - ori_frac
+    // (c * (1 - f) instead of the reference's c - c * f: one rounding apart), else ori_frac (the reference's products).
+    const int hl = lane >> 4;
+    const int oF = ((oi + 1 - hl) & (6 | hl)) | hl;
+    const int oS = ((oi + hl) & (7 - hl)) | (1 - hl);
+    const float wF = ((oi ^ hl) & 1) ? ori_frac : 1.0f - ori_frac;
+    // the four spatial cells sit at constant offsets from cell (r1, q1); parts that fall outside the 4x4 grid are
+    // predicated off (the base may then point outside the histogram -- it is only dereferenced for cells inside).
+    // Cell (r, q) is inside iff both indices are in 0..3, i.e. (r | q) has no bit above bit 1.
+    const int r2 = r1 + 1, q2 = q1 + 1;
+    const bool ok[4] = {((r1 | q1) & ~3) == 0, ((r1 | q2) & ~3) == 0, ((r2 | q1) & ~3) == 0, ((r2 | q2) & ~3) == 0};
     constexpr int CO[4] = {0, DESC_CELL_WORDS, 4 * DESC_CELL_WORDS, 5 * DESC_CELL_WORDS};
-    float* const b0 = hist + (lane & (DESC_COPIES - 1)) + o0 * DESC_COPIES + cell00 * DESC_CELL_WORDS;
-    float* const b1 = b0 + (o1 - o0) * DESC_COPIES;
-    // lanes l and l + DESC_COPIES share a copy: two phases
+    float* const cellb = hist + (lane & (DESC_COPIES - 1)) + (r1 * 4 + q1) * DESC_CELL_WORDS;
+    float* const bF = cellb + oF * DESC_COPIES;
+    float* const bS = cellb + oS * DESC_COPIES;
+    float vF[4], vS[4], old[4];
 #pragma unroll
-    for (int phase = 0; phase < 32 / DESC_COPIES; phase++) {
-        if ((lane / DESC_COPIES) == phase) {
-            float old[8];
+    for (int k = 0; k < 4; k++) { vF[k] = sp[k] * wF; vS[k] = sp[k] - vF[k]; }
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (ok[k >> 1]) old[k] = ((k & 1) ? b1 : b0)[CO[k >> 1]];   // (left unset for parts outside the grid)
+    for (int k = 0; k < 4; k++) if (ok[k]) old[k] = bF[CO[k]];     // (left unset for parts outside the grid)
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (ok[k >> 1]) ((k & 1) ? b1 : b0)[CO[k >> 1]] = old[k] + cv[k];
-        }
-        __syncwarp();
-    }
+    for (int k = 0; k < 4; k++) if (ok[k]) bF[CO[k]] = old[k] + vF[k];
+    __syncwarp();   // the other half-warp's first-bin stores precede this half's second-bin loads
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (ok[k]) old[k] = bS[CO[k]];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (ok[k]) bS[CO[k]] = old[k] + vS[k];
+    __syncwarp();
 }
 
-__device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /* smem [DESC_SMEM_WORDS] */, int lane,
+// Window radius limit of the row table (8-bit spans): scale <= DESC_MAX_SCALE.  The extraction path stays below
+// scale 3.6 (radius 38); compute_descriptor on caller-supplied keypoints reports larger scales as invalid
+// arguments (SB200_E_INVALID) instead of computing something the crate would not.
+constexpr int DESC_MAX_RADIUS = 127;
+__host__ __device__ __forceinline__ int descriptor_radius(const float scale) {
+    return (int)roundf(fminf(3.0f * scale * sqrtf(2.0f) * 5.0f * 0.5f, 1e6f));   // src/lib.rs:800
+}
+
+// returns false (warp-uniform, nothing written) when the keypoint's window exceeds DESC_MAX_RADIUS
+__device__ __forceinline__ bool descriptor_warp(const DescTarget t, float* wsm /* smem [DESC_SMEM_WORDS] */, int lane,
                                                 uint8_t* out /* 128 B */) {
     float* hist = wsm;
     uint16_t* row_tab = reinterpret_cast<uint16_t*>(wsm + DESC_HIST_WORDS);   // [DESC_MAXROWS] (span length << 8) | (xlo + radius)
@@ -692,12 +720,14 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     G.x = xr > 0.f ? (int)fminf(xr, 1e9f) : 0;
     G.y = yr > 0.f ? (int)fminf(yr, 1e9f) : 0;
     const float hist_width = 3.0f * t.scale;
-    G.radius = min((int)roundf(3.0f * t.scale * sqrtf(2.0f) * 5.0f * 0.5f), 127);  // :800 (<= 38 on this path)
+    G.radius = descriptor_radius(t.scale);  // :800 (<= 38 on the extraction path)
+    if (G.radius > DESC_MAX_RADIUS || !(t.scale > 0.f)) return false;
     const float rad = t.orientation * (3.14159265358979323846f / 180.0f);            // f32::to_radians
     double sd, cd;
     sincos((double)rad, &sd, &cd);  // libm sinf/cosf are (nearly always) correctly rounded: round once from f64
     G.sin_s = (float)sd / hist_width;
     G.cos_s = (float)cd / hist_width;
+    G.wscale = (-0.125f * 1.44269504088896341f) / (hist_width * hist_width);
     // conservative per-row column range of the rotated 5x5-cell square: x*k + t in (-2.5, 2.5)
     const float inv_s = fabsf(G.sin_s) > 1e-7f ? 1.0f / G.sin_s : 0.f;
     const float inv_c = fabsf(G.cos_s) > 1e-7f ? 1.0f / G.cos_s : 0.f;
@@ -743,22 +773,24 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
         n_rows += __popc(ne);
         total += __shfl_sync(0xffffffffu, incl, 31);
     }
+    // sentinel behind the last row: a span no cursor can leave, whose columns (>= 255 - radius > radius) lie outside
+    // the rotated grid for every orientation -- a lane that has run out of samples parks there and accumulates nothing
+    if (lane == 0) row_tab[n_rows] = 0xffffu;
     __syncwarp();
     // ---- samples, 32 at a time: every lane walks the table with its own cursor (row k, offset xo in the row),
     //      32 samples forward per batch -- one or two short rows at most, no search ----
-    uint32_t cur_k = 0, cur_xo = lane, cur_w = n_rows ? row_tab[0] : 0u;
+    uint32_t cur_k = 0, cur_xo = lane, cur_w = row_tab[0];
     const int y_first_w = (int)yq_first - G.radius;
     auto lookup = [&](const uint32_t advance, DescAt& at) -> bool {
         cur_xo += advance;
-        while (cur_k < n_rows && cur_xo >= (cur_w >> 8)) {
+        while (cur_xo >= (cur_w >> 8)) {
             cur_xo -= cur_w >> 8;
             cur_k++;
-            cur_w = cur_k < n_rows ? row_tab[cur_k] : 0u;
+            cur_w = row_tab[cur_k];
         }
-        const bool active = cur_k < n_rows;
-        at.yw = active ? y_first_w + (int)cur_k : -G.radius;
-        at.xw = active ? (int)((cur_w & 255u) + cur_xo) - G.radius : -G.radius;
-        return active;
+        at.yw = y_first_w + (int)cur_k;
+        at.xw = (int)((cur_w & 255u) + cur_xo) - G.radius;
+        return cur_k < n_rows;
     };
     if (total) {
         DescAt at_next;
@@ -815,6 +847,7 @@ __device__ __forceinline__ void descriptor_warp(const DescTarget t, float* wsm /
     }
     reinterpret_cast<uint32_t*>(out)[lane] = packed;
     __syncwarp();
+    return true;
 }
 
 struct DescParams {
@@ -922,7 +955,8 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams
 struct DescIn { float x, y, scale, orientation; };
 __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor_list(const float* __restrict__ img, int w, int h,
                                                                       int pitch, const DescIn* __restrict__ kps,
-                                                                      unsigned long long n, uint8_t* __restrict__ out) {
+                                                                      unsigned long long n, uint8_t* __restrict__ out,
+                                                                      uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char desc_smem[];  // DESC_SMEM_BYTES, dynamic (> 48 KB)
     uint64_t* s_tab = reinterpret_cast<uint64_t*>(desc_smem);
     float (*s_hist)[DESC_SMEM_WORDS] = reinterpret_cast<float (*)[DESC_SMEM_WORDS]>(desc_smem + 256);
@@ -935,7 +969,10 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor_list(const float
         DescTarget t;
         t.img = img; t.w = w; t.h = h; t.pitch = pitch;
         t.x = k.x; t.y = k.y; t.scale = k.scale; t.orientation = k.orientation;
-        descriptor_warp(t, s_hist[warp], lane, out + j * DESC_SIZE);
+        if (!descriptor_warp(t, s_hist[warp], lane, out + j * DESC_SIZE)) {
+            reinterpret_cast<uint32_t*>(out + j * DESC_SIZE)[lane] = 0u;
+            if (lane == 0) atomicOr(err, 1u);   // reported as SB200_E_INVALID by the next synchronising call
+        }
     }
 }
 

@@ -156,6 +156,8 @@ struct sb200_ctx {
     DescIn* d_dkps = nullptr;
     uint8_t* d_ddesc = nullptr;
     size_t dkps_cap = 0;
+    uint32_t* d_err = nullptr;   // device-side argument errors of k_descriptor_list, read by the next synchronising call
+    bool err_pending = false;
     // JPEG input (nvJPEG, loaded on first use): bitstreams are decoded a chunk at a time on their own streams into
     // stage buffers, so that the decode of the next chunks overlaps the extraction of chunk c
     JpegDecoder jpeg;
@@ -176,6 +178,10 @@ struct sb200_ctx {
     std::vector<StageEvents> pending;
     std::vector<cudaEvent_t> ev_pool;
     double stage_ms[SB200_STAGE_COUNT] = {0};
+    // per-launch view of the pyramid stages (profiling mode): slot octave * 8 + k, k = 0 upsample + seed blur,
+    // 1..5 blur of layer k, 6 extrema scan, 7 fused tail (filed under its first octave)
+    double fine_ms[SB200_FINE_SLOTS] = {0};
+    uint64_t fine_launches[SB200_FINE_SLOTS] = {0};
     uint64_t stage_launches[SB200_STAGE_COUNT] = {0};
     uint64_t launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -314,8 +320,10 @@ struct StageScope {
 void drain_stage_events(sb200_ctx* ctx) {
     for (auto& p : ctx->pending) {
         float ms = 0.f;
-        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
-            ctx->stage_ms[p.stage] += ms;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (p.stage < SB200_STAGE_COUNT) ctx->stage_ms[p.stage] += ms;
+            else { ctx->fine_ms[p.stage - SB200_STAGE_COUNT] += ms; ctx->fine_launches[p.stage - SB200_STAGE_COUNT]++; }
+        }
         ctx->ev_pool.push_back(p.a);
         ctx->ev_pool.push_back(p.b);
     }
@@ -613,6 +621,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
     CU(cudaMemsetAsync(s.d_rows, 0, (size_t)L.img_rows * n * sizeof(uint32_t), st));
     {
         StageScope sc(ctx, st, SB200_STAGE_SEED);
+        StageScope fine(ctx, st, SB200_STAGE_COUNT + 0);
         BlurParams p{};
         p.dst = s.d_gauss + L.o[0].off;
         p.img_stride = L.img_floats;
@@ -665,6 +674,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
                 const bool dec = (l == 3) && (o + 1 < L.n_oct) && L.o[o + 1].w >= 1 && L.o[o + 1].h >= 1;
                 // the heaviest single launch gets its own event pair (roofline of the dominant kernel)
                 StageScope top(ctx, st, (o == 0 && l == 5) ? SB200_STAGE_TOP_BLUR : -1);
+                StageScope fine(ctx, st, SB200_STAGE_COUNT + o * 8 + l);
                 if (dec) {
                     p.dec = s.d_gauss + L.o[o + 1].off;
                     p.dec_w = L.o[o + 1].w; p.dec_h = L.o[o + 1].h; p.dec_pitch = L.o[o + 1].pitch;
@@ -711,6 +721,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
         }
         if (ol.scanned) {
             StageScope sc(ctx, st, SB200_STAGE_EXTREMA);
+            StageScope fine(ctx, st, SB200_STAGE_COUNT + o * 8 + 6);
             ExtremaParams e{};
             e.gauss = s.d_gauss + ol.off;
             e.img_stride = L.img_floats;
@@ -729,6 +740,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
     if (o_tail < L.n_oct && L.o[o_tail].w >= 1 && L.o[o_tail].h >= 1) {
         // blurs + decimation + extrema of all the remaining (small) octaves: one CTA per image, one launch
         StageScope sc(ctx, st, SB200_STAGE_BLUR);
+        StageScope fine(ctx, st, SB200_STAGE_COUNT + o_tail * 8 + 7);
         TailParams t{};
         t.L = L; t.o_first = o_tail;
         t.gauss = s.d_gauss; t.mask = s.d_mask; t.rows = s.d_rows;
@@ -1114,6 +1126,16 @@ void fill_result(sb200_ctx* ctx, uint32_t n_images, sb200_result* out) {
 int finish_all(sb200_ctx* ctx) {
     for (auto& s : ctx->slot) CU(cudaStreamSynchronize(s.stream));
     if (ctx->profiling) drain_stage_events(ctx);
+    if (ctx->err_pending) {   // a device-pointer compute_descriptors ran since the last check
+        ctx->err_pending = false;
+        uint32_t e = 0;
+        CU(cudaMemcpy(&e, ctx->d_err, sizeof e, cudaMemcpyDeviceToHost));
+        if (e) {
+            CU(cudaMemset(ctx->d_err, 0, sizeof e));
+            return fail(ctx, SB200_E_INVALID, "compute_descriptors: a keypoint's scale is not in (0, %.1f] (descriptor window "
+                        "radius above %d); its descriptor was zeroed", 12.0, DESC_MAX_RADIUS);
+        }
+    }
     return SB200_OK;
 }
 
@@ -1260,6 +1282,8 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         }
         CU(cudaEventCreate(&ctx->t0));
         CU(cudaEventCreate(&ctx->t1));
+        CU(dalloc(&ctx->d_err, 1));
+        CU(cudaMemset(ctx->d_err, 0, sizeof(uint32_t)));
         return SB200_OK;
     };
     rc = body();
@@ -1288,7 +1312,7 @@ void sb200_destroy(sb200_ctx* ctx) {
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     cudaFreeHost(ctx->h_offsets); cudaFreeHost(ctx->h_kps); cudaFreeHost(ctx->h_desc);
-    cudaFree(ctx->d_dimg); cudaFree(ctx->d_dkps); cudaFree(ctx->d_ddesc); cudaFree(ctx->d_flush);
+    cudaFree(ctx->d_dimg); cudaFree(ctx->d_dkps); cudaFree(ctx->d_ddesc); cudaFree(ctx->d_flush); cudaFree(ctx->d_err);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->d_mdesc[i]); cudaFree(ctx->d_mnorm[i]); cudaFree(ctx->d_mnbp[i]); cudaFree(ctx->d_mbest[i]); }
     cudaFree(ctx->d_mout); cudaFree(ctx->d_mcount);
     delete ctx;
@@ -1741,7 +1765,8 @@ int sb200_compute_descriptors_device(sb200_ctx* ctx, const float* d_img, uint32_
     StageScope sc(ctx, st, SB200_STAGE_DESCRIPTOR);
     const int grid = (int)std::min<uint64_t>((n + DESC_WARPS - 1) / DESC_WARPS, (uint64_t)ctx->sm_count * 16);
     k_descriptor_list<<<grid, 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(d_img, (int)w, (int)h, (int)stride,
-                                                        reinterpret_cast<const DescIn*>(d_kps), n, d_out);
+                                                        reinterpret_cast<const DescIn*>(d_kps), n, d_out, ctx->d_err);
+    ctx->err_pending = true;
     count_launch(ctx, SB200_STAGE_DESCRIPTOR);
     CU(cudaGetLastError());
     return SB200_OK;
@@ -1754,6 +1779,10 @@ int sb200_compute_descriptors(sb200_ctx* ctx, const float* img, uint32_t w, uint
         return fail(ctx, SB200_E_INVALID, "bad arguments to compute_descriptors");
     CU(cudaSetDevice(ctx->device));
     if (n == 0) return SB200_OK;
+    for (uint64_t i = 0; i < n; i++)   // the crate has no limit; the kernel's row table holds windows of radius <= 127
+        if (!(kps[i].scale > 0.f) || descriptor_radius(kps[i].scale) > DESC_MAX_RADIUS)
+            return fail(ctx, SB200_E_INVALID, "compute_descriptors: keypoint %llu has scale %g, supported range is (0, 12.0] "
+                        "(descriptor window radius <= %d)", (unsigned long long)i, (double)kps[i].scale, DESC_MAX_RADIUS);
     cudaStream_t st = ctx->slot[0].stream;
     const size_t px = (size_t)w * h;
     if (px > ctx->dimg_cap) {
@@ -1966,7 +1995,21 @@ int sb200_reset_stats(sb200_ctx* ctx) {
     int rc = finish_all(ctx);
     drain_stage_events(ctx);
     for (int i = 0; i < SB200_STAGE_COUNT; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
+    for (int i = 0; i < SB200_FINE_SLOTS; i++) { ctx->fine_ms[i] = 0; ctx->fine_launches[i] = 0; }
     return rc;
+}
+
+int sb200_launch_stats(sb200_ctx* ctx, double* ms, uint64_t* launches, uint32_t cap) {
+    if (!ctx) return SB200_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = finish_all(ctx);
+    if (rc) return rc;
+    drain_stage_events(ctx);
+    for (uint32_t i = 0; i < cap && i < SB200_FINE_SLOTS; i++) {
+        if (ms) ms[i] = ctx->fine_ms[i];
+        if (launches) launches[i] = ctx->fine_launches[i];
+    }
+    return SB200_OK;
 }
 
 uint64_t sb200_launch_count(const sb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
