@@ -201,12 +201,23 @@ int sb200_match_descriptors_device(sb200_ctx* ctx, const uint8_t* d_query, uint6
                        uint64_t n_train, sb200_dmatch* out, uint64_t cap, uint64_t* n_out);
 
 /* ---- multi-GPU: contiguous shards of a batch over several contexts ------
- * One host thread per context; image i goes to context i / ceil(n/n_ctx); the
- * per-device results are concatenated in image order on the host (no
- * device-to-device traffic).  out's pointers are owned by ctxs[0]. */
+ * One host thread per context; image i goes to context i / ceil(n/n_ctx).  No device-to-device traffic and no
+ * collective: images are independent.
+ *
+ * sb200_extract_batch_multi_parts is the zero-copy form: parts[d] (n_ctx entries) receives context d's own
+ * result for its shard -- offsets local to the part, pointers owned by ctxs[d] -- and first_image[d] (n_ctx + 1
+ * entries, may be NULL) the index of the part's first image, so image i of part d is image first_image[d] + i of
+ * the batch.  The parts in order ARE the batch in image order; nothing is copied on the host.
+ *
+ * sb200_extract_batch_multi additionally concatenates the parts into one dense result owned by ctxs[0] (a
+ * multi-threaded host copy whose duration sb200_last_gather_ms reports). */
+int sb200_extract_batch_multi_parts(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* gray, uint32_t n,
+                                    uint32_t w, uint32_t h, uint32_t stride, uint64_t image_stride,
+                                    int64_t features_limit, sb200_result* parts, uint64_t* first_image);
 int sb200_extract_batch_multi(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* gray, uint32_t n,
                               uint32_t w, uint32_t h, uint32_t stride, uint64_t image_stride,
                               int64_t features_limit, sb200_result* out);
+double sb200_last_gather_ms(const sb200_ctx* ctx);
 
 /* ---- measurement hooks -------------------------------------------------- */
 #define SB200_STAGE_SEED 0        /* u8 -> 2x upsample -> seed blur          (src/lib.rs:196-210) */

@@ -121,6 +121,7 @@ class Extractor:
         self.device, self.max_width, self.max_height, self.max_batch = device, max_width, max_height, max_batch
         self.max_keypoints_per_image = max_keypoints_per_image or max(16384, max_width * max_height // 8)
         self.auto_grow = max_keypoints_per_image == 0   # an explicit capacity is a hard limit
+        self._generation = 0   # bumped by every call that replaces the pyramid resident in the context
 
     def _grow(self) -> bool:
         """Rebuilds the context with 4x the per-image candidate/keypoint capacity (bounded by the number of
@@ -139,6 +140,7 @@ class Extractor:
         return True
 
     def _retry_capacity(self, call):
+        self._generation += 1
         while True:
             st = call()
             if st == _ffi.E_CAPACITY and self._grow():
@@ -268,11 +270,15 @@ class Extractor:
     def precompute_images(self, img) -> "PrecomputedImages":
         """precompute_images::<OpenCVProcessing> (src/lib.rs:131-143); the pyramid stays on the device."""
         a = _as_gray(img)
+        self._generation += 1
         self._check(self._lib.sb200_precompute(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0]))
         return PrecomputedImages(self)
 
-    def sift_with_precomputed(self, features_limit: Optional[int] = None) -> SiftResult:
-        """sift_with_precomputed (src/lib.rs:147-177) on the resident pyramid."""
+    def sift_with_precomputed(self, features_limit: Optional[int] = None, pre: "Optional[PrecomputedImages]" = None) -> SiftResult:
+        """sift_with_precomputed (src/lib.rs:147-177) on the resident pyramid.  `pre`, when given, must still be the
+        pyramid resident in this context (a later sift / precompute call on the same context replaces it)."""
+        if pre is not None:
+            pre._check_resident()
         res = _ffi.Result()
         self._check(self._lib.sb200_extract_precomputed(
             self._h, -1 if features_limit is None else int(features_limit), C.byref(res)))
@@ -354,21 +360,24 @@ class PrecomputedImages:
     octave o.  The data lives on the device; indexing downloads the requested octave."""
 
     class _Stack:
-        def __init__(self, ex: Extractor, dims, layers, fn):
-            self._ex, self._dims, self._layers, self._fn = ex, dims, layers, fn
+        def __init__(self, pre, ex: Extractor, dims, layers, fn):
+            self._pre, self._ex, self._dims, self._layers, self._fn = pre, ex, dims, layers, fn
 
         def __len__(self):
             return len(self._dims)
 
         def __getitem__(self, o: int) -> np.ndarray:
+            self._pre._check_resident()
             w, h = self._dims[o]
             out = np.zeros((self._layers, h, w), np.float32)
             for l in range(self._layers):
                 self._ex._check(self._fn(self._ex.handle, o, l, out[l].ctypes.data))
             return out
 
-    def __init__(self, ex: Extractor):
+    def __init__(self, ex: Extractor, owns_extractor: bool = False):
         lib = ex._lib
+        self._generation = ex._generation
+        self._owns = owns_extractor
         n = C.c_uint32()
         ws = (C.c_uint32 * 16)()
         hs = (C.c_uint32 * 16)()
@@ -376,23 +385,48 @@ class PrecomputedImages:
         self.extractor = ex
         self.n_octaves = int(n.value)
         self.dims = [(int(ws[o]), int(hs[o])) for o in range(self.n_octaves)]
-        self.scale_space = PrecomputedImages._Stack(ex, self.dims, 6, lib.sb200_pyramid_layer)
-        self.dog = PrecomputedImages._Stack(ex, self.dims, 5, lib.sb200_pyramid_dog)
+        self.scale_space = PrecomputedImages._Stack(self, ex, self.dims, 6, lib.sb200_pyramid_layer)
+        self.dog = PrecomputedImages._Stack(self, ex, self.dims, 5, lib.sb200_pyramid_dog)
+
+    def _check_resident(self):
+        """In the crate PrecomputedImages is an owned value; here it is a view of the pyramid resident in a context.
+        A later call on the same context replaces that pyramid -- using the stale view is an error, not another
+        image's results."""
+        if self.extractor._generation != self._generation:
+            raise SiftError(_ffi.E_STATE, "this PrecomputedImages is stale: a later call on its Extractor replaced the "
+                            "resident pyramid (precompute_images() at module level gives every result its own context)")
+
+    def close(self):
+        if self._owns:
+            self.extractor.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------
 # module-level functions with the crate's names; contexts are cached per shape
 # ---------------------------------------------------------------------------
 _cache: dict = {}
+_CACHE_MAX = 8   # contexts hold device arenas: keep only a few alive
 
 
-def _extractor(w: int, h: int, batch: int = 1, device: int = 0) -> Extractor:
+def _extractor(w: int, h: int, batch: int = 1, device: int = 0, keep=()) -> Extractor:
+    """Context for (device, shape, batch) from a small LRU cache.  `keep`: keys the current call still uses -- they are
+    never evicted (a call that shards over more devices than the cache normally holds grows it for its duration)."""
     key = (device, w, h, batch)
-    ex = _cache.get(key)
+    ex = _cache.pop(key, None)
     if ex is None:
-        if len(_cache) >= 4:  # contexts hold device arenas: keep only a few alive
-            _cache.pop(next(iter(_cache))).close()
-        ex = _cache[key] = Extractor(w, h, batch, device)
+        while len(_cache) >= _CACHE_MAX:
+            victim = next((k for k in _cache if k not in keep), None)
+            if victim is None:
+                break
+            _cache.pop(victim).close()
+        ex = Extractor(w, h, batch, device)
+    _cache[key] = ex   # most recently used last
     return ex
 
 
@@ -412,14 +446,19 @@ def sift_with_processing(img, features_limit: Optional[int] = None, processing=O
 
 
 def precompute_images(img, device: int = 0) -> PrecomputedImages:
-    """src/lib.rs:131."""
+    """src/lib.rs:131.  The crate returns an owned value; so does this: the result holds its own context (never shared
+    with the module-level cache), released when the result is dropped."""
     a = _as_gray(img)
-    return _extractor(a.shape[1], a.shape[0], 1, device).precompute_images(a)
+    ex = Extractor(a.shape[1], a.shape[0], 1, device)
+    a = _as_gray(img)
+    ex._generation += 1
+    ex._check(ex._lib.sb200_precompute(ex.handle, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0]))
+    return PrecomputedImages(ex, owns_extractor=True)
 
 
 def sift_with_precomputed(pre: PrecomputedImages, features_limit: Optional[int] = None) -> SiftResult:
     """src/lib.rs:147."""
-    return pre.extractor.sift_with_precomputed(features_limit)
+    return pre.extractor.sift_with_precomputed(features_limit, pre)
 
 
 def match(query_descriptors, train_descriptors, device: int = 0) -> np.ndarray:
@@ -438,29 +477,47 @@ def compute_descriptor(img_f32, x: float, y: float, scale: float, orientation: f
 
 
 def sift_batch(images, features_limit: Optional[int] = None, devices: Optional[Sequence[int]] = None,
-               max_batch: int = 16) -> List[SiftResult]:
+               max_batch: int = 16, dense: bool = False) -> List[SiftResult]:
     """n same-sized images -> one SiftResult per image.  With several devices the batch is split into
-    contiguous shards, one host thread per device, results gathered in image order on the host
-    (sb200_extract_batch_multi; no device-to-device traffic)."""
+    contiguous shards, one host thread per device (no device-to-device traffic, no collective).  The per-image
+    results are cut out of each device's own result arrays (sb200_extract_batch_multi_parts: nothing is gathered
+    on the host); dense=True goes through sb200_extract_batch_multi, which first concatenates the parts into one
+    dense array."""
     a = np.asarray(images)
     if a.dtype != np.uint8 or a.ndim != 3:
         raise ValueError("expected an (n, H, W) uint8 array")
     a = np.ascontiguousarray(a)
     devices = list(devices) if devices else [0]
     n, h, w = a.shape
-    exs = [_extractor(w, h, max(1, min(max_batch, n)), d) for d in devices]
+    b = max(1, min(max_batch, n))
+    keys = {(d, w, h, b) for d in devices}
+    exs = [_extractor(w, h, b, d, keep=keys) for d in devices]
     lib = _ffi.load()
+    lim = -1 if features_limit is None else int(features_limit)
     if len(exs) == 1:
         offs, kp, de = exs[0].sift_batch(a, features_limit)
-    else:
-        handles = (C.c_void_p * len(exs))(*[e.handle for e in exs])
+        return [SiftResult(kp[offs[i]:offs[i + 1]], de[offs[i]:offs[i + 1]]) for i in range(n)]
+    handles = (C.c_void_p * len(exs))(*[e.handle for e in exs])
+    for e in exs:
+        e._generation += 1
+    if dense:
         res = _ffi.Result()
-        exs[0]._check(lib.sb200_extract_batch_multi(handles, len(exs), a.ctypes.data, n, w, h, a.strides[1],
-                                                    a.strides[0],
-                                                    -1 if features_limit is None else int(features_limit),
-                                                    C.byref(res)))
+        exs[0]._check(lib.sb200_extract_batch_multi(handles, len(exs), a.ctypes.data, n, w, h, a.strides[1], a.strides[0],
+                                                    lim, C.byref(res)))
         offs, kp, de = exs[0]._take(res)
-    return [SiftResult(kp[offs[i]:offs[i + 1]], de[offs[i]:offs[i + 1]]) for i in range(n)]
+        return [SiftResult(kp[offs[i]:offs[i + 1]], de[offs[i]:offs[i + 1]]) for i in range(n)]
+    parts = (_ffi.Result * len(exs))()
+    first = (C.c_uint64 * (len(exs) + 1))()
+    exs[0]._check(lib.sb200_extract_batch_multi_parts(handles, len(exs), a.ctypes.data, n, w, h, a.strides[1],
+                                                      a.strides[0], lim, parts, first))
+    out: List[SiftResult] = []
+    for d, e in enumerate(exs):
+        if parts[d].n_images == 0:
+            continue
+        assert len(out) == first[d]
+        offs, kp, de = e._take(parts[d])
+        out += [SiftResult(kp[offs[i]:offs[i + 1]], de[offs[i]:offs[i + 1]]) for i in range(int(parts[d].n_images))]
+    return out
 
 
 def shard_ranges(n: int, parts: int) -> List[range]:

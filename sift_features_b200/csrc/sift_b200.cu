@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -50,6 +52,7 @@ struct Slot {
     cudaEvent_t ev_fork = nullptr;     // already builds the next octave (which only needs layer 3)
     cudaEvent_t ev_join = nullptr;
     cudaEvent_t ev_counts = nullptr;
+    cudaEvent_t ev_upload = nullptr;   // the last host->device copy out of the slot's pinned staging buffer
     // input
     uint8_t* d_in = nullptr;
     uint8_t* h_in = nullptr;  // pinned staging for pageable callers
@@ -95,8 +98,10 @@ struct Slot {
 #define SB_JPEG_AHEAD 3
 #endif
 constexpr int JPEG_AHEAD = SB_JPEG_AHEAD;
-constexpr int JPEG_STREAMS = JPEG_AHEAD;
 constexpr int JPEG_STAGES = JPEG_AHEAD + 1;
+// one decode stream per stage buffer: stage buffer, nvJPEG state ("lane") and stream of chunk c are all c % JPEG_STAGES,
+// so an nvJPEG state is only ever used on one stream
+constexpr int JPEG_STREAMS = JPEG_STAGES;
 
 // stage buffer of the JPEG entry points: decoded pixels (Y or interleaved RGB) of one chunk of bitstreams
 struct JpegStage {
@@ -144,6 +149,7 @@ struct sb200_ctx {
     uint8_t* h_desc = nullptr;
     size_t res_cap = 0;
     uint64_t res_n = 0;
+    double last_gather_ms = 0.0;   // host time of the dense gather of the last sb200_extract_batch_multi
     // staged API state
     bool have_pyramid = false;
     bool have_single = false;  // slot[0] holds the intermediates of a single-image run
@@ -169,7 +175,8 @@ struct sb200_ctx {
     uint32_t* d_mnorm[2] = {nullptr, nullptr};
     uint32_t* d_mnbp[2] = {nullptr, nullptr};
     unsigned long long* d_mbest[2] = {nullptr, nullptr};
-    size_t m_cap[2] = {0, 0};
+    size_t m_cap[2] = {0, 0};       // rows d_mnorm / d_mnbp / d_mbest are sized for
+    size_t mdesc_cap[2] = {0, 0};   // rows d_mdesc is sized for (only the host entry point uses it)
     MatchOut* d_mout = nullptr;
     size_t mout_cap = 0;
     uint32_t* d_mcount = nullptr;
@@ -369,6 +376,7 @@ int alloc_slot(sb200_ctx* ctx, Slot& s) {
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.ev_counts, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_upload, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
     s.in_cap = (size_t)ctx->max_w * ctx->max_h * B;
@@ -390,6 +398,7 @@ void free_slot(Slot& s) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.side) cudaStreamDestroy(s.side);
     if (s.ev_counts) cudaEventDestroy(s.ev_counts);
+    if (s.ev_upload) cudaEventDestroy(s.ev_upload);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
@@ -888,6 +897,36 @@ int run_pipeline(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, ui
     return SB200_OK;
 }
 
+// Host-side copies of more than a few megabytes (packing pageable input into the pinned staging buffers, the dense
+// gather of the multi-device entry point) are cut into chunks that a few short-lived threads pull from a shared
+// counter: one core moves ~10 GB/s, a 32-image 1080p group is 66 MB and the results of 8192 VGA images 1.5 GB.
+struct CopyJob { void* dst; const void* src; size_t bytes; };
+void parallel_copy(const std::vector<CopyJob>& jobs) {
+    constexpr size_t CHUNK = (size_t)4 << 20;
+    struct Piece { char* d; const char* s; size_t n; };
+    std::vector<Piece> pieces;
+    size_t total = 0;
+    for (const auto& j : jobs)
+        for (size_t o = 0; o < j.bytes; o += CHUNK) {
+            pieces.push_back({(char*)j.dst + o, (const char*)j.src + o, std::min(CHUNK, j.bytes - o)});
+            total += pieces.back().n;
+        }
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>({pieces.size(), (size_t)std::max(1u, std::min(hw ? hw : 4u, 16u)), total / ((size_t)8 << 20) + 1});
+    if (nt <= 1) {
+        for (auto& q : pieces) memcpy(q.d, q.s, q.n);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (size_t i = next.fetch_add(1); i < pieces.size(); i = next.fetch_add(1)) memcpy(pieces[i].d, pieces[i].s, pieces[i].n);
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
+
 bool is_device_accessible_host(const void* p) {
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -1028,15 +1067,22 @@ int launch_group(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img,
                                          cudaMemcpyHostToDevice, st));
             }
         } else {
-            // pageable memory: pack into the pinned staging buffer, then one async copy
-            CU(cudaStreamSynchronize(st));  // staging buffer may still feed the previous upload
-            for (uint32_t i = 0; i < n; i++) {
-                const uint8_t* from = img + i * image_stride;
-                uint8_t* to = h_up + (size_t)i * rowb * h;
-                if (stride == rowb) memcpy(to, from, rowb * h);
-                else for (uint32_t y = 0; y < h; y++) memcpy(to + (size_t)y * rowb, from + (size_t)y * stride, rowb);
+            // pageable memory: pack into the slot's pinned staging buffer, then one async copy.  Only the previous copy
+            // OUT of that buffer has to be over (it was issued a whole group ago), not the slot's previous group, so the
+            // packing of group g+1 runs on the host while the GPU computes group g
+            CU(cudaEventSynchronize(s.ev_upload));
+            std::vector<CopyJob> jobs;
+            if (stride == rowb) {
+                if (contiguous) jobs.push_back({h_up, img, rowb * h * n});
+                else for (uint32_t i = 0; i < n; i++) jobs.push_back({h_up + (size_t)i * rowb * h, img + i * image_stride, rowb * h});
+            } else {
+                for (uint32_t i = 0; i < n; i++)
+                    for (uint32_t y = 0; y < h; y++)
+                        jobs.push_back({h_up + ((size_t)i * h + y) * rowb, img + i * image_stride + (size_t)y * stride, rowb});
             }
+            parallel_copy(jobs);
             CU(cudaMemcpyAsync(d_up, h_up, rowb * h * n, cudaMemcpyHostToDevice, st));
+            CU(cudaEventRecord(s.ev_upload, st));
         }
         if (channels > 1) {
             const size_t n_px = (size_t)w * h * n;
@@ -1570,6 +1616,21 @@ int sb200_device_result(sb200_ctx* ctx, uint32_t* counts, uint32_t n, const sb20
     CU(cudaStreamSynchronize(s.stream));
     if (counts && n)
         CU(cudaMemcpy(counts, s.d_counts + 2 * ctx->max_batch, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    // the kernels clamp at the per-image capacity: a denser image is truncated, and that has to be said (the host
+    // entry points grow the capacity and run detection again; here the caller owns the schedule)
+    const uint32_t m = std::min(n ? n : s.n_imgs, ctx->max_batch);
+    if (m) {
+        std::vector<uint32_t> cc(2 * (size_t)ctx->max_batch);
+        CU(cudaMemcpy(cc.data(), s.d_counts, cc.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        uint32_t need = 0;
+        for (uint32_t i = 0; i < m; i++) need = std::max(need, std::max(cc[i], cc[ctx->max_batch + i]));
+        if (need > ctx->cap) {
+            if (capacity_per_image) *capacity_per_image = ctx->cap;
+            return fail(ctx, SB200_E_CAPACITY, "an image has %u candidates / keypoints, the context holds %u per image: the "
+                        "device-resident result is truncated (create the context with a larger max_keypoints_per_image)",
+                        need, ctx->cap);
+        }
+    }
     if (d_keypoints) *d_keypoints = reinterpret_cast<const sb200_keypoint*>(s.d_out_kps);
     if (d_descriptors) *d_descriptors = s.d_out_desc;
     if (capacity_per_image) *capacity_per_image = ctx->cap;
@@ -1809,52 +1870,87 @@ int sb200_compute_descriptors(sb200_ctx* ctx, const float* img, uint32_t w, uint
     return finish_all(ctx);
 }
 
+// contiguous shards of ceil(n / n_ctx) images, one host thread per context; parts[d] = context d's own result
+static int run_shards(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* gray, uint32_t n, uint32_t w, uint32_t h,
+                      uint32_t stride, uint64_t image_stride, int64_t features_limit, sb200_result* parts, uint64_t* first) {
+    sb200_ctx* ctx = ctxs[0];
+    const uint32_t per = (n + n_ctx - 1) / n_ctx;
+    std::vector<int> rcs(n_ctx, SB200_OK);
+    std::vector<std::thread> th;
+    for (uint32_t d = 0; d < n_ctx; d++) parts[d] = sb200_result{0, 0, nullptr, nullptr, nullptr};
+    for (uint32_t d = 0; d < n_ctx; d++) {
+        const uint64_t f = std::min<uint64_t>((uint64_t)d * per, n);
+        if (f >= n) break;
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(per, n - f);
+        auto shard = [=, &rcs]() {
+            rcs[d] = sb200_extract_batch(ctxs[d], gray + f * image_stride, cnt, w, h, stride, image_stride, features_limit,
+                                         &parts[d]);
+        };
+        if (d + 1 < n_ctx && f + cnt < n) th.emplace_back(shard);
+        else { shard(); break; }   // the last non-empty shard runs on the calling thread
+    }
+    if (first) {
+        for (uint32_t d = 0; d <= n_ctx; d++) first[d] = std::min<uint64_t>((uint64_t)d * per, n);
+    }
+    for (auto& t : th) t.join();
+    for (uint32_t d = 0; d < n_ctx; d++)
+        if (rcs[d]) return fail(ctx, rcs[d], "device %u: %s", d, sb200_last_error(ctxs[d]));
+    return SB200_OK;
+}
+
+int sb200_extract_batch_multi_parts(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* gray, uint32_t n, uint32_t w,
+                                    uint32_t h, uint32_t stride, uint64_t image_stride, int64_t features_limit,
+                                    sb200_result* parts, uint64_t* first_image) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return SB200_E_INVALID;
+    sb200_ctx* ctx = ctxs[0];
+    for (uint32_t d = 1; d < n_ctx; d++)
+        if (!ctxs[d]) return fail(ctx, SB200_E_INVALID, "context %u of %u is null", d, n_ctx);
+    if (!gray || !parts || n == 0) return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch_multi_parts");
+    return run_shards(ctxs, n_ctx, gray, n, w, h, stride, image_stride, features_limit, parts, first_image);
+}
+
 int sb200_extract_batch_multi(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* gray, uint32_t n, uint32_t w,
                               uint32_t h, uint32_t stride, uint64_t image_stride, int64_t features_limit,
                               sb200_result* out) {
     if (!ctxs || n_ctx == 0 || !ctxs[0]) return SB200_E_INVALID;
     sb200_ctx* ctx = ctxs[0];
+    for (uint32_t d = 1; d < n_ctx; d++)
+        if (!ctxs[d]) return fail(ctx, SB200_E_INVALID, "context %u of %u is null", d, n_ctx);
     if (!gray || !out || n == 0) return fail(ctx, SB200_E_INVALID, "bad arguments to extract_batch_multi");
+    ctx->last_gather_ms = 0.0;
     if (n_ctx == 1) return sb200_extract_batch(ctx, gray, n, w, h, stride, image_stride, features_limit, out);
-    // contiguous shards of ceil(n / n_ctx) images, one host thread per context
-    const uint32_t per = (n + n_ctx - 1) / n_ctx;
-    std::vector<int> rcs(n_ctx, SB200_OK);
     std::vector<sb200_result> parts(n_ctx);
-    std::vector<std::thread> th;
-    for (uint32_t d = 0; d < n_ctx; d++) {
-        const uint64_t first = (uint64_t)d * per;
-        if (first >= n) { parts[d] = sb200_result{0, 0, nullptr, nullptr, nullptr}; continue; }
-        const uint32_t cnt = (uint32_t)std::min<uint64_t>(per, n - first);
-        th.emplace_back([=, &rcs, &parts]() {
-            rcs[d] = sb200_extract_batch(ctxs[d], gray + first * image_stride, cnt, w, h, stride, image_stride,
-                                         features_limit, &parts[d]);
-        });
-    }
-    for (auto& t : th) t.join();
-    for (uint32_t d = 0; d < n_ctx; d++)
-        if (rcs[d]) return fail(ctx, rcs[d], "device %u: %s", d, sb200_last_error(ctxs[d]));
-    // host-side gather in image order into ctxs[0]'s result arrays
+    int rc = run_shards(ctxs, n_ctx, gray, n, w, h, stride, image_stride, features_limit, parts.data(), nullptr);
+    if (rc) return rc;
+    // Dense gather in image order into ctxs[0]'s result arrays (its own part already sits at their front and
+    // ensure_result_capacity preserves it).  The other parts are copied by a few host threads in parallel; callers
+    // that can take one part per device (sb200_extract_batch_multi_parts) skip this copy altogether.
+    const auto t0 = std::chrono::steady_clock::now();
     uint64_t total = 0;
     for (auto& p : parts) total += p.n;
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_result_capacity(ctx, total, n);
+    rc = ensure_result_capacity(ctx, total, n);
     if (rc) return rc;
-    // ctxs[0]'s own part already sits at the front of its arrays (ensure_result_capacity preserves it)
     uint64_t pos = parts[0].n, img = parts[0].n_images;
+    std::vector<CopyJob> jobs;
     for (uint32_t d = 1; d < n_ctx; d++) {
         const sb200_result& p = parts[d];
         if (p.n_images == 0) continue;
-        memcpy(ctx->h_kps + pos, p.keypoints, p.n * sizeof(sb200_keypoint));
-        memcpy(ctx->h_desc + pos * SB200_DESC_SIZE, p.descriptors, p.n * SB200_DESC_SIZE);
+        jobs.push_back({ctx->h_kps + pos, p.keypoints, p.n * sizeof(sb200_keypoint)});
+        jobs.push_back({ctx->h_desc + pos * SB200_DESC_SIZE, p.descriptors, p.n * SB200_DESC_SIZE});
         for (uint32_t i = 0; i < p.n_images; i++) ctx->h_offsets[img + i] = pos + p.offsets[i];
         pos += p.n;
         img += p.n_images;
     }
+    parallel_copy(jobs);
     ctx->h_offsets[img] = pos;
     ctx->res_n = pos;
     fill_result(ctx, n, out);
+    ctx->last_gather_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return SB200_OK;
 }
+
+double sb200_last_gather_ms(const sb200_ctx* ctx) { return ctx ? ctx->last_gather_ms : 0.0; }
 
 // ---- descriptor matching (examples/sift-match.rs:30-35: BFMatcher(NORM_L2, crossCheck = true)) -----------------
 namespace {
@@ -1949,18 +2045,14 @@ int sb200_match_descriptors(sb200_ctx* ctx, const uint8_t* query, uint64_t n_que
     const uint8_t* h[2] = {query, train};
     const uint64_t n[2] = {n_query, n_train};
     for (int i = 0; i < 2; i++) {
-        // the descriptor buffers are sized with the other scratch arrays of the same side
-        const size_t pad = (size_t)((n[i] + MT_N - 1) / MT_N) * MT_N;
-        if (pad > ctx->m_cap[i] || !ctx->d_mdesc[i]) {
-            cudaFree(ctx->d_mdesc[i]); cudaFree(ctx->d_mnorm[i]); cudaFree(ctx->d_mnbp[i]); cudaFree(ctx->d_mbest[i]);
-            ctx->d_mdesc[i] = nullptr; ctx->d_mnorm[i] = nullptr; ctx->d_mnbp[i] = nullptr; ctx->d_mbest[i] = nullptr;
-            ctx->m_cap[i] = 0;
-            const size_t cap_rows = std::max<size_t>(pad, MT_N);
-            CU(dalloc(&ctx->d_mdesc[i], cap_rows * DESC_SIZE));
-            CU(dalloc(&ctx->d_mnorm[i], cap_rows));
-            CU(dalloc(&ctx->d_mnbp[i], cap_rows));
-            CU(dalloc(&ctx->d_mbest[i], cap_rows));
-            ctx->m_cap[i] = cap_rows;
+        // staging copy of the host descriptors; the device entry point below sizes the other scratch arrays
+        const size_t pad = std::max<size_t>((size_t)((n[i] + MT_N - 1) / MT_N) * MT_N, MT_N);
+        if (pad > ctx->mdesc_cap[i]) {
+            CU(cudaStreamSynchronize(st));
+            cudaFree(ctx->d_mdesc[i]);
+            ctx->d_mdesc[i] = nullptr; ctx->mdesc_cap[i] = 0;
+            CU(dalloc(&ctx->d_mdesc[i], pad * DESC_SIZE));
+            ctx->mdesc_cap[i] = pad;
         }
         if (n[i]) CU(cudaMemcpyAsync(ctx->d_mdesc[i], h[i], n[i] * DESC_SIZE, cudaMemcpyHostToDevice, st));
     }

@@ -13,6 +13,8 @@ Outputs (small, committed):
                         from src/snapshots/sift__sift_end2end{,-2,-3,-4}.snap (the reference's only
                         golden vectors; written by #[test] sift_end2end, src/lib.rs:1009-1056).
   bird_gray.npy         images/bird.jpg (799x533), the benches' input (benches/sift.rs:79, descriptor.rs:9)
+  tree_gray.npy         images/tree.jpg (800x600): the densest of the reference's images (~9.6k keypoints / Mpx);
+                        tiled to the bench shapes as the "natural image" workload
 """
 import os
 import re
@@ -71,6 +73,9 @@ def main():
     g = gray_rec709(f"{REF}/images/bird.jpg")
     np.save(f"{HERE}/bird_gray.npy", g)
     print("bird", g.shape)
+    g = gray_rec709(f"{REF}/images/tree.jpg")
+    np.save(f"{HERE}/tree_gray.npy", g)
+    print("tree", g.shape)
 
 
 if __name__ == "__main__":

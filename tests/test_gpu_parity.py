@@ -346,22 +346,162 @@ def test_opencv_cross_match(sf):
 
 
 def test_multi_device_shards(sf, oracle):
-    """sb200_extract_batch_multi: contiguous shards over several contexts, host-side gather in image order
-    (SURVEY.md section 8e).  Needs >= 2 devices; with one device the same entry point runs with one context."""
+    """sb200_extract_batch_multi_parts / _multi: contiguous shards over several contexts -- every device of the box, more
+    than the module's context cache normally holds -- results in image order, the zero-copy
+    parts and the dense gather identical.  With one device the same entry points run with one context."""
     from sift_features_b200 import _ffi
     ndev = _ffi.load().sb200_device_count()
-    devices = list(range(min(ndev, 4)))
-    n, w, h = 9, 160, 120
+    devices = list(range(ndev))
+    n, w, h = 19, 160, 120
     imgs = np.stack([noise_image(w, h, 300 + i) for i in range(n)])
     res = sf.sift_batch(imgs, devices=devices, max_batch=2)
-    assert len(res) == n
-    for i in (0, 4, 8):
+    dense = sf.sift_batch(imgs, devices=devices, max_batch=2, dense=True)
+    assert len(res) == len(dense) == n
+    for a, b in zip(res, dense):
+        assert a == b
+    for i in (0, 4, 8, 18):
         okp, odesc = oracle.sift(imgs[i])
         assert len(res[i]) == len(okp)
         assert np.array_equal(_bits(res[i].keypoint_array["x"]), _bits(okp["x"]))
         assert np.abs(res[i].descriptors.astype(int) - odesc.astype(int)).max(initial=0) <= 1
     if ndev < 2:
         pytest.skip("single device: multi-context gather exercised with one context only")
+
+
+def test_multi_contexts_one_device(sf):
+    """The sharding entry points with several contexts on ONE device (what a single-GPU lease can exercise): three
+    contexts, shards of unequal size, an empty trailing shard, parts == dense == one context."""
+    import ctypes as C
+    from sift_features_b200 import _ffi
+    lib = _ffi.load()
+    n, w, h = 7, 96, 80
+    imgs = np.stack([noise_image(w, h, 500 + i) for i in range(n)])
+    with sf.Extractor(w, h, 2) as ref:
+        offs, kp, de = ref.sift_batch(imgs)
+    for n_ctx in (2, 3, 4, 8):          # 8 contexts for 7 images: ceil(7/8) = 1 image each, the last context idle
+        exs = [sf.Extractor(w, h, 2) for _ in range(n_ctx)]
+        try:
+            handles = (C.c_void_p * n_ctx)(*[e.handle for e in exs])
+            parts = (_ffi.Result * n_ctx)()
+            first = (C.c_uint64 * (n_ctx + 1))()
+            assert lib.sb200_extract_batch_multi_parts(handles, n_ctx, imgs.ctypes.data, n, w, h, w, w * h, -1, parts, first) == 0
+            assert list(first) == [min(d * -(-n // n_ctx), n) for d in range(n_ctx + 1)]
+            got_kp, got_de, n_img = [], [], 0
+            for d in range(n_ctx):
+                if parts[d].n_images == 0:
+                    continue
+                assert first[d] == n_img
+                o, k, dd = exs[d]._take(parts[d])
+                assert np.array_equal(o + len(np.concatenate(got_kp)) if got_kp else o, offs[n_img:n_img + len(o)])
+                got_kp.append(k); got_de.append(dd); n_img += int(parts[d].n_images)
+            assert n_img == n
+            assert np.array_equal(np.concatenate(got_kp), kp) and np.array_equal(np.concatenate(got_de), de)
+            res = _ffi.Result()
+            assert lib.sb200_extract_batch_multi(handles, n_ctx, imgs.ctypes.data, n, w, h, w, w * h, -1, C.byref(res)) == 0
+            o2, k2, d2 = exs[0]._take(res)
+            assert np.array_equal(o2, offs) and np.array_equal(k2, kp) and np.array_equal(d2, de)
+            assert lib.sb200_last_gather_ms(exs[0].handle) >= 0.0
+        finally:
+            for e in exs:
+                e.close()
+
+
+def test_pageable_equals_pinned(sf):
+    """Host input from pageable memory (what the crate's callers hold) goes through the pinned staging buffers, group
+    after group, overlapped with the previous group's compute: same result as pinned input, strided rows included."""
+    import ctypes as C
+    from sift_features_b200 import _ffi
+    lib = _ffi.load()
+    n, w, h = 11, 200, 150
+    imgs = np.stack([noise_image(w, h, 700 + i) for i in range(n)])
+    with sf.Extractor(w, h, 3) as ex:
+        a = ex.sift_batch(imgs)                                   # pageable numpy memory
+        p = C.c_void_p()
+        assert lib.sb200_host_alloc(imgs.nbytes, C.byref(p)) == 0
+        pinned = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=imgs.shape)
+        pinned[...] = imgs
+        b = ex.sift_batch(pinned)
+        wide = np.zeros((n, h, w + 24), np.uint8)
+        wide[:, :, :w] = imgs
+        c = ex.sift_batch(wide[:, :, :w])                         # row stride != width
+        lib.sb200_host_free(p)
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
+def test_precomputed_images_are_owned(sf, oracle):
+    """PrecomputedImages is an owned value in the crate (src/lib.rs:124-128): a later sift() on another image of the
+    same shape must not change what sift_with_precomputed(pre) returns; a view of a shared context that went stale
+    raises instead of returning the other image's results."""
+    a, b = noise_image(128, 96, 1), noise_image(128, 96, 2)
+    pre = sf.precompute_images(a)
+    rb = sf.sift(b)                                               # same shape: the module-level cache's context
+    ra = sf.sift_with_precomputed(pre)
+    assert ra == sf.sift(a) and not (ra == rb)
+    assert np.array_equal(pre.scale_space[0][0].view(np.uint32), oracle.Pyramid(a).gauss(0, 0).view(np.uint32))
+    pre.close()
+    with sf.Extractor(128, 96, 1) as ex:
+        view = ex.precompute_images(a)
+        ex.sift(b)
+        with pytest.raises(sf.SiftError):
+            ex.sift_with_precomputed(pre=view)
+        with pytest.raises(sf.SiftError):
+            view.scale_space[0]
+
+
+def test_device_result_reports_truncation(sf):
+    """sb200_device_result: a device-resident result that hit the per-image capacity is reported (SB200_E_CAPACITY),
+    not silently truncated."""
+    import ctypes as C
+    from sift_features_b200 import _ffi
+    lib = _ffi.load()
+    img = noise_image(160, 120, 3)
+    with sf.Extractor(160, 120, 1, max_keypoints_per_image=16) as ex:
+        d = C.c_void_p()
+        assert lib.sb200_device_alloc(ex.handle, img.nbytes, C.byref(d)) == 0
+        assert lib.sb200_memcpy_h2d(ex.handle, d, img.ctypes.data, img.nbytes) == 0
+        assert lib.sb200_extract_batch_device(ex.handle, d, 1, 160, 120, 160, 160 * 120, -1) == 0
+        assert lib.sb200_sync(ex.handle) == 0
+        counts = (C.c_uint32 * 1)()
+        assert lib.sb200_device_result(ex.handle, counts, 1, None, None, None) == _ffi.E_CAPACITY
+        lib.sb200_device_free(ex.handle, d)
+    with sf.Extractor(160, 120, 1) as ex:
+        d = C.c_void_p()
+        assert lib.sb200_device_alloc(ex.handle, img.nbytes, C.byref(d)) == 0
+        assert lib.sb200_memcpy_h2d(ex.handle, d, img.ctypes.data, img.nbytes) == 0
+        assert lib.sb200_extract_batch_device(ex.handle, d, 1, 160, 120, 160, 160 * 120, -1) == 0
+        counts = (C.c_uint32 * 1)()
+        assert lib.sb200_device_result(ex.handle, counts, 1, None, None, None) == 0 and counts[0] > 64
+        lib.sb200_device_free(ex.handle, d)
+
+
+def test_descriptor_scale_limit(sf):
+    """compute_descriptor with a window radius beyond the kernel's row table (scale > 12) is an invalid argument, on
+    the host entry point before anything runs and on the device entry point at the next synchronising call."""
+    import ctypes as C
+    from sift_features_b200 import _ffi
+    lib = _ffi.load()
+    img = (noise_image(256, 256, 9).astype(np.float32) / np.float32(255))
+    with sf.Extractor(256, 256, 1) as ex:
+        ok = ex.compute_descriptors(img, [[128, 128, 11.9, 30.0]])
+        assert ok.shape == (1, 128) and ok.any()
+        with pytest.raises(sf.SiftError) as e:
+            ex.compute_descriptors(img, [[128, 128, 2.0, 0.0], [128, 128, 12.5, 0.0]])
+        assert e.value.status == _ffi.E_INVALID
+        k = np.array([[128, 128, 2.0, 0.0], [100, 90, 40.0, 10.0]], np.float32)
+        d_img, d_k, d_out = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        for dptr, nbytes in ((d_img, img.nbytes), (d_k, k.nbytes), (d_out, 256)):
+            assert lib.sb200_device_alloc(ex.handle, nbytes, C.byref(dptr)) == 0
+        lib.sb200_memcpy_h2d(ex.handle, d_img, img.ctypes.data, img.nbytes)
+        lib.sb200_memcpy_h2d(ex.handle, d_k, k.ctypes.data, k.nbytes)
+        assert lib.sb200_compute_descriptors_device(ex.handle, d_img, 256, 256, 256, d_k, 2, d_out) == 0
+        assert lib.sb200_sync(ex.handle) == _ffi.E_INVALID
+        out = np.zeros((2, 128), np.uint8)
+        lib.sb200_memcpy_d2h(ex.handle, out.ctypes.data, d_out, 256)
+        assert out[0].any() and not out[1].any()             # the valid keypoint was computed, the other one zeroed
+        assert lib.sb200_sync(ex.handle) == 0                 # reported once
+        for dptr in (d_img, d_k, d_out):
+            lib.sb200_device_free(ex.handle, dptr)
 
 
 @pytest.mark.parametrize("channels", [3, 4])

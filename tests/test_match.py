@@ -64,3 +64,33 @@ def test_gpu_match_real_descriptors(sf, oracle):
     # an image against itself: every keypoint whose descriptor is unique matches itself at distance 0
     assert (self_m["distance"] == 0).all() and len(self_m) >= 0.95 * len(ra)
     assert len(empty) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_match_scratch_capacities(sf, oracle):
+    """Host and device entry points share scratch arrays with separate capacities: small host match, large device
+    match, medium host match on one context (the sequence that used to overrun the host variant's staging buffer)."""
+    import ctypes as C
+    from sift_features_b200 import _ffi
+    lib = _ffi.load()
+    small_q, small_t = _random_desc(40, 1), _random_desc(50, 2)
+    big_q, big_t = _random_desc(3000, 3), _random_desc(2500, 4)
+    mid_q, mid_t = _random_desc(900, 5), _random_desc(1100, 6)
+    with sf.Extractor(8, 8, 1) as ex:
+        a = ex.match(small_q, small_t)
+        d_q, d_t = C.c_void_p(), C.c_void_p()
+        assert lib.sb200_device_alloc(ex.handle, big_q.nbytes, C.byref(d_q)) == 0
+        assert lib.sb200_device_alloc(ex.handle, big_t.nbytes, C.byref(d_t)) == 0
+        lib.sb200_memcpy_h2d(ex.handle, d_q, big_q.ctypes.data, big_q.nbytes)
+        lib.sb200_memcpy_h2d(ex.handle, d_t, big_t.ctypes.data, big_t.nbytes)
+        raw = np.zeros(len(big_q), np.dtype([("query", np.uint32), ("train", np.uint32), ("dist2", np.uint32)]))
+        cnt = C.c_uint64()
+        assert lib.sb200_match_descriptors_device(ex.handle, d_q, len(big_q), d_t, len(big_t), raw.ctypes.data, len(raw),
+                                                  C.byref(cnt)) == 0
+        b = ex.match(mid_q, mid_t)
+        lib.sb200_device_free(ex.handle, d_q); lib.sb200_device_free(ex.handle, d_t)
+    for m, (q, t) in ((a, (small_q, small_t)), (b, (mid_q, mid_t))):
+        o = oracle.match_cross_check(q, t)
+        assert np.array_equal(m["queryIdx"], o[:, 0]) and np.array_equal(m["trainIdx"], o[:, 1])
+    o = oracle.match_cross_check(big_q, big_t)
+    assert cnt.value == len(o) and np.array_equal(raw["query"][: len(o)], o[:, 0])
