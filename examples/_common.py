@@ -12,15 +12,31 @@ def is_jpeg(data: bytes) -> bool:
     return data[:2] == b"\xff\xd8"
 
 
-def load_and_sift(path: str, features_limit=None):
+def pop_processing(argv):
+    """`--processing=opencv|imageproc` anywhere on the command line.  The reference's examples call the crate's plain
+    sift(), i.e. ImageprocProcessing (src/lib.rs:71-73) -- the default here too; `opencv` selects the flavour the crate's
+    test pins (sift_with_processing::<OpenCVProcessing>)."""
+    processing = sf.ImageprocProcessing
+    for a in list(argv):
+        if a.startswith("--processing="):
+            argv.remove(a)
+            name = a.split("=", 1)[1]
+            if name not in ("opencv", "imageproc"):
+                raise SystemExit("--processing must be opencv or imageproc")
+            processing = sf.OpenCVProcessing if name == "opencv" else sf.ImageprocProcessing
+    return processing
+
+
+def load_and_sift(path: str, features_limit=None, processing=None):
     """`image::open(path).grayscale()` + `sift()` (examples/run-sift.rs:8-19).  A JPEG goes to the device as a bitstream
     (nvJPEG decode + integer luma there); anything else is decoded by OpenCV and converted on the device.
     Returns (gray image the features belong to, SiftResult)."""
+    processing = processing or sf.ImageprocProcessing
     data = open(path, "rb").read()
     if is_jpeg(data):
         with sf.Extractor(8, 8, 1) as probe:
             w, h, _ = probe.jpeg_info(data)
-        with sf.Extractor(w, h, 1) as ex:
+        with sf.Extractor(w, h, 1, processing=processing) as ex:
             gray = ex.decode_jpeg_luma(data)
             _, kp, desc = ex.sift_jpeg([data], features_limit)
         return gray, sf.SiftResult(kp, desc)
@@ -31,10 +47,10 @@ def load_and_sift(path: str, features_limit=None):
     if img.dtype != np.uint8:
         raise SystemExit("wrong image type")      # the reference's examples accept 8-bit images only
     if img.ndim == 2:
-        return img, sf.sift(img, features_limit)
+        return img, sf.sift_with_processing(img, features_limit, processing)
     rgb = np.ascontiguousarray(img[..., 2::-1])    # BGR(A) -> RGB
     h, w = rgb.shape[:2]
-    with sf.Extractor(w, h, 1) as ex:
+    with sf.Extractor(w, h, 1, processing=processing) as ex:
         return ex.rgb_to_luma(rgb), ex.sift_rgb(rgb, features_limit)
 
 

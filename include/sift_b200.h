@@ -103,8 +103,23 @@ const char* sb200_status_string(int status);
 /* number of CUDA devices visible, or a negative status */
 int sb200_device_count(void);
 
-/* ---- extraction: sift() / sift_with_processing::<OpenCVProcessing>() ----
- * src/lib.rs:71-81.  features_limit < 0 means None. */
+/* ---- Processing flavour: the type parameter P of sift_with_processing::<P>, src/lib.rs:76-90 ----
+ * Which blur / resize arithmetic builds the Gaussian pyramid.  A context starts with SB200_PROCESSING_OPENCV.
+ *   SB200_PROCESSING_OPENCV     OpenCVProcessing (src/opencv_processing.rs:39-74): the flavour the crate's test and
+ *                               insta snapshots use; pinned bit-for-bit against OpenCV 4.13.
+ *   SB200_PROCESSING_IMAGEPROC  ImageprocProcessing (src/lib.rs:992-1007) -- what the crate's plain sift() means
+ *                               (src/lib.rs:71-73).  Restated from the published algorithms of imageproc 0.25 /
+ *                               image 0.25, whose sources are not part of the reference tree and which no reference
+ *                               test exercises: PARITY UNPINNED (bit-exact against this repository's oracle only).
+ * The call drops the resident pyramid and takes effect from the next extract / precompute call. */
+#define SB200_PROCESSING_OPENCV 0
+#define SB200_PROCESSING_IMAGEPROC 1
+int sb200_set_processing(sb200_ctx* ctx, int processing);
+int sb200_get_processing(const sb200_ctx* ctx);   /* the flavour, or a negative status */
+
+/* ---- extraction: sift_with_processing::<P>() with the context's flavour P ----
+ * src/lib.rs:71-81.  features_limit < 0 means None.  (The crate's sift() is sift_with_processing::<ImageprocProcessing>;
+ * the host mirrors -- Python, C++, Rust -- select that flavour for their sift().) */
 int sb200_extract(sb200_ctx* ctx, const uint8_t* gray, uint32_t w, uint32_t h, uint32_t stride,
                   int64_t features_limit, sb200_result* out);
 

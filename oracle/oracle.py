@@ -66,6 +66,16 @@ def lib() -> C.CDLL:
     L.so_octave_sigma.argtypes = [C.c_int]
     L.so_precompute.restype = C.c_void_p
     L.so_precompute.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
+    L.so_precompute_flavour.restype = C.c_void_p
+    L.so_precompute_flavour.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.so_imageproc_taps.restype = C.c_int
+    L.so_imageproc_taps.argtypes = [C.c_double, f32p, C.c_int]
+    L.so_gaussian_blur_imageproc.restype = None
+    L.so_gaussian_blur_imageproc.argtypes = [f32p, C.c_int, C.c_int, C.c_double, f32p]
+    L.so_resize_triangle_2x.restype = None
+    L.so_resize_triangle_2x.argtypes = [f32p, C.c_int, C.c_int, f32p]
+    L.so_resize_nearest_imageproc.restype = None
+    L.so_resize_nearest_imageproc.argtypes = [f32p, C.c_int, C.c_int, f32p]
     L.so_pyramid_free.restype = None
     L.so_pyramid_free.argtypes = [C.c_void_p]
     for name in ("so_pyramid_octaves",):
@@ -129,14 +139,45 @@ def octave_sigma(s: int) -> float:
     return lib().so_octave_sigma(s)
 
 
+# ---- Processing flavour B (ImageprocProcessing, src/lib.rs:992-1007; PARITY UNPINNED, see sift_oracle.h) ----
+PROCESSING_OPENCV, PROCESSING_IMAGEPROC = 0, 1
+
+
+def imageproc_taps(sigma: float) -> np.ndarray:
+    t = np.zeros(64, np.float32)
+    n = lib().so_imageproc_taps(sigma, t, 64)
+    return t[:n].copy()
+
+
+def gaussian_blur_imageproc(img: np.ndarray, sigma: float) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.empty_like(img)
+    lib().so_gaussian_blur_imageproc(img, img.shape[1], img.shape[0], sigma, out)
+    return out
+
+
+def resize_triangle_2x(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.empty((img.shape[0] * 2, img.shape[1] * 2), np.float32)
+    lib().so_resize_triangle_2x(img, img.shape[1], img.shape[0], out)
+    return out
+
+
+def resize_nearest_imageproc(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.empty((img.shape[0] // 2, img.shape[1] // 2), np.float32)
+    lib().so_resize_nearest_imageproc(img, img.shape[1], img.shape[0], out)
+    return out
+
+
 # ---- pyramid ---------------------------------------------------------------
 class Pyramid:
     """Mirror of PrecomputedImages (src/lib.rs:124-128)."""
 
-    def __init__(self, gray: np.ndarray):
+    def __init__(self, gray: np.ndarray, processing: int = PROCESSING_OPENCV):
         gray = np.ascontiguousarray(gray, np.uint8)
         assert gray.ndim == 2
-        self._h = lib().so_precompute(gray, gray.shape[1], gray.shape[0], gray.shape[1])
+        self._h = lib().so_precompute_flavour(gray, gray.shape[1], gray.shape[0], gray.shape[1], processing)
         self.n_octaves = lib().so_pyramid_octaves(self._h)
         self.dims = [(lib().so_pyramid_width(self._h, o), lib().so_pyramid_height(self._h, o))
                      for o in range(self.n_octaves)]
@@ -190,9 +231,9 @@ class Pyramid:
             pass
 
 
-def sift(gray: np.ndarray, features_limit: int | None = None):
-    """sift_with_processing::<OpenCVProcessing> (src/lib.rs:76-81)."""
-    p = Pyramid(gray)
+def sift(gray: np.ndarray, features_limit: int | None = None, processing: int = PROCESSING_OPENCV):
+    """sift_with_processing::<P> (src/lib.rs:76-81); P = OpenCVProcessing unless processing says otherwise."""
+    p = Pyramid(gray, processing)
     try:
         return p.sift(features_limit)
     finally:

@@ -186,6 +186,138 @@ void so_resize_nearest_half(const float* src, int w, int h, float* dst) {
 }
 
 /* ------------------------------------------------------------------ */
+/* Processing flavour B: ImageprocProcessing, src/lib.rs:992-1007        */
+/*                                                                      */
+/* PARITY UNPINNED.  The arithmetic lives in two third-party crates     */
+/* that are NOT part of /root/reference (Cargo.toml:13-14: image        */
+/* ^0.25.2, imageproc ^0.25.0; no Cargo.lock, nothing vendored) and no  */
+/* reference test, snapshot or bench exercises this flavour.  What      */
+/* follows restates those crates' published algorithms (imageproc       */
+/* filter::gaussian_blur_f32 -> separable_filter_equal; image           */
+/* imageops::resize -> vertical_sample + horizontal_sample) operation   */
+/* by operation; it pins the GPU path to THIS restatement, not to the   */
+/* crates' binaries.                                                    */
+/* ------------------------------------------------------------------ */
+
+/* imageproc gaussian_kernel_f32(sigma): radius ceil(2 sigma); taps
+ * gaussian_pdf(x) = (sigma * sqrt(2 pi)).recip() * exp(-x^2 / (2 sigma^2)), all f32, not renormalised. */
+int so_imageproc_taps(double sigma64, float* taps, int cap) {
+    float sigma = (float)sigma64; /* src/lib.rs:997: `sigma as f32` */
+    int r = (int)ceilf(2.0f * sigma);
+    int ks = 2 * r + 1;
+    if (ks > cap) return -ks;
+    float norm = 1.0f / (sigma * sqrtf(2.0f * 3.14159265358979323846f));
+    for (int i = 0; i <= r; i++) {
+        float x = (float)i;
+        float v = norm * expf(-(x * x) / (2.0f * (sigma * sigma)));
+        taps[r + i] = v;
+        taps[r - i] = v;
+    }
+    return ks;
+}
+
+/* imageproc separable_filter_equal: horizontal_filter then vertical_filter; each output accumulates
+ * acc = acc + pixel * weight from zero over the taps in order (no FMA); out-of-image taps read the clamped edge pixel. */
+void so_gaussian_blur_imageproc(const float* src, int w, int h, double sigma, float* dst) {
+    float k[64];
+    int ks = so_imageproc_taps(sigma, k, 64);
+    int r = ks / 2;
+    float* tmp = (float*)malloc((size_t)w * h * sizeof(float));
+    for (int y = 0; y < h; y++) {
+        const float* s = src + (size_t)y * w;
+        float* t = tmp + (size_t)y * w;
+        for (int x = 0; x < w; x++) {
+            float acc = 0.0f;
+            for (int i = 0; i < ks; i++) {
+                int xi = x + i - r;
+                xi = xi < 0 ? 0 : (xi > w - 1 ? w - 1 : xi);
+                acc = acc + s[xi] * k[i];
+            }
+            t[x] = acc;
+        }
+    }
+    for (int y = 0; y < h; y++) {
+        float* d = dst + (size_t)y * w;
+        for (int x = 0; x < w; x++) {
+            float acc = 0.0f;
+            for (int i = 0; i < ks; i++) {
+                int yi = y + i - r;
+                yi = yi < 0 ? 0 : (yi > h - 1 ? h - 1 : yi);
+                acc = acc + tmp[(size_t)yi * w + x] * k[i];
+            }
+            d[x] = acc;
+        }
+    }
+    free(tmp);
+}
+
+/* image 0.25 imageops::sample: triangle_kernel / box_kernel and the two 1-D resampling passes, literally.
+ * resize() runs vertical_sample first (into an f32 image, unclamped), then horizontal_sample (clamped to the
+ * subpixel range, [0, 1] for f32). */
+typedef float (*so_kernel_fn)(float);
+static float so_triangle_kernel(float x) { return fabsf(x) < 1.0f ? 1.0f - fabsf(x) : 0.0f; }
+static float so_box_kernel(float x) { (void)x; return 1.0f; }
+
+static void so_sample_1d(const float* src, int w, int h, int n_new, int vertical, so_kernel_fn kernel, float support,
+                         float* out) {
+    const int n = vertical ? h : w;
+    const float ratio = (float)n / (float)n_new;
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    const float src_support = support * sratio;
+    float ws[64];
+    for (int o = 0; o < n_new; o++) {
+        float input = ((float)o + 0.5f) * ratio;
+        int64_t left = rust_f32_as_i64(floorf(input - src_support));
+        if (left < 0) left = 0;
+        if (left > n - 1) left = n - 1;
+        int64_t right = rust_f32_as_i64(ceilf(input + src_support));
+        if (right < left + 1) right = left + 1;
+        if (right > n) right = n;
+        input = input - 0.5f;
+        float sum = 0.0f;
+        int cnt = 0;
+        for (int64_t i = left; i < right; i++) {
+            float wgt = kernel(((float)i - input) / sratio);
+            ws[cnt++] = wgt;
+            sum += wgt;
+        }
+        for (int i = 0; i < cnt; i++) ws[i] /= sum;
+        if (vertical) {
+            for (int x = 0; x < w; x++) {
+                float t = 0.0f;
+                for (int i = 0; i < cnt; i++) t += src[(size_t)(left + i) * w + x] * ws[i];
+                out[(size_t)o * w + x] = t;
+            }
+        } else {
+            for (int y = 0; y < h; y++) {
+                float t = 0.0f;
+                for (int i = 0; i < cnt; i++) t += src[(size_t)y * w + (left + i)] * ws[i];
+                t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t); /* clamp(t, S::DEFAULT_MIN_VALUE, S::DEFAULT_MAX_VALUE) */
+                out[(size_t)y * n_new + o] = t;
+            }
+        }
+    }
+}
+
+static void so_resize_image_crate(const float* src, int w, int h, int nw, int nh, so_kernel_fn kernel, float support,
+                                  float* dst) {
+    if (nw <= 0 || nh <= 0) return;
+    float* tmp = (float*)malloc((size_t)w * nh * sizeof(float));
+    so_sample_1d(src, w, h, nh, 1, kernel, support, tmp);
+    so_sample_1d(tmp, w, nh, nw, 0, kernel, support, dst);
+    free(tmp);
+}
+
+/* src/lib.rs:1001: resize(img, 2w, 2h, FilterType::Triangle) */
+void so_resize_triangle_2x(const float* src, int w, int h, float* dst) {
+    so_resize_image_crate(src, w, h, 2 * w, 2 * h, so_triangle_kernel, 1.0f, dst);
+}
+/* src/lib.rs:1005: resize(img, w/2, h/2, FilterType::Nearest) */
+void so_resize_nearest_imageproc(const float* src, int w, int h, float* dst) {
+    so_resize_image_crate(src, w, h, w / 2, h / 2, so_box_kernel, 0.0f, dst);
+}
+
+/* ------------------------------------------------------------------ */
 /* pyramid: src/lib.rs:131-143, 196-279                                */
 /* ------------------------------------------------------------------ */
 struct so_pyramid {
@@ -220,6 +352,12 @@ double so_octave_sigma(int s) {
 }
 
 so_pyramid* so_precompute(const uint8_t* gray, int w, int h, int stride) {
+    return so_precompute_flavour(gray, w, h, stride, SO_PROCESSING_OPENCV);
+}
+
+/* precompute_images::<P>, src/lib.rs:131-143, with P selected at run time */
+so_pyramid* so_precompute_flavour(const uint8_t* gray, int w, int h, int stride, int flavour) {
+    const int B = flavour == SO_PROCESSING_IMAGEPROC;
     so_pyramid* p = (so_pyramid*)calloc(1, sizeof(so_pyramid));
     /* create_seed_image, src/lib.rs:196-210 */
     float* f = (float*)malloc((size_t)w * h * sizeof(float));
@@ -228,10 +366,12 @@ so_pyramid* so_precompute(const uint8_t* gray, int w, int h, int stride) {
             f[(size_t)y * w + x] = (float)gray[(size_t)y * stride + x] / 255.0f; /* img.convert(), :198 */
     int W = w * INV_DELTA_MIN, H = h * INV_DELTA_MIN;
     float* up = (float*)malloc((size_t)W * H * sizeof(float));
-    so_resize_linear_2x(f, w, h, up);
+    if (B) so_resize_triangle_2x(f, w, h, up);
+    else so_resize_linear_2x(f, w, h, up);
     free(f);
     float* seed = (float*)malloc((size_t)W * H * sizeof(float));
-    so_gaussian_blur(up, W, H, so_seed_sigma(), seed);
+    if (B) so_gaussian_blur_imageproc(up, W, H, so_seed_sigma(), seed);
+    else so_gaussian_blur(up, W, H, so_seed_sigma(), seed);
     free(up);
 
     /* src/lib.rs:133-134 */
@@ -250,9 +390,10 @@ so_pyramid* so_precompute(const uint8_t* gray, int w, int h, int stride) {
         p->gauss[o] = (float*)malloc(px * SO_LAYERS * sizeof(float));
         memcpy(p->gauss[o], initial, px * sizeof(float));
         free(initial);
-        for (int s = 1; s < SO_LAYERS; s++) /* sigmas.iter().skip(1), :233 */
-            so_gaussian_blur(p->gauss[o] + px * (s - 1), cw, ch, so_octave_sigma(s),
-                             p->gauss[o] + px * s);
+        for (int s = 1; s < SO_LAYERS; s++) { /* sigmas.iter().skip(1), :233 */
+            if (B) so_gaussian_blur_imageproc(p->gauss[o] + px * (s - 1), cw, ch, so_octave_sigma(s), p->gauss[o] + px * s);
+            else so_gaussian_blur(p->gauss[o] + px * (s - 1), cw, ch, so_octave_sigma(s), p->gauss[o] + px * s);
+        }
         /* build_dog, :271-279 */
         p->dog[o] = (float*)malloc(px * SO_DOG_LAYERS * sizeof(float));
         for (int s = 0; s < SO_DOG_LAYERS; s++) {
@@ -265,7 +406,8 @@ so_pyramid* so_precompute(const uint8_t* gray, int w, int h, int stride) {
             /* :245-248: layer index len-3 = 3, nearest to (w/2, h/2) */
             int nw = cw / 2, nh = ch / 2;
             initial = (float*)malloc((size_t)(nw > 0 ? nw : 1) * (nh > 0 ? nh : 1) * sizeof(float));
-            so_resize_nearest_half(p->gauss[o] + px * 3, cw, ch, initial);
+            if (B) so_resize_nearest_imageproc(p->gauss[o] + px * 3, cw, ch, initial);
+            else so_resize_nearest_half(p->gauss[o] + px * 3, cw, ch, initial);
             cw = nw; ch = nh;
         } else {
             initial = NULL;
@@ -691,7 +833,13 @@ size_t so_sift_with_precomputed(const so_pyramid* p, int64_t features_limit, so_
 
 size_t so_sift(const uint8_t* gray, int w, int h, int stride, int64_t features_limit, so_keypoint* kps,
                uint8_t* desc, size_t cap) {
-    so_pyramid* p = so_precompute(gray, w, h, stride);
+    return so_sift_flavour(gray, w, h, stride, features_limit, SO_PROCESSING_OPENCV, kps, desc, cap);
+}
+
+/* sift_with_processing::<P>, src/lib.rs:76-81 */
+size_t so_sift_flavour(const uint8_t* gray, int w, int h, int stride, int64_t features_limit, int flavour,
+                       so_keypoint* kps, uint8_t* desc, size_t cap) {
+    so_pyramid* p = so_precompute_flavour(gray, w, h, stride, flavour);
     size_t n = so_sift_with_precomputed(p, features_limit, kps, desc, cap);
     so_pyramid_free(p);
     return n;

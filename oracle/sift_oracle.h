@@ -8,10 +8,11 @@
  * cpu_baseline / --impl reference legs may load this library; the product
  * (sift_features_b200/) never links, imports or calls it.
  *
- * Parity status: PINNED -- against (1) cv2.GaussianBlur / cv2.resize of
+ * Parity status (flavour A, the default of every function without a flavour argument): PINNED -- against (1) cv2.GaussianBlur / cv2.resize of
  * OpenCV 4.13 bit-for-bit on the pyramid arithmetic, (2) cv2.SIFT_create on
  * identical pixels, (3) the crate's four insta snapshots with the tolerance a
  * different JPEG decoder forces (see tests/test_oracle_golden.py).
+ * Flavour B (ImageprocProcessing): PARITY UNPINNED, see below.
  *
  * Every function cites the reference lines it follows (paths relative to
  * /root/reference).
@@ -58,12 +59,23 @@ void so_gaussian_blur(const float* src, int w, int h, double sigma, float* dst);
 void so_resize_linear_2x(const float* src, int w, int h, float* dst /* 2w x 2h */);
 void so_resize_nearest_half(const float* src, int w, int h, float* dst /* (w/2) x (h/2) */);
 
+/* ---- Processing flavour B (ImageprocProcessing, src/lib.rs:992-1007): PARITY UNPINNED ----
+ * imageproc 0.25 / image 0.25 are not part of the reference tree and no reference test uses this flavour; these
+ * functions restate the crates' published algorithms (see the block comment in sift_oracle.c). */
+#define SO_PROCESSING_OPENCV 0
+#define SO_PROCESSING_IMAGEPROC 1
+int so_imageproc_taps(double sigma, float* taps, int cap);
+void so_gaussian_blur_imageproc(const float* src, int w, int h, double sigma, float* dst);
+void so_resize_triangle_2x(const float* src, int w, int h, float* dst /* 2w x 2h */);
+void so_resize_nearest_imageproc(const float* src, int w, int h, float* dst /* (w/2) x (h/2) */);
+
 /* the five per-octave sigmas of src/lib.rs:220-229 (index 1..5) and the seed sigma (:207) */
 double so_seed_sigma(void);
 double so_octave_sigma(int s);
 
 /* ---- pyramid: src/lib.rs:131-143, 196-279 ---- */
-so_pyramid* so_precompute(const uint8_t* gray, int w, int h, int stride);
+so_pyramid* so_precompute(const uint8_t* gray, int w, int h, int stride);                         /* flavour A */
+so_pyramid* so_precompute_flavour(const uint8_t* gray, int w, int h, int stride, int flavour);
 void so_pyramid_free(so_pyramid* p);
 int so_pyramid_octaves(const so_pyramid* p);
 int so_pyramid_width(const so_pyramid* p, int octave);
@@ -86,7 +98,9 @@ void so_compute_descriptor(const float* img, int w, int h, float x, float y, flo
 size_t so_sift_with_precomputed(const so_pyramid* p, int64_t features_limit, so_keypoint* kps,
                                 uint8_t* desc, size_t cap);
 size_t so_sift(const uint8_t* gray, int w, int h, int stride, int64_t features_limit,
-               so_keypoint* kps, uint8_t* desc, size_t cap);
+               so_keypoint* kps, uint8_t* desc, size_t cap);                                       /* flavour A */
+size_t so_sift_flavour(const uint8_t* gray, int w, int h, int stride, int64_t features_limit, int flavour,
+                       so_keypoint* kps, uint8_t* desc, size_t cap);
 
 #ifdef __cplusplus
 }

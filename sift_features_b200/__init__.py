@@ -16,11 +16,14 @@ All computation happens in hand-written sm_100a CUDA kernels inside
 libsift_b200.so; this package only marshals buffers.  There is NO CPU fallback:
 without the built library or without a CUDA device every call raises.
 
-Processing flavour: the crate's only pinned flavour is OpenCVProcessing
-(src/opencv_processing.rs; the flavour its test and snapshots use) and that is
-what the kernels implement bit-for-bit.  `sift()` in the crate defaults to
-ImageprocProcessing (src/lib.rs:71-73, 992-1007), whose third-party arithmetic is
-not available to pin; here `sift()` is `sift_with_processing::<OpenCVProcessing>`.
+Processing flavour (the crate's `P: Processing`, src/lib.rs:76-90), both implemented on the GPU:
+  * OpenCVProcessing (src/opencv_processing.rs) -- the flavour the crate's test, snapshots and benches use;
+    pinned bit-for-bit against OpenCV 4.13.  Default of `Extractor` and of every batched entry point.
+  * ImageprocProcessing (src/lib.rs:992-1007) -- what the crate's plain `sift()` means (src/lib.rs:71-73), and
+    therefore what the module-level `sift()` here selects.  Its arithmetic lives in the imageproc / image crates,
+    which are not part of the reference tree: restated from their published algorithms, PARITY UNPINNED
+    (bit-exact against this repository's oracle only).  Use `sift_with_processing(img, limit, OpenCVProcessing)`
+    for the pinned flavour, exactly as the crate's own test does.
 """
 from __future__ import annotations
 
@@ -33,7 +36,7 @@ import numpy as np
 from . import _ffi
 
 __all__ = [
-    "KeyPoint", "SiftResult", "PrecomputedImages", "OpenCVProcessing", "ImageprocProcessing", "Extractor",
+    "KeyPoint", "SiftResult", "PrecomputedImages", "Processing", "OpenCVProcessing", "ImageprocProcessing", "Extractor",
     "SiftError", "sift", "sift_with_processing", "precompute_images", "sift_with_precomputed",
     "compute_descriptor", "compute_descriptors", "sift_batch", "match", "MATCH_DTYPE", "KEYPOINT_DTYPE",
 ]
@@ -87,14 +90,29 @@ class SiftResult:
                 and np.array_equal(self.descriptors, other.descriptors))
 
 
-class OpenCVProcessing:
-    """Marker for the blur/resize flavour of src/opencv_processing.rs (implemented on the GPU)."""
+class Processing:
+    """src/lib.rs:86-90: the blur / resize implementation the pyramid is built with.  The crate's trait has three
+    associated functions and static dispatch; here an implementation is a marker class whose FLAVOUR selects the
+    device kernels (sb200_set_processing)."""
+    FLAVOUR = -1
 
 
-class ImageprocProcessing:
-    """Marker for src/lib.rs:992-1007 (imageproc/image crates).  Not implemented: its arithmetic
-    lives in third-party crates that are not part of the reference tree and no reference test
-    pins it."""
+class OpenCVProcessing(Processing):
+    """src/opencv_processing.rs:39-74: GaussianBlur(ksize = 0, sigma), resize INTER_LINEAR / INTER_NEAREST.  Pinned."""
+    FLAVOUR = _ffi.PROCESSING_OPENCV
+
+
+class ImageprocProcessing(Processing):
+    """src/lib.rs:992-1007: imageproc gaussian_blur_f32, image resize Triangle / Nearest -- the crate's default.
+    Restated from the crates' published algorithms; parity unpinned."""
+    FLAVOUR = _ffi.PROCESSING_IMAGEPROC
+
+
+def _flavour(processing) -> int:
+    f = getattr(processing, "FLAVOUR", None)
+    if f not in (_ffi.PROCESSING_OPENCV, _ffi.PROCESSING_IMAGEPROC):
+        raise ValueError("processing must be OpenCVProcessing or ImageprocProcessing")
+    return f
 
 
 def _as_gray(img) -> np.ndarray:
@@ -110,8 +128,10 @@ class Extractor:
     """One sb200 context: a device, its arenas and streams.  Not re-entrant (use one per thread)."""
 
     def __init__(self, max_width: int, max_height: int, max_batch: int = 1, device: int = 0,
-                 max_keypoints_per_image: int = 0):
+                 max_keypoints_per_image: int = 0, processing=OpenCVProcessing):
         self._lib = _ffi.load()
+        self.processing = processing
+        flavour = _flavour(processing)
         self._h = C.c_void_p()
         st = self._lib.sb200_create(device, max_width, max_height, max_batch, max_keypoints_per_image,
                                     C.byref(self._h))
@@ -121,6 +141,7 @@ class Extractor:
         self.device, self.max_width, self.max_height, self.max_batch = device, max_width, max_height, max_batch
         self.max_keypoints_per_image = max_keypoints_per_image or max(16384, max_width * max_height // 8)
         self.auto_grow = max_keypoints_per_image == 0   # an explicit capacity is a hard limit
+        self._check(self._lib.sb200_set_processing(self._h, flavour))
         self._generation = 0   # bumped by every call that replaces the pyramid resident in the context
 
     def _grow(self) -> bool:
@@ -136,6 +157,7 @@ class Extractor:
         st = self._lib.sb200_create(self.device, self.max_width, self.max_height, self.max_batch, cap, C.byref(self._h))
         if st != _ffi.OK:
             raise SiftError(st, "re-creating the context with a larger capacity failed")
+        self._check(self._lib.sb200_set_processing(self._h, _flavour(self.processing)))
         self.max_keypoints_per_image = cap
         return True
 
@@ -189,7 +211,7 @@ class Extractor:
 
     # -- the crate's entry points ----------------------------------------
     def sift(self, img, features_limit: Optional[int] = None) -> SiftResult:
-        """sift / sift_with_processing::<OpenCVProcessing> (src/lib.rs:71-81)."""
+        """sift_with_processing::<P> (src/lib.rs:76-81) with the extractor's Processing P."""
         a = _as_gray(img)
         res = _ffi.Result()
         self._retry_capacity(lambda: self._lib.sb200_extract(
@@ -268,7 +290,7 @@ class Extractor:
         return self._lib.sb200_jpeg_backend(self._h).decode()
 
     def precompute_images(self, img) -> "PrecomputedImages":
-        """precompute_images::<OpenCVProcessing> (src/lib.rs:131-143); the pyramid stays on the device."""
+        """precompute_images::<P> (src/lib.rs:131-143) with the extractor's Processing; the pyramid stays on the device."""
         a = _as_gray(img)
         self._generation += 1
         self._check(self._lib.sb200_precompute(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0]))
@@ -414,10 +436,11 @@ _cache: dict = {}
 _CACHE_MAX = 8   # contexts hold device arenas: keep only a few alive
 
 
-def _extractor(w: int, h: int, batch: int = 1, device: int = 0, keep=()) -> Extractor:
-    """Context for (device, shape, batch) from a small LRU cache.  `keep`: keys the current call still uses -- they are
-    never evicted (a call that shards over more devices than the cache normally holds grows it for its duration)."""
-    key = (device, w, h, batch)
+def _extractor(w: int, h: int, batch: int = 1, device: int = 0, keep=(), processing=OpenCVProcessing) -> Extractor:
+    """Context for (device, shape, batch[, processing]) from a small LRU cache.  `keep`: keys the current call still
+    uses -- they are never evicted (a call that shards over more devices than the cache normally holds grows it for
+    its duration)."""
+    key = (device, w, h, batch) if processing is OpenCVProcessing else (device, w, h, batch, _flavour(processing))
     ex = _cache.pop(key, None)
     if ex is None:
         while len(_cache) >= _CACHE_MAX:
@@ -425,32 +448,30 @@ def _extractor(w: int, h: int, batch: int = 1, device: int = 0, keep=()) -> Extr
             if victim is None:
                 break
             _cache.pop(victim).close()
-        ex = Extractor(w, h, batch, device)
+        ex = Extractor(w, h, batch, device) if processing is OpenCVProcessing else Extractor(w, h, batch, device, 0, processing)
     _cache[key] = ex   # most recently used last
     return ex
 
 
 def sift(img, features_limit: Optional[int] = None, device: int = 0) -> SiftResult:
-    """src/lib.rs:71 (OpenCVProcessing flavour, see the module docstring)."""
-    a = _as_gray(img)
-    return _extractor(a.shape[1], a.shape[0], 1, device).sift(a, features_limit)
+    """src/lib.rs:71-73: `sift_with_processing::<ImageprocProcessing>(img, features_limit)`, like the crate.  (That
+    flavour's arithmetic is restated from the imageproc / image crates and unpinned; the flavour the crate's own test
+    pins is `sift_with_processing(img, limit, OpenCVProcessing)`.)"""
+    return sift_with_processing(img, features_limit, ImageprocProcessing, device)
 
 
 def sift_with_processing(img, features_limit: Optional[int] = None, processing=OpenCVProcessing,
                          device: int = 0) -> SiftResult:
     """src/lib.rs:76.  `processing` selects the blur/resize flavour (the crate's type parameter P)."""
-    if processing is not OpenCVProcessing:
-        raise NotImplementedError("only OpenCVProcessing (src/opencv_processing.rs) is implemented on the GPU; "
-                                  "ImageprocProcessing's third-party arithmetic is unpinned")
-    return sift(img, features_limit, device)
+    a = _as_gray(img)
+    return _extractor(a.shape[1], a.shape[0], 1, device, processing=processing).sift(a, features_limit)
 
 
-def precompute_images(img, device: int = 0) -> PrecomputedImages:
-    """src/lib.rs:131.  The crate returns an owned value; so does this: the result holds its own context (never shared
-    with the module-level cache), released when the result is dropped."""
+def precompute_images(img, processing=OpenCVProcessing, device: int = 0) -> PrecomputedImages:
+    """src/lib.rs:131: precompute_images::<P>(img).  The crate returns an owned value; so does this: the result holds
+    its own context (never shared with the module-level cache), released when the result is dropped."""
     a = _as_gray(img)
-    ex = Extractor(a.shape[1], a.shape[0], 1, device)
-    a = _as_gray(img)
+    ex = Extractor(a.shape[1], a.shape[0], 1, device, 0, processing)
     ex._generation += 1
     ex._check(ex._lib.sb200_precompute(ex.handle, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0]))
     return PrecomputedImages(ex, owns_extractor=True)
@@ -477,7 +498,7 @@ def compute_descriptor(img_f32, x: float, y: float, scale: float, orientation: f
 
 
 def sift_batch(images, features_limit: Optional[int] = None, devices: Optional[Sequence[int]] = None,
-               max_batch: int = 16, dense: bool = False) -> List[SiftResult]:
+               max_batch: int = 16, dense: bool = False, processing=OpenCVProcessing) -> List[SiftResult]:
     """n same-sized images -> one SiftResult per image.  With several devices the batch is split into
     contiguous shards, one host thread per device (no device-to-device traffic, no collective).  The per-image
     results are cut out of each device's own result arrays (sb200_extract_batch_multi_parts: nothing is gathered
@@ -490,8 +511,8 @@ def sift_batch(images, features_limit: Optional[int] = None, devices: Optional[S
     devices = list(devices) if devices else [0]
     n, h, w = a.shape
     b = max(1, min(max_batch, n))
-    keys = {(d, w, h, b) for d in devices}
-    exs = [_extractor(w, h, b, d, keep=keys) for d in devices]
+    keys = {(d, w, h, b) if processing is OpenCVProcessing else (d, w, h, b, _flavour(processing)) for d in devices}
+    exs = [_extractor(w, h, b, d, keep=keys, processing=processing) for d in devices]
     lib = _ffi.load()
     lim = -1 if features_limit is None else int(features_limit)
     if len(exs) == 1:

@@ -15,10 +15,18 @@ constexpr int MAX_ORI = ORI_BINS / 2;                // a circular 36-bin histog
 constexpr int DESC_SIZE = 128;
 constexpr int MAX_OCT = 16;
 
-// Blur radii of the six Gaussian kernels (index 0 = seed blur, 1..5 = octave
-// layers): OpenCV ksize = round(8 sigma + 1) | 1 -> 11, 11, 13, 17, 21, 27 taps.
-__host__ __device__ constexpr int blur_radius(int l) {
-    return l == 0 ? 5 : l == 1 ? 5 : l == 2 ? 6 : l == 3 ? 8 : l == 4 ? 10 : 13;
+// Processing flavour (the crate's `P: Processing` type parameter, src/lib.rs:76-90): which blur / resize arithmetic
+// builds the pyramid.  0 = OpenCVProcessing (src/opencv_processing.rs, the one the crate's test and snapshots pin),
+// 1 = ImageprocProcessing (src/lib.rs:992-1007, what the crate's sift() defaults to).
+constexpr int FL_OPENCV = 0;
+constexpr int FL_IMAGEPROC = 1;
+
+// Blur radii of the six Gaussian kernels (index 0 = seed blur, 1..5 = octave layers).
+//   OpenCV:    ksize = round(8 sigma + 1) | 1           -> 11, 11, 13, 17, 21, 27 taps
+//   imageproc: radius = ceil(2 sigma), sigma as f32     ->  7,  7,  9,  9, 11, 15 taps
+__host__ __device__ constexpr int blur_radius(int l, int fl = FL_OPENCV) {
+    return fl == FL_OPENCV ? (l == 0 ? 5 : l == 1 ? 5 : l == 2 ? 6 : l == 3 ? 8 : l == 4 ? 10 : 13)
+                           : (l == 0 ? 3 : l == 1 ? 3 : l == 2 ? 4 : l == 3 ? 4 : l == 4 ? 5 : 7);
 }
 constexpr int MAX_TAPS = 27;
 

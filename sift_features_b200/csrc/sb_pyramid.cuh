@@ -11,6 +11,18 @@
 //   * decimation (src/lib.rs:245-248): even rows / even columns of layer 3;
 //   * DoG (src/lib.rs:271-279): G[l+1] - G[l], recomputed on the fly (never stored).
 // The translation unit is compiled with --fmad=false: every FMA below is explicit.
+//
+// Flavour FL_IMAGEPROC (template parameter FL = 1) swaps in the arithmetic of the crate's default Processing
+// (src/lib.rs:992-1007: imageproc::filter::gaussian_blur_f32, image::imageops::resize) as restated by the oracle
+// from the published algorithms of imageproc 0.25 / image 0.25 -- PARITY UNPINNED: those crates' sources are not
+// part of the reference tree and no reference test exercises this flavour:
+//   * blur: taps exp(-x^2 / 2 sigma^2) / (sigma sqrt(2 pi)) in f32, radius ceil(2 sigma), NOT renormalised; horizontal
+//     pass then vertical pass, each acc = 0, acc = acc + x[i] * k[i] left to right / top to bottom (a multiply and an
+//     add, no FMA, no symmetric folding); border = clamp to the edge pixel;
+//   * 2x upsample (resize, FilterType::Triangle): vertical pass then horizontal pass, out = a * wa + b * wb with
+//     (wa, wb) in {(.25, .75), (.75, .25)} and the clamped edge weights renormalised to (1, 0); result clamped to [0, 1];
+//   * decimation (resize, FilterType::Nearest): source pixel floor((d + 0.5) * (n_src / n_dst)) evaluated in f32 (the odd
+//     pixels 2d + 1), result clamped to [0, 1].
 #pragma once
 #include <cuda.h>
 
@@ -22,6 +34,14 @@ namespace sb {
 __constant__ float c_taps[N_LAYERS][32];
 // the same taps duplicated into both halves of a 64-bit operand for the packed f32x2 arithmetic
 __constant__ float2 c_taps2[N_LAYERS][32];
+// the same for flavour FL_IMAGEPROC
+__constant__ float c_taps_b[N_LAYERS][32];
+__constant__ float2 c_taps2_b[N_LAYERS][32];
+
+template <int FL>
+__device__ __forceinline__ float tap(const int l, const int i) { return FL == FL_OPENCV ? c_taps[l][i] : c_taps_b[l][i]; }
+template <int FL>
+__device__ __forceinline__ float2 tap2(const int l, const int i) { return FL == FL_OPENCV ? c_taps2[l][i] : c_taps2_b[l][i]; }
 
 // Blackwell packed single precision (SASS FFMA2 / FADD2 / FMUL2): two independent IEEE round-to-nearest
 // operations per instruction, i.e. the same bits as the scalar fmaf / + / * -- but half the issue slots,
@@ -49,10 +69,22 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
     return d;
 }
 
+// acc + a * k per half with a separately rounded product (the imageproc flavour's accumulation).  Scalar intrinsics:
+// ptxas contracts a mul.rn.f32x2 followed by an add.rn.f32x2 into one FFMA2 (observed in SASS; the explicit rounding
+// modifier does not stop it for the packed forms), which __fmul_rn / __fadd_rn are documented never to allow.
+__device__ __forceinline__ float2 madd_unfused2(const float2 acc, const float2 a, const float2 k) {
+    return make_float2(__fadd_rn(acc.x, __fmul_rn(a.x, k.x)), __fadd_rn(acc.y, __fmul_rn(a.y, k.y)));
+}
+
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
     return i;
+}
+// source index of a filter tap that falls outside the image: BORDER_REFLECT_101 (OpenCV) / clamp to the edge (imageproc)
+template <int FL>
+__device__ __forceinline__ int border_index(const int i, const int n) {
+    return FL == FL_OPENCV ? reflect101(i, n) : min(max(i, 0), n - 1);
 }
 
 // source indices / weight of the 2x bilinear upsample for destination index d (n source samples)
@@ -70,9 +102,9 @@ __device__ __forceinline__ int lerp2x_lo(int d, int n) {
     return s < 0 ? 0 : (s > n - 1 ? n - 1 : s);
 }
 
-template <int L>
+template <int L, int FL = FL_OPENCV>
 struct BlurCfg {
-    static constexpr int R = blur_radius(L);
+    static constexpr int R = blur_radius(L, FL);
     static constexpr int TW = 128, TH = 64;      // output tile
     static constexpr int SH = TH + 2 * R;        // staged rows
     static constexpr int SW = TW + 2 * R;        // staged columns
@@ -104,9 +136,10 @@ struct BlurParams {
 // One kernel for all six Gaussian blurs.  L selects the tap set; SEED fuses
 // u8 -> f32/255 -> 2x bilinear upsample in front of the blur (create_seed_image,
 // src/lib.rs:196-210); DECIMATE also writes the even pixels into the next octave.
-template <int L, bool SEED, bool DECIMATE>
+template <int L, bool SEED, bool DECIMATE, int FL = FL_OPENCV>
 __global__ void __launch_bounds__(256, 2) k_blur(const BlurParams p) {
-    using C = BlurCfg<L>;
+    static_assert(FL == FL_OPENCV || (!SEED && !DECIMATE), "the imageproc flavour upsamples and decimates in its own kernels");
+    using C = BlurCfg<L, FL>;
     constexpr int R = C::R;
     extern __shared__ __align__(16) float smem[];
     float* stage = smem;
@@ -173,8 +206,8 @@ __global__ void __launch_bounds__(256, 2) k_blur(const BlurParams p) {
             int row = idx / C::SW, col = idx - row * C::SW;
             float v = 0.0f;
             if (row < rows_needed && col < cols_needed) {
-                int gy = reflect101(ty0 - R + row, h);
-                int gx = reflect101(tx0 - R + col, w);
+                int gy = border_index<FL>(ty0 - R + row, h);
+                int gx = border_index<FL>(tx0 - R + col, w);
                 v = __ldg(src + (long long)gy * p.pitch + gx);
             }
             stage[row * C::SPITCH + col] = v;
@@ -200,9 +233,10 @@ __global__ void __launch_bounds__(256, 2) k_blur(const BlurParams p) {
                 float out[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    float acc = win[j] * c_taps[L][0];
+                    float acc = win[j] * tap<FL>(L, 0);
 #pragma unroll
-                    for (int i = 1; i <= 2 * R; i++) acc = fmaf(win[j + i], c_taps[L][i], acc);
+                    for (int i = 1; i <= 2 * R; i++)
+                        acc = FL == FL_OPENCV ? fmaf(win[j + i], tap<FL>(L, i), acc) : __fadd_rn(acc, __fmul_rn(win[j + i], tap<FL>(L, i)));
                     out[j] = acc;
                 }
                 float4* ip = reinterpret_cast<float4*>(inter + row * C::IPITCH + seg * 8);
@@ -228,9 +262,16 @@ __global__ void __launch_bounds__(256, 2) k_blur(const BlurParams p) {
             for (int j = 0; j < C::PY + 2 * R; j++) c[j] = inter[(y0 + j) * C::IPITCH + x];
 #pragma unroll
             for (int j = 0; j < C::PY; j++) {
-                float acc = c[j + R] * c_taps[L][R];
+                float acc;
+                if (FL == FL_OPENCV) {
+                    acc = c[j + R] * tap<FL>(L, R);
 #pragma unroll
-                for (int i = 1; i <= R; i++) acc = fmaf(c[j + R + i] + c[j + R - i], c_taps[L][R + i], acc);
+                    for (int i = 1; i <= R; i++) acc = fmaf(c[j + R + i] + c[j + R - i], tap<FL>(L, R + i), acc);
+                } else {
+                    acc = c[j] * tap<FL>(L, 0);
+#pragma unroll
+                    for (int i = 1; i <= 2 * R; i++) acc = __fadd_rn(acc, __fmul_rn(c[j + i], tap<FL>(L, i)));
+                }
                 const int gy = ty0 + y0 + j;
                 if (gy < h && gx < w) {
                     dst[(long long)gy * p.pitch + gx] = acc;
@@ -310,6 +351,75 @@ __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
         else for (int c = 0; c < 4 && 4 * k + c < 2 * W; c++) q[c] = o[c];
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// Flavour FL_IMAGEPROC: the two resizes of the crate's default Processing as kernels of their own.
+//
+// k_upsample2x_b -- image::imageops::resize(.., FilterType::Triangle) for the exact 2x case of src/lib.rs:201-205,
+// fused with the u8 -> f32 / 255 conversion (:198).  The image crate samples vertically first (into an f32 image),
+// then horizontally; for 2x the normalised triangle weights are (.25, .75) / (.75, .25) and (1, 0) at the clamped
+// ends, each output is the sum of at most two products accumulated from zero, and the final value is clamped to
+// [0, 1].  A thread owns one output row and four output columns {4k .. 4k+3} (input columns 2k-1 .. 2k+2).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float tri2x(const float a, const float b, const bool odd, const bool at_end) {
+    // output 2k (odd = false): a = in[k-1], b = in[k];  output 2k+1 (odd = true): a = in[k], b = in[k+1];
+    // at_end: the outer neighbour does not exist and the surviving weight renormalises to exactly 1
+    if (at_end) return odd ? a : b;
+    return odd ? a * 0.75f + b * 0.25f : a * 0.25f + b * 0.75f;
+}
+
+__global__ void __launch_bounds__(256) k_upsample2x_b(const UpsampleParams p) {
+    __shared__ float s_norm[256];
+    s_norm[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;      // output columns 4k .. 4k+3
+    const int Y = blockIdx.y;                                  // output row
+    const long long img = blockIdx.z;
+    const int W = p.in_w, H = p.in_h;
+    if (4 * k >= 2 * W) return;
+    const uint8_t* in = p.in + img * p.in_img_stride;
+    // vertical pass for the four input columns: rows (ky - 1, ky) for an even output row, (ky, ky + 1) for an odd one
+    const int ky = Y >> 1;
+    const bool yodd = Y & 1;
+    const int ya = yodd ? ky : max(ky - 1, 0), yb = yodd ? min(ky + 1, H - 1) : ky;
+    const bool yend = yodd ? (ky == H - 1) : (ky == 0);
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int x = min(max(2 * k - 1 + c, 0), W - 1);
+        v[c] = tri2x(s_norm[in[(long long)ya * p.in_stride + x]], s_norm[in[(long long)yb * p.in_stride + x]], yodd, yend);
+    }
+    // horizontal pass: v[c] is input column 2k - 1 + c
+    float o[4];
+    o[0] = tri2x(v[0], v[1], false, 2 * k == 0);
+    o[1] = tri2x(v[1], v[2], true, 2 * k == W - 1);
+    o[2] = tri2x(v[1], v[2], false, false);          // output 4k+2 exists only when input column 2k+1 does
+    o[3] = tri2x(v[2], v[3], true, 2 * k + 1 == W - 1);
+    float* q = p.dst + img * p.img_stride + (long long)Y * p.pitch + 4 * k;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        if (4 * k + c < 2 * W) q[c] = fminf(fmaxf(o[c], 0.0f), 1.0f);
+}
+
+// k_decimate_b -- image::imageops::resize(.., FilterType::Nearest) to (w/2, h/2) (src/lib.rs:245-248): the box
+// kernel with support 0 keeps the one source pixel floor((d + 0.5) * (n_src / n_dst)), all in f32, clamped to the
+// image; vertical pass, horizontal pass, clamp to [0, 1].
+struct DecimateParams {
+    const float* src;   // layer 3 of the octave, image 0
+    float* dst;         // layer 0 of the next octave, image 0
+    long long img_stride;
+    int w, h, pitch, dw, dh, dpitch;
+};
+__global__ void __launch_bounds__(256) k_decimate_b(const DecimateParams p) {
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+    const long long img = blockIdx.z;
+    if (dx >= p.dw) return;
+    const float ry = (float)p.h / (float)p.dh, rx = (float)p.w / (float)p.dw;
+    const int sy = min(max((int)floorf(((float)dy + 0.5f) * ry), 0), p.h - 1);
+    const int sx = min(max((int)floorf(((float)dx + 0.5f) * rx), 0), p.w - 1);
+    const float v = p.src[img * p.img_stride + (long long)sy * p.pitch + sx];
+    p.dst[img * p.img_stride + (long long)dy * p.dpitch + dx] = fminf(fmaxf(v, 0.0f), 1.0f);
 }
 
 // ---------------------------------------------------------------------------
@@ -536,9 +646,9 @@ __host__ __device__ constexpr int march_tile_w(int l) { return SB_MARCH_TW(l); }
 #define SB_MARCH_SEG(l) 16
 #endif
 
-template <int L>
+template <int L, int FL = FL_OPENCV>
 struct MarchCfg {
-    static constexpr int R = blur_radius(L);
+    static constexpr int R = blur_radius(L, FL);
     static constexpr int RA = (R + 3) / 4 * 4;   // left halo of the box: a TMA box starts on a 16-byte boundary
     static constexpr int XO = RA - R;            // box column of the first element the filter needs
     static constexpr int TW = march_tile_w(L), BH = SB_MARCH_BH(L);   // strip width, rows per band
@@ -569,10 +679,11 @@ struct MarchCfg {
     static_assert((TW / 2) * (BH / PY) == THREADS, "one column-pass task per thread");
 };
 
-template <int L, bool DECIMATE>
-__global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM) k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
+template <int L, bool DECIMATE, int FL = FL_OPENCV>
+__global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTAS_PER_SM) k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
                                                         const int src_layer, const int seg_rows) {
-    using C = MarchCfg<L>;
+    static_assert(FL == FL_OPENCV || !DECIMATE, "the imageproc flavour decimates in its own kernel");
+    using C = MarchCfg<L, FL>;
     constexpr int R = C::R;
     constexpr int STAGE_FLOATS = C::BH * C::BW, SLOT_FLOATS = C::BH * C::IPITCH;
     extern __shared__ __align__(1024) float smem_march[];
@@ -629,7 +740,7 @@ __global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM
                 const int row = idx / C::SW, col = idx - row * C::SW;
                 const int gx = tx0 - R + col;
                 if (gx < 0 || gx >= w) {
-                    const int rx = reflect101(gx, w) - (tx0 - R);
+                    const int rx = border_index<FL>(gx, w) - (tx0 - R);
                     if (rx >= 0 && rx < C::SW) st[row * C::BW + C::XO + col] = st[row * C::BW + C::XO + rx];
                 }
             }
@@ -647,7 +758,7 @@ __global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM
             int srow = row;         // stage row this lane filters
             bool copy_prev = false; // the mirrored row belongs to the previous band: copy its row-pass result from the ring
             if (vedge) {
-                const int yy = reflect101(band_y0 + row, h);
+                const int yy = border_index<FL>(band_y0 + row, h);
                 srow = yy - band_y0;
                 copy_prev = srow < 0;
             }
@@ -682,12 +793,17 @@ __global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM
                         const int ti = i < R ? 2 * R - i : i;
                         if ((sidx & 1) == 0) {
                             const float2 in = make_float2(win[sidx], win[sidx + 1]);
-                            acc[jp] = (i == 0) ? mul2(in, c_taps2[L][ti]) : fma2(in, c_taps2[L][ti], acc[jp]);
+                            if (i == 0) acc[jp] = mul2(in, tap2<FL>(L, ti));
+                            else if (FL == FL_OPENCV) acc[jp] = fma2(in, tap2<FL>(L, ti), acc[jp]);
+                            else acc[jp] = madd_unfused2(acc[jp], in, tap2<FL>(L, ti));
                         } else if (i == 0) {
-                            acc[jp] = make_float2(win[sidx] * c_taps[L][ti], win[sidx + 1] * c_taps[L][ti]);
+                            acc[jp] = make_float2(win[sidx] * tap<FL>(L, ti), win[sidx + 1] * tap<FL>(L, ti));
+                        } else if (FL == FL_OPENCV) {
+                            acc[jp].x = fmaf(win[sidx], tap<FL>(L, ti), acc[jp].x);
+                            acc[jp].y = fmaf(win[sidx + 1], tap<FL>(L, ti), acc[jp].y);
                         } else {
-                            acc[jp].x = fmaf(win[sidx], c_taps[L][ti], acc[jp].x);
-                            acc[jp].y = fmaf(win[sidx + 1], c_taps[L][ti], acc[jp].y);
+                            acc[jp].x = __fadd_rn(acc[jp].x, __fmul_rn(win[sidx], tap<FL>(L, ti)));
+                            acc[jp].y = __fadd_rn(acc[jp].y, __fmul_rn(win[sidx + 1], tap<FL>(L, ti)));
                         }
                     }
                 }
@@ -725,9 +841,16 @@ __global__ void __launch_bounds__(MarchCfg<L>::THREADS, MarchCfg<L>::CTAS_PER_SM
             float2 out[C::PY];
 #pragma unroll
             for (int j = 0; j < C::PY; j++) {
-                float2 acc = mul2(c[j + R], c_taps2[L][R]);
+                float2 acc;
+                if (FL == FL_OPENCV) {
+                    acc = mul2(c[j + R], tap2<FL>(L, R));
 #pragma unroll
-                for (int i = 1; i <= R; i++) acc = fma2(add2(c[j + R + i], c[j + R - i]), c_taps2[L][R + i], acc);
+                    for (int i = 1; i <= R; i++) acc = fma2(add2(c[j + R + i], c[j + R - i]), tap2<FL>(L, R + i), acc);
+                } else {   // top to bottom, a multiply and an add per tap (taps named by their upper-half index)
+                    acc = mul2(c[j], tap2<FL>(L, 2 * R));
+#pragma unroll
+                    for (int i = 1; i <= 2 * R; i++) acc = madd_unfused2(acc, c[j + i], tap2<FL>(L, i < R ? 2 * R - i : i));
+                }
                 out[j] = acc;
             }
             float* q = qband;

@@ -130,6 +130,7 @@ struct sb200_ctx {
     // TMA descriptors of the Gaussian arenas: [slot][octave][destination layer 1..5]
     CUtensorMap tmap[N_SLOTS][MAX_OCT][N_LAYERS];
     CUtensorMap tmap_m[N_SLOTS][MAX_OCT][N_LAYERS];  // marching blur: (BW x 32) boxes
+    int flavour = FL_OPENCV;                   // Processing flavour of the pyramid (sb200_set_processing)
     bool march = true;                         // SB200_BLUR=tile selects the independent-tile TMA blur (debugging aid)
     int seg_rows_override = 0;                 // SB200_SEG_ROWS: fixed segment height of the marching blur (tests)
     bool tail = true;                          // SB200_TAIL=0: per-layer launches for the small octaves too (debugging aid)
@@ -271,6 +272,22 @@ void gaussian_taps(double sigma, float* out, int& ksize) {
     }
     const double inv = 1.0 / sum;
     for (int i = 0; i < ksize; i++) out[i] = (float)(t[i] * inv);
+}
+
+// imageproc 0.25 gaussian_blur_f32(img, sigma as f32) (src/lib.rs:997): kernel radius ceil(2 sigma), taps
+// gaussian_pdf(x) = (sigma * sqrt(2 pi)).recip() * exp(-x^2 / (2 sigma^2)) in f32, NOT renormalised.  Restated from
+// the published algorithm (the imageproc sources are not part of the reference tree): parity unpinned.
+void imageproc_taps(double sigma64, float* out, int& ksize) {
+    const float sigma = (float)sigma64;
+    const int r = (int)ceilf(2.0f * sigma);
+    ksize = 2 * r + 1;
+    const float norm = 1.0f / (sigma * sqrtf(2.0f * 3.14159265358979323846f));
+    for (int i = 0; i <= r; i++) {
+        const float x = (float)i;
+        const float v = norm * expf(-(x * x) / (2.0f * (sigma * sigma)));
+        out[r + i] = v;
+        out[r - i] = v;
+    }
 }
 
 // sigmas of src/lib.rs:207 and :220-229
@@ -461,9 +478,9 @@ int encode_one(sb200_ctx* ctx, int slot, int o) {
     return SB200_OK;
 }
 
-template <int LI>
+template <int LI, int FL>
 int encode_march(sb200_ctx* ctx, int slot, int o) {
-    using C = MarchCfg<LI>;
+    using C = MarchCfg<LI, FL>;
     const OctLayout& ol = ctx->L.o[o];
     const cuuint64_t gdim[4] = {(cuuint64_t)ol.w, (cuuint64_t)ol.h, (cuuint64_t)N_LAYERS, (cuuint64_t)ctx->max_batch};
     const cuuint64_t gstr[3] = {(cuuint64_t)ol.pitch * 4, (cuuint64_t)ol.layer_stride * 4,
@@ -501,11 +518,18 @@ int build_tensor_maps(sb200_ctx* ctx) {
         if (ol.w < TMA_MIN_DIM || ol.h < TMA_MIN_DIM) continue;
         for (int sl = 0; sl < N_SLOTS; sl++) {
             int r;
-            if ((o == 0 && (r = encode_one<0>(ctx, sl, o))) || (r = encode_one<1>(ctx, sl, o)) || (r = encode_one<2>(ctx, sl, o)) || (r = encode_one<3>(ctx, sl, o)) ||
-                (r = encode_one<4>(ctx, sl, o)) || (r = encode_one<5>(ctx, sl, o)) || (r = encode_extrema(ctx, sl, o)) ||
-                (o == 0 && (r = encode_march<0>(ctx, sl, o))) || (r = encode_march<1>(ctx, sl, o)) || (r = encode_march<2>(ctx, sl, o)) ||
-                (r = encode_march<3>(ctx, sl, o)) || (r = encode_march<4>(ctx, sl, o)) || (r = encode_march<5>(ctx, sl, o)))
-                return r;
+            if (ctx->flavour == FL_OPENCV) {
+                if ((o == 0 && (r = encode_one<0>(ctx, sl, o))) || (r = encode_one<1>(ctx, sl, o)) || (r = encode_one<2>(ctx, sl, o)) || (r = encode_one<3>(ctx, sl, o)) ||
+                    (r = encode_one<4>(ctx, sl, o)) || (r = encode_one<5>(ctx, sl, o)) || (r = encode_extrema(ctx, sl, o)) ||
+                    (o == 0 && (r = encode_march<0, FL_OPENCV>(ctx, sl, o))) || (r = encode_march<1, FL_OPENCV>(ctx, sl, o)) || (r = encode_march<2, FL_OPENCV>(ctx, sl, o)) ||
+                    (r = encode_march<3, FL_OPENCV>(ctx, sl, o)) || (r = encode_march<4, FL_OPENCV>(ctx, sl, o)) || (r = encode_march<5, FL_OPENCV>(ctx, sl, o)))
+                    return r;
+            } else {
+                if ((r = encode_extrema(ctx, sl, o)) ||
+                    (o == 0 && (r = encode_march<0, FL_IMAGEPROC>(ctx, sl, o))) || (r = encode_march<1, FL_IMAGEPROC>(ctx, sl, o)) || (r = encode_march<2, FL_IMAGEPROC>(ctx, sl, o)) ||
+                    (r = encode_march<3, FL_IMAGEPROC>(ctx, sl, o)) || (r = encode_march<4, FL_IMAGEPROC>(ctx, sl, o)) || (r = encode_march<5, FL_IMAGEPROC>(ctx, sl, o)))
+                    return r;
+            }
         }
         ctx->tmap_ok[o] = true;
     }
@@ -559,11 +583,18 @@ void launch_blur_tma(cudaStream_t st, const CUtensorMap& tm, const BlurParams& p
     k_blur_tma<LI, DEC><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer);
 }
 
-template <int LI, bool DEC>
+template <int LI, bool DEC, int FL = FL_OPENCV>
 int set_march_attr(sb200_ctx* ctx) {
-    CU(cudaFuncSetAttribute(k_blur_march<LI, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MarchCfg<LI>::SMEM));
-    CU(cudaFuncSetAttribute(k_blur_march<LI, DEC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_blur_march<LI, DEC, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MarchCfg<LI, FL>::SMEM));
+    CU(cudaFuncSetAttribute(k_blur_march<LI, DEC, FL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return SB200_OK;
+}
+
+template <int LI>
+int set_imageproc_attrs(sb200_ctx* ctx) {
+    CU(cudaFuncSetAttribute(k_blur<LI, false, false, FL_IMAGEPROC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)BlurCfg<LI, FL_IMAGEPROC>::SMEM));
+    return set_march_attr<LI, false, FL_IMAGEPROC>(ctx);
 }
 
 // rows per vertical segment of the marching blur.  Taller segments amortise the per-CTA start (first TMA round
@@ -594,12 +625,24 @@ int march_seg_rows(const sb200_ctx* ctx, int w, int h, uint32_t n, int tile_w, i
     return best_rows;
 }
 
-template <int LI, bool DEC>
+template <int LI, bool DEC, int FL = FL_OPENCV>
 void launch_blur_march(sb200_ctx* ctx, cudaStream_t st, const CUtensorMap& tm, const BlurParams& p, uint32_t n, int src_layer) {
-    using C = MarchCfg<LI>;
+    using C = MarchCfg<LI, FL>;
     const int seg = march_seg_rows(ctx, p.w, p.h, n, C::TW, C::CTAS_PER_SM);
     dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + seg - 1) / seg, n);
-    k_blur_march<LI, DEC><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer, seg);
+    k_blur_march<LI, DEC, FL><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer, seg);
+}
+
+// one blur of the imageproc flavour: marching TMA kernel for octaves that own a tensor map, generic tiles otherwise
+template <int LI>
+void launch_blur_imageproc(sb200_ctx* ctx, Slot& s, cudaStream_t st, int o, const BlurParams& p, uint32_t n, int src_layer) {
+    if (ctx->tmap_ok[o] && ctx->march) {
+        launch_blur_march<LI, false, FL_IMAGEPROC>(ctx, st, ctx->tmap_m[s.index][o][LI], p, n, src_layer);
+    } else {
+        using C = BlurCfg<LI, FL_IMAGEPROC>;
+        dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + C::TH - 1) / C::TH, n);
+        k_blur<LI, false, false, FL_IMAGEPROC><<<grid, C::THREADS, C::SMEM, st>>>(p);
+    }
 }
 
 template <bool KEEP_FLAT>
@@ -622,9 +665,93 @@ int tail_first_octave(const sb200_ctx* ctx) {
     return o;
 }
 
+// The pyramid in the arithmetic of the crate's default Processing (ImageprocProcessing, src/lib.rs:992-1007): the same
+// stages as below with the imageproc tap sets / clamp borders, the image crate's two resizes as kernels of their own,
+// every octave through the per-layer launches (no fused tail).  The extrema scan and everything after it do not
+// depend on the flavour.
+int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, uint32_t in_stride,
+                              uint64_t in_img_stride, const uint8_t* d_in) {
+    const PyrLayout& L = ctx->L;
+    cudaStream_t st = s.stream;
+    CU(cudaMemsetAsync(s.d_rows, 0, (size_t)L.img_rows * n * sizeof(uint32_t), st));
+    auto blur_params = [&](int o, int src_layer, int dst_layer) {
+        const OctLayout& ol = L.o[o];
+        BlurParams p{};
+        p.src = s.d_gauss + ol.off + (long long)src_layer * ol.layer_stride;
+        p.dst = s.d_gauss + ol.off + (long long)dst_layer * ol.layer_stride;
+        p.img_stride = L.img_floats;
+        p.w = ol.w; p.h = ol.h; p.pitch = ol.pitch;
+        return p;
+    };
+    {
+        StageScope sc(ctx, st, SB200_STAGE_SEED);
+        StageScope fine(ctx, st, SB200_STAGE_COUNT + 0);
+        // upsample into layer 5 of octave 0 (free until the last blur of the octave overwrites it), seed blur into layer 0
+        UpsampleParams u{};
+        u.in = d_in; u.in_img_stride = (long long)in_img_stride;
+        u.in_w = (int)w; u.in_h = (int)h; u.in_stride = (int)in_stride;
+        u.dst = s.d_gauss + L.o[0].off + 5 * L.o[0].layer_stride;
+        u.img_stride = L.img_floats; u.pitch = L.o[0].pitch;
+        dim3 grid((((int)w + 1) / 2 + 255) / 256, 2 * h, n);
+        k_upsample2x_b<<<grid, 256, 0, st>>>(u);
+        launch_blur_imageproc<0>(ctx, s, st, 0, blur_params(0, 5, 0), n, 5);
+        count_launch(ctx, SB200_STAGE_SEED, 2);
+    }
+    for (int o = 0; o < L.n_oct; o++) {
+        const OctLayout& ol = L.o[o];
+        if (ol.w < 1 || ol.h < 1) continue;
+        {
+            StageScope sc(ctx, st, SB200_STAGE_BLUR);
+            for (int l = 1; l < N_LAYERS; l++) {
+                {
+                    StageScope fine(ctx, st, SB200_STAGE_COUNT + o * 8 + l);
+                    const BlurParams p = blur_params(o, l - 1, l);
+                    switch (l) {
+                        case 1: launch_blur_imageproc<1>(ctx, s, st, o, p, n, 0); break;
+                        case 2: launch_blur_imageproc<2>(ctx, s, st, o, p, n, 1); break;
+                        case 3: launch_blur_imageproc<3>(ctx, s, st, o, p, n, 2); break;
+                        case 4: launch_blur_imageproc<4>(ctx, s, st, o, p, n, 3); break;
+                        default: launch_blur_imageproc<5>(ctx, s, st, o, p, n, 4); break;
+                    }
+                    count_launch(ctx, SB200_STAGE_BLUR);
+                }
+                if (l == 3 && o + 1 < L.n_oct && L.o[o + 1].w >= 1 && L.o[o + 1].h >= 1) {
+                    DecimateParams d{};
+                    d.src = s.d_gauss + ol.off + 3 * ol.layer_stride;
+                    d.dst = s.d_gauss + L.o[o + 1].off;
+                    d.img_stride = L.img_floats;
+                    d.w = ol.w; d.h = ol.h; d.pitch = ol.pitch;
+                    d.dw = L.o[o + 1].w; d.dh = L.o[o + 1].h; d.dpitch = L.o[o + 1].pitch;
+                    k_decimate_b<<<dim3((d.dw + 255) / 256, d.dh, n), 256, 0, st>>>(d);
+                    count_launch(ctx, SB200_STAGE_BLUR);
+                }
+            }
+        }
+        if (ol.scanned) {
+            StageScope sc(ctx, st, SB200_STAGE_EXTREMA);
+            StageScope fine(ctx, st, SB200_STAGE_COUNT + o * 8 + 6);
+            ExtremaParams e{};
+            e.gauss = s.d_gauss + ol.off;
+            e.img_stride = L.img_floats;
+            e.layer_stride = ol.layer_stride;
+            e.w = ol.w; e.h = ol.h; e.pitch = ol.pitch;
+            e.mask = s.d_mask + ol.mask_off;
+            e.mask_img_stride = L.img_mask_words;
+            e.mask_pitch = ol.mask_pitch;
+            e.rows = s.d_rows + ol.row_base;
+            e.rows_img_stride = L.img_rows;
+            launch_extrema<false>(ctx, st, s.index, o, e, n);
+            count_launch(ctx, SB200_STAGE_EXTREMA);
+        }
+    }
+    CU(cudaGetLastError());
+    return SB200_OK;
+}
+
 // Gaussian scale space + DoG/extrema masks for the n images staged in slot.d_in
 int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, uint32_t in_stride,
                     uint64_t in_img_stride, const uint8_t* d_in) {
+    if (ctx->flavour == FL_IMAGEPROC) return enqueue_pyramid_imageproc(ctx, s, n, w, h, in_stride, in_img_stride, d_in);
     const PyrLayout& L = ctx->L;
     cudaStream_t st = s.stream;
     CU(cudaMemsetAsync(s.d_rows, 0, (size_t)L.img_rows * n * sizeof(uint32_t), st));
@@ -1265,7 +1392,24 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
                 for (int i = 0; i < 32; i++) taps2[l][i] = make_float2(taps[l][i], taps[l][i]);
             CU(cudaMemcpyToSymbol(c_taps2, taps2, sizeof taps2));
         }
+        {   // the imageproc flavour's tap sets
+            float tb[N_LAYERS][32];
+            float2 tb2[N_LAYERS][32];
+            memset(tb, 0, sizeof tb);
+            for (int l = 0; l < N_LAYERS; l++) {
+                int ks = 0;
+                imageproc_taps(l == 0 ? seed_sigma() : octave_sigma(l), tb[l], ks);
+                if (ks != 2 * blur_radius(l, FL_IMAGEPROC) + 1)
+                    return fail(ctx, SB200_E_INVALID, "internal: tap count %d of imageproc kernel %d", ks, l);
+                for (int i = 0; i < 32; i++) tb2[l][i] = make_float2(tb[l][i], tb[l][i]);
+            }
+            CU(cudaMemcpyToSymbol(c_taps_b, tb, sizeof tb));
+            CU(cudaMemcpyToSymbol(c_taps2_b, tb2, sizeof tb2));
+        }
         int r;
+        if ((r = set_imageproc_attrs<0>(ctx)) || (r = set_imageproc_attrs<1>(ctx)) || (r = set_imageproc_attrs<2>(ctx)) ||
+            (r = set_imageproc_attrs<3>(ctx)) || (r = set_imageproc_attrs<4>(ctx)) || (r = set_imageproc_attrs<5>(ctx)))
+            return r;
         if ((r = set_blur_attr<0, true, false>(ctx))) return r;
         if ((r = set_blur_attr<1, false, false>(ctx))) return r;
         if ((r = set_blur_attr<2, false, false>(ctx))) return r;
@@ -1362,6 +1506,29 @@ void sb200_destroy(sb200_ctx* ctx) {
     for (int i = 0; i < 2; i++) { cudaFree(ctx->d_mdesc[i]); cudaFree(ctx->d_mnorm[i]); cudaFree(ctx->d_mnbp[i]); cudaFree(ctx->d_mbest[i]); }
     cudaFree(ctx->d_mout); cudaFree(ctx->d_mcount);
     delete ctx;
+}
+
+int sb200_set_processing(sb200_ctx* ctx, int processing) {
+    if (!ctx) return SB200_E_INVALID;
+    if (processing != SB200_PROCESSING_OPENCV && processing != SB200_PROCESSING_IMAGEPROC)
+        return fail(ctx, SB200_E_INVALID, "unknown processing flavour %d", processing);
+    CU(cudaSetDevice(ctx->device));
+    if (processing == ctx->flavour) return SB200_OK;
+    for (auto& t : ctx->slot) {
+        CU(cudaStreamSynchronize(t.stream));
+        CU(cudaStreamSynchronize(t.side));
+        for (auto& g : t.graphs) cudaGraphExecDestroy(g.exec);   // captured with the other flavour's kernels
+        t.graphs.clear();
+        t.busy = false;
+    }
+    ctx->flavour = processing == SB200_PROCESSING_IMAGEPROC ? FL_IMAGEPROC : FL_OPENCV;
+    ctx->cur_w = ctx->cur_h = 0;   // the marching blur's TMA boxes depend on the tap radius: rebuilt at the next call
+    ctx->have_pyramid = ctx->have_single = false;
+    return SB200_OK;
+}
+
+int sb200_get_processing(const sb200_ctx* ctx) {
+    return !ctx ? -SB200_E_INVALID : ctx->flavour == FL_IMAGEPROC ? SB200_PROCESSING_IMAGEPROC : SB200_PROCESSING_OPENCV;
 }
 
 static int extract_batch_impl(sb200_ctx* ctx, const Source& src, uint32_t n, uint32_t w, uint32_t h, int64_t features_limit,

@@ -260,7 +260,7 @@ def test_concurrent_contexts(sf):
     device at once give what each gives alone."""
     import threading
     imgs = [noise_image(320 + 32 * i, 240, 700 + i) for i in range(4)]
-    alone = [sf.sift(g) for g in imgs]
+    alone = [sf.sift_with_processing(g) for g in imgs]
     got, errs = [None] * 4, []
 
     def work(i):
@@ -336,7 +336,7 @@ def test_opencv_cross_match(sf):
     cv2 = pytest.importorskip("cv2")
     g = load_gray("bird")
     ckp, cdesc = cv2.SIFT_create().detectAndCompute(g, None)
-    res = sf.sift(g)
+    res = sf.sift_with_processing(g, None, sf.OpenCVProcessing)
     m = cv2.BFMatcher(cv2.NORM_L2, True).match(res.descriptors.astype(np.float32), cdesc)
     assert len(m) >= 0.9 * min(len(res), len(ckp))
     ka = res.keypoint_array
@@ -435,9 +435,9 @@ def test_precomputed_images_are_owned(sf, oracle):
     raises instead of returning the other image's results."""
     a, b = noise_image(128, 96, 1), noise_image(128, 96, 2)
     pre = sf.precompute_images(a)
-    rb = sf.sift(b)                                               # same shape: the module-level cache's context
+    rb = sf.sift_with_processing(b)                               # same shape: the module-level cache's context
     ra = sf.sift_with_precomputed(pre)
-    assert ra == sf.sift(a) and not (ra == rb)
+    assert ra == sf.sift_with_processing(a) and not (ra == rb)
     assert np.array_equal(pre.scale_space[0][0].view(np.uint32), oracle.Pyramid(a).gauss(0, 0).view(np.uint32))
     pre.close()
     with sf.Extractor(128, 96, 1) as ex:
