@@ -117,6 +117,17 @@ int sb200_device_count(void);
 int sb200_set_processing(sb200_ctx* ctx, int processing);
 int sb200_get_processing(const sb200_ctx* ctx);   /* the flavour, or a negative status */
 
+/* ---- optional OpenCV-style post-filters of the host results ----
+ * What cv::SIFT::detectAndCompute does after detection and the crate does not (the comparison target of the crate's
+ * own bench, benches/sift.rs:99-113 `opencv_sift`): remove_duplicates != 0 drops keypoints that repeat (x, y, size,
+ * angle) of another one (KeyPointsFilter::removeDuplicatedSorted; the survivors come out in its sorted order: x, y
+ * ascending, size descending, angle ascending); retain_best = n >= 0 keeps, when more than n remain, every keypoint
+ * whose response is at least the n-th largest (KeyPointsFilter::retainBest: ties at the boundary survive), in the
+ * order the first step left; retain_best < 0 switches it off.  Both are off by default (the crate's behaviour) and
+ * apply to the host-result entry points (extract, extract_batch*, extract_precomputed), not to device-resident
+ * results.  Independent of features_limit, which is the crate's own truncation (strongest first). */
+int sb200_set_postfilter(sb200_ctx* ctx, int remove_duplicates, int64_t retain_best);
+
 /* ---- extraction: sift_with_processing::<P>() with the context's flavour P ----
  * src/lib.rs:71-81.  features_limit < 0 means None.  (The crate's sift() is sift_with_processing::<ImageprocProcessing>;
  * the host mirrors -- Python, C++, Rust -- select that flavour for their sift().) */

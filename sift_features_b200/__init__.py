@@ -158,6 +158,8 @@ class Extractor:
         if st != _ffi.OK:
             raise SiftError(st, "re-creating the context with a larger capacity failed")
         self._check(self._lib.sb200_set_processing(self._h, _flavour(self.processing)))
+        if getattr(self, "_postfilter", None):
+            self.set_postfilter(*self._postfilter)
         self.max_keypoints_per_image = cap
         return True
 
@@ -169,6 +171,13 @@ class Extractor:
                 continue
             self._check(st)
             return
+
+    def set_postfilter(self, remove_duplicates: bool = False, retain_best: Optional[int] = None):
+        """OpenCV-style post-filters of the host results (sb200_set_postfilter): what cv::SIFT does after detection
+        and the crate does not -- KeyPointsFilter::removeDuplicatedSorted and retainBest(n).  Off by default."""
+        self._postfilter = (bool(remove_duplicates), retain_best)
+        self._check(self._lib.sb200_set_postfilter(self._h, int(bool(remove_duplicates)),
+                                                   -1 if retain_best is None else int(retain_best)))
 
     # -- plumbing ---------------------------------------------------------
     @property

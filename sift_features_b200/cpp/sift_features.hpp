@@ -39,18 +39,30 @@ struct GrayImageView {
     uint32_t width, height, stride;
 };
 
+// src/lib.rs:86-90: the blur / resize implementation the pyramid is built with.  The crate's trait has three
+// associated functions and static dispatch; here an implementation is a tag type whose FLAVOUR selects the device
+// kernels (sb200_set_processing).
+struct OpenCVProcessing {     // src/opencv_processing.rs:39-74 -- the flavour the crate's test and snapshots pin
+    static constexpr int FLAVOUR = SB200_PROCESSING_OPENCV;
+};
+struct ImageprocProcessing {  // src/lib.rs:992-1007 -- the crate's default; restated, parity unpinned
+    static constexpr int FLAVOUR = SB200_PROCESSING_IMAGEPROC;
+};
+
 // One context per (thread, device); owns the device arenas.  Not re-entrant.
 class Extractor {
 public:
-    Extractor(uint32_t max_w, uint32_t max_h, uint32_t max_batch = 1, int device = 0) {
+    Extractor(uint32_t max_w, uint32_t max_h, uint32_t max_batch = 1, int device = 0,
+              int processing = SB200_PROCESSING_OPENCV) {
         int st = sb200_create(device, max_w, max_h, max_batch, 0, &ctx_);
         if (st) throw Error(st, std::string("sb200_create: ") + sb200_status_string(st));
+        check(sb200_set_processing(ctx_, processing));
     }
     ~Extractor() { sb200_destroy(ctx_); }
     Extractor(const Extractor&) = delete;
     Extractor& operator=(const Extractor&) = delete;
 
-    // sift / sift_with_processing::<OpenCVProcessing>, src/lib.rs:71-81
+    // sift_with_processing::<P> with the context's flavour P, src/lib.rs:76-81
     SiftResult sift(const GrayImageView& img, std::optional<size_t> features_limit = std::nullopt) {
         sb200_result r{};
         check(sb200_extract(ctx_, img.data, img.width, img.height, img.stride,
@@ -85,6 +97,21 @@ public:
     void precompute_images(const GrayImageView& img) {
         check(sb200_precompute(ctx_, img.data, img.width, img.height, img.stride));
     }
+    // PrecomputedImages accessors, src/lib.rs:124-128: octave count / sizes and the (6,h,w) Gaussian or (5,h,w) DoG
+    // stack of one octave, row-major
+    uint32_t n_octaves() {
+        uint32_t n = 0;
+        check(sb200_pyramid_info(ctx_, &n, nullptr, nullptr, 0));
+        return n;
+    }
+    std::pair<uint32_t, uint32_t> octave_size(uint32_t octave) {
+        uint32_t n = 0, w[SB200_MAX_OCTAVES] = {0}, h[SB200_MAX_OCTAVES] = {0};
+        check(sb200_pyramid_info(ctx_, &n, w, h, SB200_MAX_OCTAVES));
+        if (octave >= n) throw Error(SB200_E_INVALID, "octave out of range");
+        return {w[octave], h[octave]};
+    }
+    std::vector<float> scale_space(uint32_t octave) { return stack(octave, 6, sb200_pyramid_layer); }
+    std::vector<float> dog(uint32_t octave) { return stack(octave, 5, sb200_pyramid_dog); }
     // sift_with_precomputed, src/lib.rs:147-177
     SiftResult sift_with_precomputed(std::optional<size_t> features_limit = std::nullopt) {
         sb200_result r{};
@@ -114,6 +141,13 @@ private:
     void check(int st) {
         if (st) throw Error(st, sb200_last_error(ctx_));
     }
+    std::vector<float> stack(uint32_t octave, uint32_t layers, int (*fn)(sb200_ctx*, uint32_t, uint32_t, float*)) {
+        const auto wh = octave_size(octave);
+        const size_t px = (size_t)wh.first * wh.second;
+        std::vector<float> out(px * layers);
+        for (uint32_t l = 0; l < layers; l++) check(fn(ctx_, octave, l, out.data() + px * l));
+        return out;
+    }
     static SiftResult take(const sb200_result& r, uint32_t i) {
         SiftResult s;
         const uint64_t a = r.offsets[i], b = r.offsets[i + 1];
@@ -128,10 +162,16 @@ private:
     sb200_ctx* ctx_ = nullptr;
 };
 
-// src/lib.rs:71 as a free function (creates a context sized for this image)
-inline SiftResult sift(const GrayImageView& img, std::optional<size_t> features_limit = std::nullopt) {
-    Extractor ex(img.width, img.height);
+// src/lib.rs:76 as a free function (creates a context sized for this image): sift_with_processing<P>(img, limit)
+template <class P>
+inline SiftResult sift_with_processing(const GrayImageView& img, std::optional<size_t> features_limit = std::nullopt) {
+    Extractor ex(img.width, img.height, 1, 0, P::FLAVOUR);
     return ex.sift(img, features_limit);
+}
+
+// src/lib.rs:71-73: the crate's sift() is sift_with_processing::<ImageprocProcessing>
+inline SiftResult sift(const GrayImageView& img, std::optional<size_t> features_limit = std::nullopt) {
+    return sift_with_processing<ImageprocProcessing>(img, features_limit);
 }
 
 }  // namespace sift_features

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <functional>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -151,6 +152,9 @@ struct sb200_ctx {
     size_t res_cap = 0;
     uint64_t res_n = 0;
     double last_gather_ms = 0.0;   // host time of the dense gather of the last sb200_extract_batch_multi
+    // optional OpenCV-style post-filters of the host results (sb200_set_postfilter)
+    bool pf_dedup = false;
+    int64_t pf_retain = -1;
     // staged API state
     bool have_pyramid = false;
     bool have_single = false;  // slot[0] holds the intermediates of a single-image run
@@ -1288,7 +1292,83 @@ int collect_group(sb200_ctx* ctx, Slot& s) {
     return SB200_OK;
 }
 
+// OpenCV-style post-filters of the host result (cv::SIFT::detectAndCompute: KeyPointsFilter::removeDuplicatedSorted,
+// then retainBest when nfeatures > 0; the comparison target of benches/sift.rs:99-113).  Host code on the pinned
+// result arrays, per image, a few threads over the images of a batch:
+//   * remove_duplicates: keypoints sorted by (x asc, y asc, size desc, angle asc, response desc, natural index) and
+//     those equal to their predecessor in (x, y, size, angle) dropped -- the crate keeps such duplicates (two initial
+//     extrema converging on one refined point), OpenCV does not;
+//   * retain_best n: when more than n remain, every keypoint whose response is >= the n-th largest response is kept
+//     (ties at the boundary survive, as in OpenCV), in the order the previous step left.
+void apply_postfilter(sb200_ctx* ctx, uint32_t n_images) {
+    if (!ctx->pf_dedup && ctx->pf_retain < 0) return;
+    if (ctx->res_n == 0) return;
+    std::vector<std::vector<uint32_t>> keep(n_images);
+    auto one = [&](uint32_t im) {
+        const uint64_t a = ctx->h_offsets[im], b = ctx->h_offsets[im + 1];
+        const sb200_keypoint* k = ctx->h_kps + a;
+        std::vector<uint32_t>& idx = keep[im];
+        idx.resize(b - a);
+        for (uint32_t i = 0; i < idx.size(); i++) idx[i] = i;
+        if (ctx->pf_dedup && idx.size() > 1) {
+            std::sort(idx.begin(), idx.end(), [k](uint32_t i, uint32_t j) {
+                const sb200_keypoint &p = k[i], &q = k[j];
+                if (p.x != q.x) return p.x < q.x;
+                if (p.y != q.y) return p.y < q.y;
+                if (p.size != q.size) return p.size > q.size;
+                if (p.angle != q.angle) return p.angle < q.angle;
+                if (p.response != q.response) return p.response > q.response;
+                return i < j;
+            });
+            size_t m = 0;
+            for (size_t j = 1; j < idx.size(); j++) {
+                const sb200_keypoint &p = k[idx[m]], &q = k[idx[j]];
+                if (p.x != q.x || p.y != q.y || p.size != q.size || p.angle != q.angle) idx[++m] = idx[j];
+            }
+            idx.resize(m + 1);
+        }
+        if (ctx->pf_retain >= 0 && idx.size() > (uint64_t)ctx->pf_retain) {
+            if (ctx->pf_retain == 0) { idx.clear(); return; }
+            std::vector<float> r(idx.size());
+            for (size_t j = 0; j < idx.size(); j++) r[j] = k[idx[j]].response;
+            std::nth_element(r.begin(), r.begin() + (ctx->pf_retain - 1), r.end(), std::greater<float>());
+            const float thr = r[ctx->pf_retain - 1];
+            size_t m = 0;
+            for (size_t j = 0; j < idx.size(); j++) if (k[idx[j]].response >= thr) idx[m++] = idx[j];
+            idx.resize(m);
+        }
+    };
+    {
+        std::atomic<uint32_t> next{0};
+        auto work = [&]() { for (uint32_t im = next.fetch_add(1); im < n_images; im = next.fetch_add(1)) one(im); };
+        const unsigned hw = std::thread::hardware_concurrency();
+        const uint32_t nt = std::min<uint32_t>({n_images, std::max(1u, std::min(hw ? hw : 4u, 16u)), (uint32_t)(ctx->res_n / 4096 + 1)});
+        std::vector<std::thread> th;
+        for (uint32_t t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+    }
+    // compaction towards the front, image by image (a destination never runs ahead of its source)
+    std::vector<sb200_keypoint> tk;
+    std::vector<uint8_t> td;
+    uint64_t pos = 0;
+    for (uint32_t im = 0; im < n_images; im++) {
+        const uint64_t a = ctx->h_offsets[im], b = ctx->h_offsets[im + 1];
+        tk.assign(ctx->h_kps + a, ctx->h_kps + b);
+        td.assign(ctx->h_desc + a * SB200_DESC_SIZE, ctx->h_desc + b * SB200_DESC_SIZE);
+        ctx->h_offsets[im] = pos;
+        for (uint32_t i : keep[im]) {
+            ctx->h_kps[pos] = tk[i];
+            memcpy(ctx->h_desc + pos * SB200_DESC_SIZE, td.data() + (size_t)i * SB200_DESC_SIZE, SB200_DESC_SIZE);
+            pos++;
+        }
+    }
+    ctx->h_offsets[n_images] = pos;
+    ctx->res_n = pos;
+}
+
 void fill_result(sb200_ctx* ctx, uint32_t n_images, sb200_result* out) {
+    apply_postfilter(ctx, n_images);
     out->n = ctx->res_n;
     out->n_images = n_images;
     out->offsets = ctx->h_offsets;
@@ -1524,6 +1604,13 @@ int sb200_set_processing(sb200_ctx* ctx, int processing) {
     ctx->flavour = processing == SB200_PROCESSING_IMAGEPROC ? FL_IMAGEPROC : FL_OPENCV;
     ctx->cur_w = ctx->cur_h = 0;   // the marching blur's TMA boxes depend on the tap radius: rebuilt at the next call
     ctx->have_pyramid = ctx->have_single = false;
+    return SB200_OK;
+}
+
+int sb200_set_postfilter(sb200_ctx* ctx, int remove_duplicates, int64_t retain_best) {
+    if (!ctx) return SB200_E_INVALID;
+    ctx->pf_dedup = remove_duplicates != 0;
+    ctx->pf_retain = retain_best < 0 ? -1 : retain_best;
     return SB200_OK;
 }
 

@@ -4,7 +4,7 @@
 //! `libsift_b200.so` (C ABI: include/sift_b200.h).  NOT compiled in the build image (no rustc); kept as
 //! the reference-side binding described in INTEGRATION.md.
 use image::GrayImage;
-use ndarray::{Array2, ArrayView2};
+use ndarray::{Array2, Array3, ArrayView2};
 use std::os::raw::{c_char, c_int};
 
 #[repr(C)]
@@ -48,6 +48,10 @@ extern "C" {
     fn sb200_create(device: c_int, max_w: u32, max_h: u32, max_batch: u32, max_kp: u32, out: *mut *mut Sb200Ctx) -> c_int;
     fn sb200_destroy(ctx: *mut Sb200Ctx);
     fn sb200_last_error(ctx: *const Sb200Ctx) -> *const c_char;
+    fn sb200_set_processing(ctx: *mut Sb200Ctx, processing: c_int) -> c_int;
+    fn sb200_pyramid_info(ctx: *mut Sb200Ctx, n_octaves: *mut u32, widths: *mut u32, heights: *mut u32, cap: u32) -> c_int;
+    fn sb200_pyramid_layer(ctx: *mut Sb200Ctx, octave: u32, layer: u32, out: *mut f32) -> c_int;
+    fn sb200_pyramid_dog(ctx: *mut Sb200Ctx, octave: u32, layer: u32, out: *mut f32) -> c_int;
     fn sb200_extract(ctx: *mut Sb200Ctx, gray: *const u8, w: u32, h: u32, stride: u32, limit: i64, out: *mut Sb200Result) -> c_int;
     fn sb200_precompute(ctx: *mut Sb200Ctx, gray: *const u8, w: u32, h: u32, stride: u32) -> c_int;
     fn sb200_extract_precomputed(ctx: *mut Sb200Ctx, limit: i64, out: *mut Sb200Result) -> c_int;
@@ -97,15 +101,38 @@ pub fn sift_jpeg(jpeg: &[u8], features_limit: Option<usize>) -> SiftResult {
     Context::take(unsafe { &r.assume_init() })
 }
 
+/// `src/lib.rs:86-90`: the blur / resize implementation the pyramid is built with.  In the crate the trait has three
+/// associated functions; here the arithmetic runs in device kernels and an implementation only names its flavour
+/// (`sb200_set_processing`).
+pub trait Processing {
+    const FLAVOUR: c_int;
+}
+/// `src/lib.rs:992-1007`: imageproc `gaussian_blur_f32`, image `resize` (Triangle / Nearest) -- the crate's default.
+/// Restated from the crates' published algorithms; parity unpinned.
+pub struct ImageprocProcessing;
+impl Processing for ImageprocProcessing {
+    const FLAVOUR: c_int = 1;
+}
+/// `src/opencv_processing.rs:39-74`: OpenCV `GaussianBlur` / `resize` -- the flavour the crate's test and snapshots pin.
+pub struct OpenCVProcessing;
+impl Processing for OpenCVProcessing {
+    const FLAVOUR: c_int = 0;
+}
+
 /// One context per (thread, device); owns the device arenas.
 pub struct Context(*mut Sb200Ctx);
 
 impl Context {
     pub fn new(max_w: u32, max_h: u32) -> Self {
+        Self::with_processing::<OpenCVProcessing>(max_w, max_h)
+    }
+    pub fn with_processing<P: Processing>(max_w: u32, max_h: u32) -> Self {
         let mut p = std::ptr::null_mut();
         let st = unsafe { sb200_create(0, max_w, max_h, 1, 0, &mut p) };
         assert!(st == 0, "sb200_create failed with status {st} (no CUDA device? there is no CPU fallback)");
-        Context(p)
+        let ctx = Context(p);
+        ctx.check(unsafe { sb200_set_processing(ctx.0, P::FLAVOUR) });
+        ctx
     }
     fn check(&self, st: c_int) {
         if st != 0 {
@@ -136,22 +163,50 @@ impl Drop for Context {
     }
 }
 
-/// Device-resident pyramid of the last `precompute_images` (src/lib.rs:124-128).
+/// `src/lib.rs:124-128`: the Gaussian scale space and the DoG stacks of one image, octave by octave, as
+/// `(6, h, w)` / `(5, h, w)` arrays.  The arrays are host copies of the device-resident pyramid, which stays in the
+/// context for `sift_with_precomputed`.
 pub struct PrecomputedImages {
     ctx: Context,
+    pub scale_space: Vec<Array3<f32>>,
+    pub dog: Vec<Array3<f32>>,
+    pub n_octaves: usize,
 }
 
-/// src/lib.rs:71 (OpenCVProcessing flavour: the one the crate's test and snapshots pin).
+fn download_stack(ctx: &Context, octave: u32, layers: usize, w: usize, h: usize,
+                  f: unsafe extern "C" fn(*mut Sb200Ctx, u32, u32, *mut f32) -> c_int) -> Array3<f32> {
+    let mut buf = vec![0f32; layers * h * w];
+    for l in 0..layers {
+        ctx.check(unsafe { f(ctx.0, octave, l as u32, buf[l * h * w..].as_mut_ptr()) });
+    }
+    Array3::from_shape_vec((layers, h, w), buf).unwrap()
+}
+
+/// src/lib.rs:71-73: `sift_with_processing::<ImageprocProcessing>(img, features_limit)`, as in the crate.
 pub fn sift(img: &GrayImage, features_limit: Option<usize>) -> SiftResult {
-    Context::new(img.width(), img.height()).sift(img, features_limit)
+    sift_with_processing::<ImageprocProcessing>(img, features_limit)
 }
 
-/// src/lib.rs:131
-pub fn precompute_images(img: &GrayImage) -> PrecomputedImages {
-    let ctx = Context::new(img.width(), img.height());
+/// src/lib.rs:76-81
+pub fn sift_with_processing<P: Processing>(img: &GrayImage, features_limit: Option<usize>) -> SiftResult {
+    Context::with_processing::<P>(img.width(), img.height()).sift(img, features_limit)
+}
+
+/// src/lib.rs:131-143
+pub fn precompute_images<P: Processing>(img: &GrayImage) -> PrecomputedImages {
+    let ctx = Context::with_processing::<P>(img.width(), img.height());
     let st = unsafe { sb200_precompute(ctx.0, img.as_raw().as_ptr(), img.width(), img.height(), img.width()) };
     ctx.check(st);
-    PrecomputedImages { ctx }
+    let (mut n, mut ws, mut hs) = (0u32, [0u32; 16], [0u32; 16]);
+    ctx.check(unsafe { sb200_pyramid_info(ctx.0, &mut n, ws.as_mut_ptr(), hs.as_mut_ptr(), 16) });
+    let mut scale_space = Vec::with_capacity(n as usize);
+    let mut dog = Vec::with_capacity(n as usize);
+    for o in 0..n {
+        let (w, h) = (ws[o as usize] as usize, hs[o as usize] as usize);
+        scale_space.push(download_stack(&ctx, o, 6, w, h, sb200_pyramid_layer));
+        dog.push(download_stack(&ctx, o, 5, w, h, sb200_pyramid_dog));
+    }
+    PrecomputedImages { ctx, scale_space, dog, n_octaves: n as usize }
 }
 
 /// src/lib.rs:147

@@ -71,8 +71,11 @@ def test_invalid_arguments_rejected_before_any_device_work(sf):
     assert lib.sb200_extract(None, None, 1, 1, 1, -1, None) == _ffi.E_INVALID
     with pytest.raises(ValueError):
         sf.sift(np.zeros((4, 4), np.float32))
-    with pytest.raises(NotImplementedError):
-        sf.sift_with_processing(np.zeros((4, 4), np.uint8), None, sf.ImageprocProcessing)
+    with pytest.raises(ValueError):                                              # not a Processing implementation
+        sf.sift_with_processing(np.zeros((4, 4), np.uint8), None, object)
+    assert lib.sb200_set_processing(None, 0) == _ffi.E_INVALID and lib.sb200_get_processing(None) < 0
+    assert lib.sb200_set_postfilter(None, 1, 10) == _ffi.E_INVALID
+    assert lib.sb200_extract_batch_multi_parts(None, 0, None, 1, 1, 1, 1, 1, -1, None, None) == _ffi.E_INVALID
 
 
 def test_product_never_imports_the_oracle():

@@ -520,3 +520,51 @@ def test_rgb_input(sf, oracle, channels):
     edge = np.repeat(np.repeat(edge, 8, 0), 2, 1)
     with sf.Extractor(16, 8, 1) as ex:
         assert np.array_equal(ex.rgb_to_luma(edge), oracle.rgb_to_luma(edge))
+
+
+def _np_postfilter(kp, dedup, retain):
+    idx = list(range(len(kp)))
+    if dedup and len(idx) > 1:
+        idx.sort(key=lambda i: (kp["x"][i], kp["y"][i], -kp["size"][i], kp["angle"][i], -kp["response"][i], i))
+        out = [idx[0]]
+        for j in idx[1:]:
+            p, q = kp[out[-1]], kp[j]
+            if (p["x"], p["y"], p["size"], p["angle"]) != (q["x"], q["y"], q["size"], q["angle"]):
+                out.append(j)
+        idx = out
+    if retain is not None and len(idx) > retain:
+        if retain == 0:
+            return []
+        thr = np.sort(kp["response"][idx])[::-1][retain - 1]
+        idx = [i for i in idx if kp["response"][i] >= thr]
+    return idx
+
+
+@pytest.mark.parametrize("name", ["bird", "tree_small"])
+def test_opencv_post_filters(sf, name):
+    """The optional OpenCV-style post-filters: duplicate removal and retainBest as
+    cv::SIFT::detectAndCompute applies them -- against a numpy restatement on the unfiltered result (exact) and
+    against cv2.SIFT_create's own keypoint counts (the crate differs from OpenCV by well under 1 % of keypoints)."""
+    cv2 = pytest.importorskip("cv2")
+    g = load_gray(name)
+    with sf.Extractor(g.shape[1], g.shape[0], 2) as ex:
+        plain = ex.sift(g)
+        for dedup, retain in ((True, None), (False, 100), (True, 200), (True, 0), (True, 10 ** 6)):
+            ex.set_postfilter(dedup, retain)
+            got = ex.sift(g)
+            idx = _np_postfilter(plain.keypoint_array, dedup, retain)
+            assert np.array_equal(got.keypoint_array, plain.keypoint_array[idx])
+            assert np.array_equal(got.descriptors, plain.descriptors[idx])
+        ex.set_postfilter(True, None)
+        dd = ex.sift(g)
+        offs, kp, de = ex.sift_batch(np.stack([g, g, g]))         # batches go through the same filter, image by image
+        assert all(np.array_equal(kp[offs[i]:offs[i + 1]], dd.keypoint_array) for i in range(3))
+        ex.set_postfilter(True, 300)
+        best = ex.sift(g)
+        ex.set_postfilter(False, None)
+        assert ex.sift(g) == plain                                # and off again
+    assert len(dd) < len(plain) or name == "bird"                # the crate keeps duplicates, OpenCV does not
+    ncv = len(cv2.SIFT_create().detect(g, None))
+    assert abs(len(dd) - ncv) <= max(3, 0.01 * ncv), (len(dd), ncv)
+    ncv300 = len(cv2.SIFT_create(nfeatures=300).detect(g, None))
+    assert abs(len(best) - ncv300) <= 3, (len(best), ncv300)

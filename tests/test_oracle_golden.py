@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 from scipy.spatial import cKDTree
 
-from conftest import load_gray, load_snapshot, noise_image
+from conftest import assert_golden, load_gray, load_snapshot, noise_image
 
 
 @pytest.mark.parametrize("name,count", [("bird_small", 225), ("tree_small", 1270)])
@@ -28,6 +28,24 @@ def test_snapshot_tolerance(oracle, name, count):
     # descriptors of matched keypoints are close in L2 (512-norm vectors)
     l2 = np.linalg.norm(desc[i4[ok]].astype(float) - sdesc[ok].astype(float), axis=1)
     assert np.median(l2) < 25.0
+
+
+@pytest.mark.parametrize("name", ["bird_small", "tree_small"])
+def test_snapshot_conditional_descriptor_pin(oracle, name):
+    """The tighter pin: golden keypoints that the oracle reproduces to within 0.02 px, 0.5 degrees and 1 % in size
+    must also carry nearly the golden descriptor bytes -- this ties the descriptor arithmetic (not only the detector)
+    to the crate's own golden vectors.  The residual is the +-1 grey level of the other JPEG decoder."""
+    kps, desc = oracle.sift(load_gray(name))
+    assert_golden(name, kps, desc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bird_small", "tree_small"])
+def test_gpu_result_against_crate_snapshots(sf, name):
+    """The same comparison with the CUDA path in the oracle's place: the reference's golden vectors checked against
+    what the GPU returns, directly."""
+    res = sf.sift_with_processing(load_gray(name), None, sf.OpenCVProcessing)
+    assert_golden(name, res.keypoint_array, res.descriptors)
 
 
 @pytest.mark.parametrize("name", ["bird_small", "tree_small"])
