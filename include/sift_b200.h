@@ -148,6 +148,11 @@ int sb200_extract_batch(sb200_ctx* ctx, const uint8_t* gray, uint32_t n, uint32_
 int sb200_extract_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n, uint32_t w,
                                uint32_t h, uint32_t stride, uint64_t image_stride,
                                int64_t features_limit);
+/* The pyramid stages alone (seed, five blurs per octave + decimation, DoG/extrema masks) for a device-resident
+ * batch, on alternating slots like sb200_extract_batch_device: precompute_images (src/lib.rs:131-143) for n images
+ * at once, and the measurement hook behind bench.py's "pyramid_dog pipelined" figure. */
+int sb200_pyramid_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n, uint32_t w, uint32_t h,
+                               uint32_t stride, uint64_t image_stride);
 /* device-side view of the last sb200_extract_batch_device: per-image keypoint
  * counts are copied to `counts` (n entries, host); d_keypoints / d_descriptors
  * receive the device base pointers of the dense, batch-wide result arrays (image
@@ -218,7 +223,8 @@ const char* sb200_jpeg_backend(const sb200_ctx* ctx);
  * neighbours on the GPU (u8 x u8 Gram matrix on the tensor cores, exact integer distances): for every query
  * row the train row with the smallest squared L2 distance (smallest index on ties), kept when the query row
  * is in turn the nearest of that train row.  Matches are written in ascending query order; *n_out receives
- * their number (SB200_E_CAPACITY if it exceeds cap; n_query always suffices). */
+ * their number (SB200_E_CAPACITY if it exceeds cap; n_query always suffices).  Rows of `out` beyond *n_out, up to
+ * min(cap, n_query), are overwritten with unspecified values. */
 int sb200_match_descriptors(sb200_ctx* ctx, const uint8_t* query, uint64_t n_query, const uint8_t* train, uint64_t n_train,
                 sb200_dmatch* out, uint64_t cap, uint64_t* n_out);
 /* device-pointer variant: descriptor matrices already in device memory (16-byte aligned, e.g. the

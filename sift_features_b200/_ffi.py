@@ -23,7 +23,7 @@ FINE_SLOTS = 128
 # every symbol include/sift_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "sb200_create", "sb200_destroy", "sb200_last_error", "sb200_status_string", "sb200_device_count",
-    "sb200_set_processing", "sb200_get_processing", "sb200_set_postfilter", "sb200_extract", "sb200_extract_batch", "sb200_extract_batch_device", "sb200_device_result", "sb200_sync",
+    "sb200_set_processing", "sb200_get_processing", "sb200_set_postfilter", "sb200_extract", "sb200_extract_batch", "sb200_extract_batch_device", "sb200_pyramid_batch_device", "sb200_device_result", "sb200_sync",
     "sb200_precompute", "sb200_extract_precomputed", "sb200_pyramid_info", "sb200_pyramid_layer",
     "sb200_pyramid_dog", "sb200_last_candidates", "sb200_last_sift_keypoints", "sb200_compute_descriptors",
     "sb200_compute_descriptors_device", "sb200_extract_batch_multi", "sb200_extract_batch_multi_parts",
@@ -66,6 +66,7 @@ def load() -> C.CDLL:
         "sb200_extract": (C.c_int, [vp, u8p, u32, u32, u32, i64, C.POINTER(Result)]),
         "sb200_extract_batch": (C.c_int, [vp, u8p, u32, u32, u32, u32, u64, i64, C.POINTER(Result)]),
         "sb200_extract_batch_device": (C.c_int, [vp, vp, u32, u32, u32, u32, u64, i64]),
+        "sb200_pyramid_batch_device": (C.c_int, [vp, vp, u32, u32, u32, u32, u64]),
         "sb200_device_result": (C.c_int, [vp, vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u32)]),
         "sb200_sync": (C.c_int, [vp]),
         "sb200_precompute": (C.c_int, [vp, u8p, u32, u32, u32]),

@@ -11,7 +11,10 @@
 // tcgen05.ld and keep a running (distance, index) minimum per query row while the next stage is being filled.
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocation + MMA issue (one elected lane), tcgen05.commit onto the mbarriers
-//   warps 2..5  : epilogue, warp w owns TMEM lanes 32*(w%4) .. +31 (one query row per thread)
+//   warps 2..9  : epilogue, warp w owns TMEM lanes 32*(w%4) .. +31 (one query row per thread) and one half of the
+//                 tile's 256 columns: two 64-column tcgen05.ld per tile and thread, then per column pair two IMADs
+//                 (256 |b|^2 + column - 512 a.b, signed: the |a|^2 term is constant per row and added at the end)
+//                 and one three-input minimum, with the tile's |b|^2 values staged once in shared memory
 // The kernel is run in both directions (query->train, train->query); k_match_cross keeps the mutual pairs in
 // ascending query order.  Ties resolve to the smallest index (integer distances: deterministic).
 #pragma once
@@ -26,15 +29,20 @@ constexpr int MT_N = 256;        // train rows per tile (UMMA N)
 constexpr int MT_K = 128;        // descriptor bytes == one swizzle-128B row
 constexpr int MT_UK = 32;        // K per tcgen05.mma for 8-bit operands
 constexpr int MT_STAGES = 3;     // train tiles in flight
-constexpr int MT_THREADS = 192;
+constexpr int MT_EPI_WARPS = 8;
+constexpr int MT_THREADS = 64 + 32 * MT_EPI_WARPS;
 constexpr uint32_t MT_A_BYTES = MT_M * MT_K;
 constexpr uint32_t MT_B_BYTES = MT_N * MT_K;
 constexpr size_t MT_SMEM = 1024 + MT_A_BYTES + (size_t)MT_STAGES * MT_B_BYTES;   // 1 KB slack for the 1024-byte alignment
 constexpr uint32_t MT_TMEM_COLS = 512;
 
+// |b|^2 entry of a padding row: larger than any real (|b|^2 << 8) - 512 a.b, so a padding column never wins a minimum
+constexpr uint32_t MT_NBP_PAD = 0x7fffff00u;
+constexpr uint32_t MT_NBP_REAL_MAX = 0x7f800000u;   // real entries are at most (128 * 255^2 << 8) + 255 = 0x7f0080ff
+
 struct MatchParams {
     const uint32_t* norm_a;        // [n_a] |a|^2
-    const uint32_t* nbp;           // [ceil(n_b / MT_N) * MT_N]  (|b|^2 << 8) | (j & 255), zero beyond n_b
+    const uint32_t* nbp;           // [ceil(n_b / MT_N) * MT_N]  (|b|^2 << 8) | (j & 255); MT_NBP_PAD beyond n_b
     uint32_t n_a, n_b;
     uint32_t tiles_per_cta;        // train tiles per CTA: blockIdx.y selects the range (the ranges are merged by atomicMin)
     unsigned long long* best;      // [n_a]  (distance^2 << 32) | argmin j; all-ones before the launch
@@ -80,6 +88,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_nn(const __grid_constan
     uint8_t* const sB = sm + MT_A_BYTES;
     __shared__ __align__(8) uint64_t full_a, full_b[MT_STAGES], empty_b[MT_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) uint32_t s_nbp[2][MT_N];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * MT_M;
     // this CTA's train tiles: [t_first, t_first + n_tiles)
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_nn(const __grid_constan
     if (tid == 0) {
         mbar_init(&full_a, 1);
         for (int s = 0; s < MT_STAGES; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], MT_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // whole warp: allocate all of TMEM (one CTA per SM), publish the base address
@@ -143,50 +152,67 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_nn(const __grid_constan
             }
         }
     } else {
-        // ---- epilogue: thread <-> TMEM lane <-> query row ----
-        const int q = warp & 3;
+        // ---- epilogue: thread <-> TMEM lane <-> query row, warp <-> one half of the tile's columns ----
+        const int q = warp & 3;                      // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;            // columns [128 * half, 128 * half + 128) of every tile
+        const int etid = tid - 64;                   // 0 .. 255 among the epilogue threads
         const int row = m0 + 32 * q + lane;
         const uint32_t na256 = (row < (int)p.n_a) ? (__ldg(p.norm_a + row) << 8) : 0u;
         uint32_t best_d2 = 0xffffffffu, best_j = 0;
         for (int t = 0; t < n_tiles; t++) {
             const int acc = t & 1;
+            const int tg = t_first + t;   // global tile index
+            // the tile's 256 (|b|^2 << 8 | column) words, one per epilogue thread, double-buffered: the named barrier
+            // below also orders the reuse of a buffer (every warp passed the barrier of tile t-1 after reading tile t-2)
+            s_nbp[acc][etid] = __ldg(p.nbp + (size_t)tg * MT_N + etid);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * MT_EPI_WARPS) : "memory");
             mbar_wait(&tmem_full[acc], (uint32_t)(t >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * MT_N;
-            const int tg = t_first + t;   // global tile index
-            const uint32_t* nbp = p.nbp + (size_t)tg * MT_N;
-            const int valid = min(MT_N, (int)p.n_b - tg * MT_N);
-            uint32_t tmin[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // (distance^2 << 8) | column, four chains
-#pragma unroll 1
-            for (int c0 = 0; c0 < MT_N; c0 += 32) {
-                uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * MT_N + (uint32_t)half * 128u;
+            uint32_t v[128];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint32_t* u = v + 64 * c;
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr + (uint32_t)c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 <= valid) {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) tmin[k & 3] = min(tmin[k & 3], __ldg(nbp + c0 + k) + na256 - 512u * v[k]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 32; k++)
-                        if (c0 + k < valid) tmin[k & 3] = min(tmin[k & 3], __ldg(nbp + c0 + k) + na256 - 512u * v[k]);
-                }
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+                    "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+                    "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+                      "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+                      "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31]),
+                      "=r"(u[32]), "=r"(u[33]), "=r"(u[34]), "=r"(u[35]), "=r"(u[36]), "=r"(u[37]), "=r"(u[38]), "=r"(u[39]),
+                      "=r"(u[40]), "=r"(u[41]), "=r"(u[42]), "=r"(u[43]), "=r"(u[44]), "=r"(u[45]), "=r"(u[46]), "=r"(u[47]),
+                      "=r"(u[48]), "=r"(u[49]), "=r"(u[50]), "=r"(u[51]), "=r"(u[52]), "=r"(u[53]), "=r"(u[54]), "=r"(u[55]),
+                      "=r"(u[56]), "=r"(u[57]), "=r"(u[58]), "=r"(u[59]), "=r"(u[60]), "=r"(u[61]), "=r"(u[62]), "=r"(u[63])
+                    : "r"(taddr + 64u * (uint32_t)c));
             }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // the accumulator stage is in registers: hand it back before the arithmetic
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            const uint32_t tile_min = min(min(tmin[0], tmin[1]), min(tmin[2], tmin[3]));
-            const uint32_t d2 = tile_min >> 8;
-            if (tile_min != 0xffffffffu && d2 < best_d2) { best_d2 = d2; best_j = (uint32_t)(tg * MT_N) + (tile_min & 255u); }
+            // signed: 256 (|b|^2 - 2 a.b) + column lies in (-2^31, 2^31) because |a|^2, |b|^2 <= 128 * 255^2 < 2^23
+            int tmin[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+            const uint4* nb4 = reinterpret_cast<const uint4*>(&s_nbp[acc][128 * half]);
+#pragma unroll
+            for (int k = 0; k < 128; k += 4) {
+                const uint4 nb = nb4[k >> 2];   // the same address for every lane: one broadcast
+                const int t0 = (int)nb.x - 512 * (int)v[k], t1 = (int)nb.y - 512 * (int)v[k + 1];
+                const int t2 = (int)nb.z - 512 * (int)v[k + 2], t3 = (int)nb.w - 512 * (int)v[k + 3];
+                tmin[(k >> 2) & 1] = __vimin3_s32(tmin[(k >> 2) & 1], t0, t1);
+                tmin[2 + ((k >> 2) & 1)] = __vimin3_s32(tmin[2 + ((k >> 2) & 1)], t2, t3);
+            }
+            const int tile_min = min(min(tmin[0], tmin[1]), min(tmin[2], tmin[3]));
+            if (tile_min < (int)MT_NBP_REAL_MAX) {   // a real column (padding columns sit at MT_NBP_PAD)
+                const uint32_t full = (uint32_t)tile_min + na256;   // 256 d^2 + column, >= 0
+                const uint32_t d2 = full >> 8;
+                if (d2 < best_d2) { best_d2 = d2; best_j = (uint32_t)(tg * MT_N) + (full & 255u); }
+            }
         }
-        // merge with the other tile ranges of this row: smaller distance first, then smaller index
+        // merge with the other column half and the other tile ranges of this row: smaller distance first, then smaller index
         if (row < (int)p.n_a && best_d2 != 0xffffffffu) atomicMin(p.best + row, ((unsigned long long)best_d2 << 32) | best_j);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -211,7 +237,7 @@ __global__ void __launch_bounds__(256) k_match_prep(const uint8_t* __restrict__ 
     }
     if (lane == 0) {
         if (row < n) norm[row] = s;
-        nbp[row] = row < n ? ((s << 8) | (row & 255u)) : 0u;
+        nbp[row] = row < n ? ((s << 8) | (row & 255u)) : MT_NBP_PAD;
     }
 }
 

@@ -681,7 +681,8 @@ struct MarchCfg {
 
 template <int L, bool DECIMATE, int FL = FL_OPENCV>
 __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTAS_PER_SM) k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
-                                                        const int src_layer, const int seg_rows) {
+                                                        const int src_layer, const int bands_per_cta, const int strips,
+                                                        const long long total_bands) {
     static_assert(FL == FL_OPENCV || !DECIMATE, "the imageproc flavour decimates in its own kernel");
     using C = MarchCfg<L, FL>;
     constexpr int R = C::R;
@@ -691,20 +692,35 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
     float* const stage = smem_march;                               // NSTG x BH x BW (TMA box layout)
     float* const inter = smem_march + C::NSTG * STAGE_FLOATS;      // RING_ROWS x IPITCH
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * C::TW;
-    const int ya = blockIdx.y * seg_rows;
-    const int img = blockIdx.z;
     const int w = p.w, h = p.h;
-    const int yb = min(ya + seg_rows, h);
+    // Work distribution: the (strip, image) columns of the launch, each cut into bands of BH output rows, form one
+    // sequence of total_bands bands; CTA c owns the bands [c * bands_per_cta, (c + 1) * bands_per_cta) of it and marches
+    // down every piece of a column that falls into its range.  Every CTA gets the same number of bands whatever the
+    // image height, strip count and batch size are, so a launch has no partially filled last wave.
+    const int nb = (h + C::BH - 1) / C::BH;                        // bands per column
+    const long long gb_end = min((long long)(blockIdx.x + 1) * bands_per_cta, total_bands);
+    bool first_piece = true;
+    for (long long gb = (long long)blockIdx.x * bands_per_cta; gb < gb_end;) {
+    const int unit = (int)(gb / nb), band0 = (int)(gb - (long long)unit * nb);
+    const int take = (int)min((long long)(nb - band0), gb_end - gb);
+    gb += take;
+    const int tx0 = (unit % strips) * C::TW;
+    const int img = unit / strips;
+    const int ya = band0 * C::BH;
+    const int yb = min(ya + take * C::BH, h);
     const int n_out = (yb - ya + C::BH - 1) / C::BH;           // output bands
     const int n_in = (yb - ya + 2 * R + C::BH - 1) / C::BH;    // input bands (n_out or n_out + 1)
     const int in0 = ya - R;                                    // first input row of band 0
     const bool hedge = tx0 - R < 0 || tx0 + C::TW + R > w;
-    if (tid == 0) {
+    if (tid == 0) {   // fresh barriers per piece (every load of the previous piece has been waited for)
 #pragma unroll
-        for (int b = 0; b < C::NSTG; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[b])));
+        for (int b = 0; b < C::NSTG; b++) {
+            if (!first_piece) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar[b])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[b])));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    first_piece = false;
     __syncthreads();
     auto issue = [&](const int b, const int stg) {   // band b into stage buffer stg == b % NSTG
         const uint32_t bar_a = smem_u32(&bar[stg]);
@@ -902,6 +918,7 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
         }
         __syncthreads();
     }
+    }   // pieces
 }
 
 // ---------------------------------------------------------------------------

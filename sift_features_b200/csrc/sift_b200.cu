@@ -82,7 +82,7 @@ struct Slot {
     uint32_t* h_counts = nullptr;  // pinned mirror of d_counts
     // CUDA graphs of the whole per-group kernel sequence, keyed by its launch parameters (a few shapes per slot)
     struct PipeGraph {
-        uint32_t n, w, h, stride; uint64_t img_stride; const uint8_t* d_in;
+        uint32_t n, w, h, stride; uint64_t img_stride; const uint8_t* d_in; bool detect;
         cudaGraphExec_t exec; uint64_t launches, stage_launches[SB200_STAGE_COUNT]; uint64_t last_use;
     };
     std::vector<PipeGraph> graphs;
@@ -601,40 +601,27 @@ int set_imageproc_attrs(sb200_ctx* ctx) {
     return set_march_attr<LI, false, FL_IMAGEPROC>(ctx);
 }
 
-// rows per vertical segment of the marching blur.  Taller segments amortise the per-CTA start (first TMA round
-// trip) and the 2R halo rows of the row pass; more segments fill the machine.  Pick the height with the best
-// product of (a) wave efficiency of the resulting grid on the resident CTA slots and (b) useful rows per CTA.
-int march_seg_rows(const sb200_ctx* ctx, int w, int h, uint32_t n, int tile_w, int ctas_per_sm) {
-    if (ctx->seg_rows_override > 0) return ctx->seg_rows_override;
-    const long long strips = (w + tile_w - 1) / tile_w;
-    const long long slots = (long long)ctas_per_sm * ctx->sm_count;
-    const long long S = strips * n;
-    // plenty of strips (large batches): the other slot's kernels fill any tail, only the per-CTA overhead counts --
-    // tall segments (measured at 32 images of 1080p: throughput flat from ~540 rows up, ~3 % above 256-row
-    // segments, while the launch on its own -- no other slot filling its tail -- is best around 400-550 rows)
-    const long long segs_tall = (h + 575) / 576;
-    if (S * segs_tall >= 2 * slots) return (int)(((h + segs_tall - 1) / segs_tall + 31) / 32 * 32);
-    // few strips (single images): the launch is alone on the machine, wave quantisation decides
-    int best_rows = 64;
-    double best = -1.0;
-    for (int rows = 64; rows < h + 32; rows += 32) {
-        const long long segs = (h + rows - 1) / rows;
-        const long long total = S * segs;
-        const long long waves = (total + slots - 1) / slots;
-        const double wave_eff = (double)total / (double)(waves * slots);
-        const double useful = (double)std::min(rows, h) / (double)(std::min(rows, h) + 40);   // ~40 rows: start-up + halo
-        const double score = wave_eff * useful;
-        if (score > best + 1e-9) { best = score; best_rows = rows; }
-    }
-    return best_rows;
-}
-
+// Launch shape of the marching blur: the (strip, image) columns of the launch are cut into bands of 32 output rows
+// and dealt out evenly, in order, to the CTAs of the grid (k_blur_march).  A CTA marches down a contiguous run of
+// bands -- the rest of one column, the head of the next.  The run length is chosen so that the grid is a whole number
+// of waves of the machine's resident-CTA slots (no partially filled last wave, whatever the image height, strip count
+// and batch size) with runs of about MARCH_TARGET_BANDS bands: long enough to amortise a piece's pipeline start and
+// 2R halo rows, short enough that the CTAs in flight at any time work on neighbouring strips of a few images (their
+// halos hit in L2 and their rows share DRAM pages -- one wave of very long runs measured 1.3-1.5x slower).
+constexpr int MARCH_MIN_BANDS = 2;
+constexpr int MARCH_TARGET_BANDS = 17;
 template <int LI, bool DEC, int FL = FL_OPENCV>
 void launch_blur_march(sb200_ctx* ctx, cudaStream_t st, const CUtensorMap& tm, const BlurParams& p, uint32_t n, int src_layer) {
     using C = MarchCfg<LI, FL>;
-    const int seg = march_seg_rows(ctx, p.w, p.h, n, C::TW, C::CTAS_PER_SM);
-    dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + seg - 1) / seg, n);
-    k_blur_march<LI, DEC, FL><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer, seg);
+    const int strips = (p.w + C::TW - 1) / C::TW;
+    const long long nb = (p.h + C::BH - 1) / C::BH;
+    const long long total = (long long)strips * n * nb;
+    const long long slots = (long long)C::CTAS_PER_SM * ctx->sm_count;
+    const long long waves = std::max<long long>(1, (total + MARCH_TARGET_BANDS * slots / 2) / (MARCH_TARGET_BANDS * slots));
+    long long per = std::max<long long>((total + waves * slots - 1) / (waves * slots), std::min<long long>(MARCH_MIN_BANDS, nb));
+    if (ctx->seg_rows_override > 0) per = std::max(1, ctx->seg_rows_override / C::BH);   // SB200_SEG_ROWS (tests)
+    const long long grid = (total + per - 1) / per;
+    k_blur_march<LI, DEC, FL><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer, (int)per, strips, total);
 }
 
 // one blur of the imageproc flavour: marching TMA kernel for octaves that own a tensor map, generic tiles otherwise
@@ -977,33 +964,35 @@ int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
 // and replayed: one launch per group on the host, and no per-kernel launch latency between the many short kernels of
 // the small octaves on the device.  Stage timing (profiling) needs events between the kernels: plain launches then.
 int run_pipeline(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, uint32_t stride, uint64_t img_stride,
-                 const uint8_t* d_in, int64_t limit) {
+                 const uint8_t* d_in, int64_t limit, bool detect = true) {
     if (!ctx->use_graphs || ctx->profiling) {
         int rc = enqueue_pyramid(ctx, s, n, w, h, stride, img_stride, d_in);
-        if (rc) return rc;
+        if (rc || !detect) return rc;
         return enqueue_detect(ctx, s, n, limit);
     }
     if (limit >= 0) {   // features_limit is a kernel argument (and adds the sort): run directly
         int rc = enqueue_pyramid(ctx, s, n, w, h, stride, img_stride, d_in);
-        if (rc) return rc;
+        if (rc || !detect) return rc;
         return enqueue_detect(ctx, s, n, limit);
     }
     Slot::PipeGraph* hit = nullptr;
     for (auto& g : s.graphs)
-        if (g.n == n && g.w == w && g.h == h && g.stride == stride && g.img_stride == img_stride && g.d_in == d_in) hit = &g;
+        if (g.n == n && g.w == w && g.h == h && g.stride == stride && g.img_stride == img_stride && g.d_in == d_in &&
+            g.detect == detect)
+            hit = &g;
     if (!hit) {
         const uint64_t l0 = ctx->launches;
         uint64_t sl0[SB200_STAGE_COUNT];
         for (int i = 0; i < SB200_STAGE_COUNT; i++) sl0[i] = ctx->stage_launches[i];
         CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
         int rc = enqueue_pyramid(ctx, s, n, w, h, stride, img_stride, d_in);
-        if (!rc) rc = enqueue_detect(ctx, s, n, limit);
+        if (!rc && detect) rc = enqueue_detect(ctx, s, n, limit);
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail(ctx, SB200_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
         Slot::PipeGraph g{};
-        g.n = n; g.w = w; g.h = h; g.stride = stride; g.img_stride = img_stride; g.d_in = d_in;
+        g.n = n; g.w = w; g.h = h; g.stride = stride; g.img_stride = img_stride; g.d_in = d_in; g.detect = detect;
         e = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(ctx, SB200_E_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e));
@@ -1861,6 +1850,35 @@ int sb200_extract_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n
     return SB200_OK;
 }
 
+int sb200_pyramid_batch_device(sb200_ctx* ctx, const uint8_t* d_gray, uint32_t n, uint32_t w, uint32_t h, uint32_t stride,
+                               uint64_t image_stride) {
+    if (!ctx) return SB200_E_INVALID;
+    if (!d_gray || n == 0 || n > ctx->max_batch || stride < w)
+        return fail(ctx, SB200_E_INVALID, "bad arguments to pyramid_batch_device");
+    CU(cudaSetDevice(ctx->device));
+    int rc = set_image_size(ctx, w, h);
+    if (rc) return rc;
+    Slot& s = ctx->slot[ctx->dev_rr];
+    ctx->last_slot = ctx->dev_rr;
+    ctx->dev_rr = (ctx->dev_rr + 1) % N_SLOTS;
+    if (ctx->use_graphs && !ctx->profiling && d_gray != s.d_in) {
+        if (image_stride == (uint64_t)stride * h) {
+            CU(cudaMemcpy2DAsync(s.d_in, w, d_gray, stride, w, (size_t)h * n, cudaMemcpyDeviceToDevice, s.stream));
+        } else {
+            for (uint32_t i = 0; i < n; i++)
+                CU(cudaMemcpy2DAsync(s.d_in + (size_t)i * w * h, w, d_gray + i * image_stride, stride, w, h,
+                                     cudaMemcpyDeviceToDevice, s.stream));
+        }
+        d_gray = s.d_in; stride = w; image_stride = (uint64_t)w * h;
+    }
+    rc = run_pipeline(ctx, s, n, w, h, stride, image_stride, d_gray, -1, false);
+    if (rc) return rc;
+    s.n_imgs = n;
+    ctx->have_pyramid = (n == 1);
+    ctx->have_single = false;
+    return SB200_OK;
+}
+
 int sb200_device_result(sb200_ctx* ctx, uint32_t* counts, uint32_t n, const sb200_keypoint** d_keypoints,
                         const uint8_t** d_descriptors, uint32_t* capacity_per_image) {
     if (!ctx) return SB200_E_INVALID;
@@ -2266,8 +2284,17 @@ int sb200_match_descriptors_device(sb200_ctx* ctx, const uint8_t* d_query, uint6
         mp.best = ctx->d_mbest[a];
         // one CTA per 128 query rows and per range of train tiles: enough CTAs for two per SM-slot (one CTA holds
         // all of an SM's tensor memory), ranges of at least four tiles
+        // one CTA per 128 query rows and per range of train tiles; one CTA holds all of an SM's tensor memory, so the
+        // grid runs in rounds of sm_count CTAs: pick the split whose rounds x (tiles per CTA + start-up) is smallest
         const uint32_t row_ctas = (uint32_t)((n[a] + MT_M - 1) / MT_M), tiles = (uint32_t)((n[b] + MT_N - 1) / MT_N);
-        uint32_t splits = std::max<uint32_t>(1, std::min<uint32_t>((2u * ctx->sm_count + row_ctas - 1) / row_ctas, (tiles + 3) / 4));
+        uint32_t splits = 1;
+        double best_cost = 1e30;
+        for (uint32_t sp = 1; sp <= tiles; sp++) {
+            const uint32_t per = (tiles + sp - 1) / sp, eff = (tiles + per - 1) / per;
+            const uint64_t rounds = ((uint64_t)row_ctas * eff + ctx->sm_count - 1) / ctx->sm_count;
+            const double cost = (double)rounds * (per + 1.5);
+            if (cost < best_cost - 1e-9) { best_cost = cost; splits = sp; }
+        }
         mp.tiles_per_cta = (tiles + splits - 1) / splits;
         splits = (tiles + mp.tiles_per_cta - 1) / mp.tiles_per_cta;
         CU(cudaMemsetAsync(ctx->d_mbest[a], 0xff, n[a] * sizeof(unsigned long long), st));
@@ -2278,15 +2305,14 @@ int sb200_match_descriptors_device(sb200_ctx* ctx, const uint8_t* d_query, uint6
                                       (uint32_t)std::min<uint64_t>(ctx->mout_cap, 0xffffffffull), ctx->d_mcount);
     ctx->launches++;
     CU(cudaGetLastError());
+    // one round trip: the count and every row the caller's buffer could hold leave the device together (at most
+    // n_query rows of 12 bytes), instead of count, synchronise, rows, synchronise
     uint32_t cnt = 0;
+    const uint64_t room = std::min<uint64_t>(n_query, cap);
     CU(cudaMemcpyAsync(&cnt, ctx->d_mcount, 4, cudaMemcpyDeviceToHost, st));
+    if (room) CU(cudaMemcpyAsync(out, ctx->d_mout, room * sizeof(sb200_dmatch), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *n_out = cnt;
-    const uint64_t m = std::min<uint64_t>(cnt, cap);
-    if (m) {
-        CU(cudaMemcpyAsync(out, ctx->d_mout, m * sizeof(sb200_dmatch), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    }
     return cnt > cap ? fail(ctx, SB200_E_CAPACITY, "%u matches exceed the output capacity %llu", cnt, (unsigned long long)cap) : SB200_OK;
 }
 
