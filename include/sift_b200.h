@@ -39,7 +39,7 @@ extern "C" {
 
 #define SB200_DESC_SIZE 128   /* DESCRIPTOR_SIZE, src/lib.rs:111-112 */
 #define SB200_MAX_OCTAVES 16
-#define SB200_MAX_DIM 4096    /* max input width/height (seed image <= 8192) */
+#define SB200_MAX_DIM 8192    /* max input width/height (seed image <= 16384: an 8K frame, 7680 x 4320, fits) */
 
 /* status codes */
 #define SB200_OK 0

@@ -50,15 +50,17 @@ struct PyrLayout {
     OctLayout o[MAX_OCT];
 };
 
-// candidate key: octave:4 | scale:2 | y:13 | x:13  (natural order == integer order)
-__host__ __device__ inline uint32_t pack_key(int o, int s, int y, int x) {
-    return ((uint32_t)o << 28) | ((uint32_t)s << 26) | ((uint32_t)y << 13) | (uint32_t)x;
+// candidate key: octave | scale | y:16 | x:16  (natural order == integer order); 64-bit so that seed images of up to
+// 65535 pixels per side fit (SB200_MAX_DIM = 8192 input pixels -> 16384-pixel seed image)
+typedef unsigned long long CandKey;
+__host__ __device__ inline CandKey pack_key(int o, int s, int y, int x) {
+    return ((CandKey)o << 34) | ((CandKey)s << 32) | ((CandKey)y << 16) | (CandKey)x;
 }
-__host__ __device__ inline void unpack_key(uint32_t k, int& o, int& s, int& y, int& x) {
-    o = (int)(k >> 28);
-    s = (int)((k >> 26) & 3u);
-    y = (int)((k >> 13) & 0x1fffu);
-    x = (int)(k & 0x1fffu);
+__host__ __device__ inline void unpack_key(CandKey k, int& o, int& s, int& y, int& x) {
+    o = (int)(k >> 34);
+    s = (int)((k >> 32) & 3u);
+    y = (int)((k >> 16) & 0xffffu);
+    x = (int)(k & 0xffffu);
 }
 
 // refined scale-space point (output of the refinement kernel, one per candidate)

@@ -1366,7 +1366,7 @@ __global__ void __launch_bounds__(1024) k_rowscan(const uint32_t* __restrict__ r
 // (bit l of B0 is column 60*strip - 2 + 2l, bit l of B1 the column after it).
 __global__ void __launch_bounds__(256) k_compact(const PyrLayout L, const uint32_t* __restrict__ mask,
                                                   const uint32_t* __restrict__ rows,
-                                                  const uint32_t* __restrict__ rowoff, uint32_t* __restrict__ keys,
+                                                  const uint32_t* __restrict__ rowoff, CandKey* __restrict__ keys,
                                                   uint32_t cap) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ridx = blockIdx.x * 8 + warp;
@@ -1381,7 +1381,7 @@ __global__ void __launch_bounds__(256) k_compact(const PyrLayout L, const uint32
     const int s = local / ol.h + 1, y = local - (s - 1) * ol.h;
     const uint2* words = reinterpret_cast<const uint2*>(mask + img * L.img_mask_words + ol.mask_off + (long long)local * ol.mask_pitch);
     uint32_t pos0 = rowoff[img * L.img_rows + ridx];
-    uint32_t* out = keys + img * (long long)cap;
+    CandKey* out = keys + img * (long long)cap;
     const int ns = ol.mask_pitch >> 1;
     for (int sb = 0; sb < ns; sb += 32) {
         uint2 word = (sb + lane < ns) ? words[sb + lane] : make_uint2(0u, 0u);

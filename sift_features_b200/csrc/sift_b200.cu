@@ -69,7 +69,7 @@ struct Slot {
     uint32_t* d_counts = nullptr;  // cand_count[B], kp_count[B], out_count[B], out_off[B+1]
     uint32_t* d_sched = nullptr;   // work counters [4], scratch counts [B], candidate prefix sums [B+1]
     // candidates / keypoints
-    uint32_t* d_keys = nullptr;
+    CandKey* d_keys = nullptr;
     Refined* d_refined = nullptr;
     uint32_t* d_nori = nullptr;
     float* d_angles = nullptr;
@@ -2020,7 +2020,8 @@ int sb200_last_candidates(sb200_ctx* ctx, sb200_candidate* out, uint64_t cap, ui
     const PyrLayout& L = ctx->L;
     cudaStream_t st = s.stream;
     CU(cudaStreamSynchronize(st));
-    uint32_t *d_mask = nullptr, *d_rows = nullptr, *d_rowoff = nullptr, *d_cnt = nullptr, *d_keys = nullptr;
+    uint32_t *d_mask = nullptr, *d_rows = nullptr, *d_rowoff = nullptr, *d_cnt = nullptr;
+    CandKey* d_keys = nullptr;
     int rc = SB200_OK;
     auto cleanup = [&]() { cudaFree(d_mask); cudaFree(d_rows); cudaFree(d_rowoff); cudaFree(d_cnt); cudaFree(d_keys); };
     auto body = [&]() -> int {
@@ -2052,8 +2053,8 @@ int sb200_last_candidates(sb200_ctx* ctx, sb200_candidate* out, uint64_t cap, ui
             dim3 grid((L.img_rows + 7) / 8, 1);
             k_compact<<<grid, 256, 0, st>>>(L, d_mask, d_rows, d_rowoff, d_keys, cnt);
             ctx->launches++;
-            std::vector<uint32_t> keys(m);
-            CU(cudaMemcpyAsync(keys.data(), d_keys, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            std::vector<CandKey> keys(m);
+            CU(cudaMemcpyAsync(keys.data(), d_keys, (size_t)m * sizeof(CandKey), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             for (uint32_t i = 0; i < m; i++) {
                 int o, sc, y, x;

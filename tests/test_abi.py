@@ -67,7 +67,7 @@ def test_invalid_arguments_rejected_before_any_device_work(sf):
     lib = _ffi.load()
     h = C.c_void_p()
     assert lib.sb200_create(0, 0, 10, 1, 0, C.byref(h)) == _ffi.E_INVALID
-    assert lib.sb200_create(0, 5000, 10, 1, 0, C.byref(h)) == _ffi.E_INVALID   # > SB200_MAX_DIM
+    assert lib.sb200_create(0, 9000, 10, 1, 0, C.byref(h)) == _ffi.E_INVALID   # > SB200_MAX_DIM
     assert lib.sb200_extract(None, None, 1, 1, 1, -1, None) == _ffi.E_INVALID
     with pytest.raises(ValueError):
         sf.sift(np.zeros((4, 4), np.float32))

@@ -104,6 +104,39 @@ def test_maximum_size(sf, oracle):
     assert len(res) > 50000
 
 
+def test_8k_frame(sf, oracle):
+    """Beyond the 4096-pixel limit of round 1 (64-bit candidate keys, SB200_MAX_DIM = 8192): a 7680 x 4320 frame (seed
+    image 15360 x 8640, 12 octaves).  The CPU oracle needs minutes for the whole frame, so the check is structural: the
+    right octave count, the keypoint density of the same noise at 4K, every keypoint inside the frame, and -- exactly --
+    the oracle's keypoints in a strip of the frame whose pyramid does not depend on the rest of it (the top 64 rows of
+    octave 0 see at most the first ~200 input rows)."""
+    w, h = 7680, 4320
+    img = noise_image(w, h, 4321)
+    with sf.Extractor(w, h, 1) as ex:
+        pre = ex.precompute_images(img)
+        assert pre.n_octaves == 12 and pre.dims[0] == (2 * w, 2 * h)
+        res = ex.sift_with_precomputed()
+        ka = ex.last_sift_keypoints()
+        cand = ex.last_candidates()
+    assert 3.9e3 * 33.2 < len(res) < 4.4e3 * 33.2            # ~4.17 k keypoints per input megapixel on this noise
+    kp = res.keypoint_array
+    assert kp["x"].min() >= 0 and kp["x"].max() < w and kp["y"].min() >= 0 and kp["y"].max() < h
+    assert kp["x"].max() > 4096 + 3000 and kp["y"].max() > 4096              # coordinates past the old 13-bit limit
+    # octave-0 keypoints near the top edge depend on the top input rows only: compare with the oracle on a crop
+    crop = np.ascontiguousarray(img[:256])
+    okp, _ = oracle.sift(crop)
+    top = lambda a: a[(a["y"] < 40)]
+    got = top(kp)
+    ref = top(okp)
+    oct0 = lambda a: a[a["size"] < 3.5 / 2]                                   # octave 0: size = kp_scale / 2 < 1.8
+    g0, r0 = oct0(got), oct0(ref)
+    assert len(g0) == len(r0) and len(g0) > 1000
+    assert np.array_equal(_bits(g0["x"]), _bits(r0["x"])) and np.array_equal(_bits(g0["y"]), _bits(r0["y"]))
+    # white noise loses contrast with every octave: keypoints survive in octaves 0..2 only, extrema candidates much deeper
+    assert ka["octave"].max() == 2 and cand["octave"].max() >= 7
+    assert cand["x"].max() > 8192 and cand["y"].max() > 8192                 # 14-bit seed-image coordinates
+
+
 @pytest.mark.parametrize("seg_rows", [512, 96])
 def test_blur_segment_heights(sf, oracle, monkeypatch, seg_rows):
     """The marching blur cuts an octave into vertical segments whose height depends on the batch; a large batch
@@ -247,7 +280,8 @@ def test_fuzz_sizes(sf, oracle):
         _check_image(sf, oracle, g, pyramid=(case % 6 == 0))
 
 
-@pytest.mark.parametrize("w,h", [(4096, 10), (10, 4096), (2000, 16), (16, 2000), (4096, 1), (1, 4096), (3000, 33), (33, 3000)])
+@pytest.mark.parametrize("w,h", [(4096, 10), (10, 4096), (2000, 16), (16, 2000), (4096, 1), (1, 4096), (3000, 33), (33, 3000),
+                                 (8192, 12), (12, 8192), (5000, 40)])
 def test_extreme_aspect(sf, oracle, w, h):
     """Strips and ribbons up to the maximum dimension: octaves that run out of rows or columns long before the other
     dimension does (TMA boxes wider / taller than the layer, single-row layers, the fused tail on 1-pixel-wide octaves)."""
