@@ -618,7 +618,9 @@ void launch_blur_march(sb200_ctx* ctx, cudaStream_t st, const CUtensorMap& tm, c
     const long long total = (long long)strips * n * nb;
     const long long slots = (long long)C::CTAS_PER_SM * ctx->sm_count;
     const long long waves = std::max<long long>(1, (total + MARCH_TARGET_BANDS * slots / 2) / (MARCH_TARGET_BANDS * slots));
-    long long per = std::max<long long>((total + waves * slots - 1) / (waves * slots), std::min<long long>(MARCH_MIN_BANDS, nb));
+    // a launch that cannot fill the machine anyway (single images, the small octaves) is latency bound: one band per CTA
+    const long long min_bands = total <= slots ? 1 : std::min<long long>(MARCH_MIN_BANDS, nb);
+    long long per = std::max<long long>((total + waves * slots - 1) / (waves * slots), min_bands);
     if (ctx->seg_rows_override > 0) per = std::max(1, ctx->seg_rows_override / C::BH);   // SB200_SEG_ROWS (tests)
     const long long grid = (total + per - 1) / per;
     k_blur_march<LI, DEC, FL><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer, (int)per, strips, total);
