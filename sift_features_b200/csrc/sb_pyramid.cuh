@@ -698,9 +698,20 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
     // down every piece of a column that falls into its range.  Every CTA gets the same number of bands whatever the
     // image height, strip count and batch size are, so a launch has no partially filled last wave.
     const int nb = (h + C::BH - 1) / C::BH;                        // bands per column
-    const long long gb_end = min((long long)(blockIdx.x + 1) * bands_per_cta, total_bands);
+    long long gb, gb_end;
+    if (bands_per_cta > 0) {
+        gb = (long long)blockIdx.x * bands_per_cta;
+        gb_end = min(gb + bands_per_cta, total_bands);
+    } else {
+        // aligned mode: every column is cut into k = -bands_per_cta pieces of (almost) equal length and a CTA owns exactly
+        // one piece -- one pipeline start per CTA, and the CTAs of neighbouring strips walk the same rows at the same time
+        const int k = -bands_per_cta;
+        const int unit = blockIdx.x / k, pc = blockIdx.x - unit * k;
+        gb = (long long)unit * nb + (long long)pc * nb / k;
+        gb_end = (long long)unit * nb + (long long)(pc + 1) * nb / k;
+    }
     bool first_piece = true;
-    for (long long gb = (long long)blockIdx.x * bands_per_cta; gb < gb_end;) {
+    while (gb < gb_end) {
     const int unit = (int)(gb / nb), band0 = (int)(gb - (long long)unit * nb);
     const int take = (int)min((long long)(nb - band0), gb_end - gb);
     gb += take;
@@ -752,12 +763,16 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
         float* const st = stage + stg * STAGE_FLOATS;
         const int band_y0 = in0 + b * C::BH;
         if (hedge) {  // block-uniform: box element (row, XO + col) holds image pixel (band_y0 + row, tx0 - R + col)
-            for (int idx = tid; idx < C::BH * C::SW; idx += C::THREADS) {
-                const int row = idx / C::SW, col = idx - row * C::SW;
-                const int gx = tx0 - R + col;
-                if (gx < 0 || gx >= w) {
-                    const int rx = border_index<FL>(gx, w) - (tx0 - R);
-                    if (rx >= 0 && rx < C::SW) st[row * C::BW + C::XO + col] = st[row * C::BW + C::XO + rx];
+            // only the R columns left of the image and the first R columns right of it feed a stored output: a warp
+            // takes one such column, its lanes the rows of the band
+            const int nl = max(R - tx0, 0);                       // strip columns [0, nl) lie left of the image
+            const int cr0 = w - tx0 + R;                          // first strip column right of the image
+            const int np = nl + max(min(C::SW, cr0 + R) - cr0, 0);
+            for (int c = warp; c < np; c += C::THREADS / 32) {
+                const int col = c < nl ? c : cr0 + (c - nl);
+                const int rx = border_index<FL>(tx0 - R + col, w) - (tx0 - R);
+                if (rx >= 0 && rx < C::SW) {
+                    for (int row = lane; row < C::BH; row += 32) st[row * C::BW + C::XO + col] = st[row * C::BW + C::XO + rx];
                 }
             }
             __syncthreads();

@@ -134,6 +134,7 @@ struct sb200_ctx {
     int flavour = FL_OPENCV;                   // Processing flavour of the pyramid (sb200_set_processing)
     bool march = true;                         // SB200_BLUR=tile selects the independent-tile TMA blur (debugging aid)
     int seg_rows_override = 0;                 // SB200_SEG_ROWS: fixed segment height of the marching blur (tests)
+    int pieces_override = 0;                   // SB200_PIECES: pieces per column of the aligned distribution (experiments)
     bool tail = true;                          // SB200_TAIL=0: per-layer launches for the small octaves too (debugging aid)
     bool use_graphs = true;                    // SB200_GRAPHS=0: plain stream launches
     bool fork_octaves = true;                  // SB200_FORK=0: every kernel of a group on one stream
@@ -622,7 +623,18 @@ void launch_blur_march(sb200_ctx* ctx, cudaStream_t st, const CUtensorMap& tm, c
     const long long min_bands = total <= slots ? 1 : std::min<long long>(MARCH_MIN_BANDS, nb);
     long long per = std::max<long long>((total + waves * slots - 1) / (waves * slots), min_bands);
     if (ctx->seg_rows_override > 0) per = std::max(1, ctx->seg_rows_override / C::BH);   // SB200_SEG_ROWS (tests)
-    const long long grid = (total + per - 1) / per;
+    long long grid = (total + per - 1) / per;
+    if (ctx->seg_rows_override <= 0 && (waves >= 2 || ctx->pieces_override > 0)) {
+        // A launch of several waves: every column is cut into k pieces of (almost) equal length, one piece per CTA, so
+        // that a CTA starts its pipeline once and the CTAs of neighbouring strips walk the same rows at the same time.
+        // Launch time measured on B200 ~ (columns * k / slots + 0.5) * (nb / k + 1.45) band steps (the half wave is the
+        // tail, 1.45 bands the start of a piece): minimal at k = sqrt(0.5 * nb * slots / (1.45 * columns)).
+        long long k = (long long)std::llround(std::sqrt(0.5 * (double)nb * (double)slots / (1.45 * (double)strips * n)));
+        if (ctx->pieces_override > 0) k = ctx->pieces_override;   // SB200_PIECES (experiments)
+        k = std::max<long long>(1, std::min<long long>(k, nb));
+        per = -k;
+        grid = (long long)strips * n * k;
+    }
     k_blur_march<LI, DEC, FL><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer, (int)per, strips, total);
 }
 
@@ -1509,6 +1521,8 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
             CU(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM));
             const char* sr = getenv("SB200_SEG_ROWS");
             if (sr && atoi(sr) >= 32) ctx->seg_rows_override = atoi(sr) / 32 * 32;
+            const char* pc = getenv("SB200_PIECES");
+            if (pc && atoi(pc) >= 1) ctx->pieces_override = atoi(pc);
         }
         CU(cudaFuncSetAttribute(k_match_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
         CU(cudaFuncSetAttribute(k_extrema_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXT_SMEM));
