@@ -145,6 +145,32 @@ def test_blur_segment_heights(sf, oracle, monkeypatch, seg_rows):
     _check_image(sf, oracle, noise_image(700, 650, 21))
 
 
+@pytest.mark.parametrize("pieces,size", [(1, (700, 650)), (3, (700, 650)), (7, (333, 517)), (64, (260, 200))])
+def test_blur_aligned_pieces(sf, oracle, monkeypatch, pieces, size):
+    """A launch of several waves (large batches) cuts every column of the marching blur into k equal pieces, one per
+    CTA; SB200_PIECES forces that distribution on a single image, with k = 1, k not dividing the band count, and k
+    larger than the band count of every octave (clamped to one band per CTA).  Same bit-exact pyramid."""
+    monkeypatch.setenv("SB200_PIECES", str(pieces))
+    _check_image(sf, oracle, noise_image(size[0], size[1], 33 + pieces))
+
+
+def test_blur_batch_distribution(sf, oracle):
+    """A batch large enough for the multi-wave (aligned pieces) distribution on octave 0 and the single-wave one on
+    the small octaves: every image of the batch equals the single-image result, and image 0 equals the oracle."""
+    w, h, n = 640, 480, 48
+    imgs = np.stack([noise_image(w, h, 900 + i) for i in range(n)])
+    with sf.Extractor(w, h, n) as ex:
+        off, kps, desc = ex.sift_batch(imgs)
+    with sf.Extractor(w, h, 1) as ex1:
+        for i in (0, 17, n - 1):
+            one = ex1.sift(imgs[i])
+            a, b = int(off[i]), int(off[i + 1])
+            assert b - a == len(one) and b > a
+            assert np.array_equal(desc[a:b], one.descriptors)
+            assert kps[a:b].tobytes() == one.keypoint_array.tobytes()
+    _check_image(sf, oracle, imgs[0])
+
+
 @pytest.mark.parametrize("env", [{"SB200_BLUR": "tile"}, {"SB200_TAIL": "0"}, {"SB200_GRAPHS": "0", "SB200_FORK": "0"}])
 def test_alternative_paths(sf, oracle, monkeypatch, env):
     """The debugging switches select older / simpler code paths (independent-tile TMA blur, per-layer launches for
