@@ -518,6 +518,7 @@ def run_config4(args, lib, sf, dist, rank, world):
             return (time.perf_counter() - t0) / reps, kp
         reps = 2
         t_parts, kp = timed(run_parts, ndev, reps)
+        shard_ms = [round(lib.sb200_last_shard_ms(e.handle), 2) for e in exs]
         t_dense, _ = timed(run_dense, ndev, reps)
         gather_ms = lib.sb200_last_gather_ms(H0)
         out = {"workload": f"ONE batch of {n} 640x480 noise images sharded over {ndev} GPU(s) by "
@@ -528,6 +529,7 @@ def run_config4(args, lib, sf, dist, rank, world):
                                 "gather_frac_of_step": gather_ms / (1e3 * t_dense),
                                 "note": "sb200_extract_batch_multi: the same plus a multi-threaded host concatenation "
                                         "into one dense result array"},
+               "shard_ms_per_device": shard_ms,
                "h2d_bytes": n * w * h, "d2h_bytes": int(kp * 148 + (n + 1) * 8)}
         if ndev > 1:
             t1, _ = timed(run_parts, 1, 1)

@@ -250,6 +250,9 @@ int sb200_extract_batch_multi(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint
                               uint32_t w, uint32_t h, uint32_t stride, uint64_t image_stride,
                               int64_t features_limit, sb200_result* out);
 double sb200_last_gather_ms(const sb200_ctx* ctx);
+/* Host wall time (ms) this context's shard took in the last sb200_extract_batch_multi / _multi_parts call: the
+ * slowest shard is the call's critical path. */
+double sb200_last_shard_ms(const sb200_ctx* ctx);
 
 /* ---- measurement hooks -------------------------------------------------- */
 #define SB200_STAGE_SEED 0        /* u8 -> 2x upsample -> seed blur          (src/lib.rs:196-210) */

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sb200_precompute", "sb200_extract_precomputed", "sb200_pyramid_info", "sb200_pyramid_layer",
     "sb200_pyramid_dog", "sb200_last_candidates", "sb200_last_sift_keypoints", "sb200_compute_descriptors",
     "sb200_compute_descriptors_device", "sb200_extract_batch_multi", "sb200_extract_batch_multi_parts",
-    "sb200_last_gather_ms", "sb200_set_profiling", "sb200_stage_stats",
+    "sb200_last_gather_ms", "sb200_last_shard_ms", "sb200_set_profiling", "sb200_stage_stats",
     "sb200_reset_stats", "sb200_launch_stats", "sb200_launch_count", "sb200_stage_name", "sb200_algorithmic_bytes", "sb200_timer_start",
     "sb200_timer_stop", "sb200_timer_elapsed_ms", "sb200_host_alloc", "sb200_host_free", "sb200_device_alloc",
     "sb200_device_free", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_flush_l2", "sb200_match_descriptors", "sb200_match_descriptors_device",
@@ -91,6 +91,7 @@ def load() -> C.CDLL:
         "sb200_extract_batch_multi_parts": (C.c_int, [C.POINTER(vp), u32, u8p, u32, u32, u32, u32, u64, i64,
                                                        C.POINTER(Result), C.POINTER(u64)]),
         "sb200_last_gather_ms": (C.c_double, [vp]),
+        "sb200_last_shard_ms": (C.c_double, [vp]),
         "sb200_set_profiling": (C.c_int, [vp, C.c_int]),
         "sb200_stage_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(u64), u32]),
         "sb200_reset_stats": (C.c_int, [vp]),

@@ -153,6 +153,7 @@ struct sb200_ctx {
     size_t res_cap = 0;
     uint64_t res_n = 0;
     double last_gather_ms = 0.0;   // host time of the dense gather of the last sb200_extract_batch_multi
+    double last_shard_ms = 0.0;    // host time this context's shard of the last multi-device call took
     // optional OpenCV-style post-filters of the host results (sb200_set_postfilter)
     bool pf_dedup = false;
     int64_t pf_retain = -1;
@@ -1193,7 +1194,9 @@ int launch_group(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img,
         uint8_t* const h_up = channels > 1 ? s.h_rgb : s.h_in;
         const bool contiguous = (image_stride == (uint64_t)stride * h);
         if (is_device_accessible_host(img)) {
-            if (contiguous) {
+            if (contiguous && stride == rowb) {   // densely packed batch: one linear copy
+                CU(cudaMemcpyAsync(d_up, img, rowb * h * n, cudaMemcpyHostToDevice, st));
+            } else if (contiguous) {
                 CU(cudaMemcpy2DAsync(d_up, rowb, img, stride, rowb, (size_t)h * n, cudaMemcpyHostToDevice, st));
             } else {
                 for (uint32_t i = 0; i < n; i++)
@@ -2172,8 +2175,10 @@ static int run_shards(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* gra
         if (f >= n) break;
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(per, n - f);
         auto shard = [=, &rcs]() {
+            const auto t0 = std::chrono::steady_clock::now();
             rcs[d] = sb200_extract_batch(ctxs[d], gray + f * image_stride, cnt, w, h, stride, image_stride, features_limit,
                                          &parts[d]);
+            ctxs[d]->last_shard_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         };
         if (d + 1 < n_ctx && f + cnt < n) th.emplace_back(shard);
         else { shard(); break; }   // the last non-empty shard runs on the calling thread
@@ -2240,6 +2245,7 @@ int sb200_extract_batch_multi(sb200_ctx* const* ctxs, uint32_t n_ctx, const uint
 }
 
 double sb200_last_gather_ms(const sb200_ctx* ctx) { return ctx ? ctx->last_gather_ms : 0.0; }
+double sb200_last_shard_ms(const sb200_ctx* ctx) { return ctx ? ctx->last_shard_ms : 0.0; }
 
 // ---- descriptor matching (examples/sift-match.rs:30-35: BFMatcher(NORM_L2, crossCheck = true)) -----------------
 namespace {

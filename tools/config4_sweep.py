@@ -32,6 +32,9 @@ for B in [int(x) for x in sys.argv[1:]] or [128, 64, 32]:
         ts = []
         for _ in range(3):
             t0 = time.perf_counter(); run(); ts.append(time.perf_counter() - t0)
-        print(f"B={B:4d} devices={k}: {n / min(ts):9.0f} images/s best, {n / np.median(ts):9.0f} median ({1e3 * min(ts):.1f} ms)", flush=True)
+        lib.sb200_last_shard_ms.restype = C.c_double
+        shard = [round(lib.sb200_last_shard_ms(e.handle), 1) for e in exs[:k]]
+        print(f"B={B:4d} devices={k}: {n / min(ts):9.0f} images/s best, {n / np.median(ts):9.0f} median ({1e3 * min(ts):.1f} ms); "
+              f"last call: shard ms per device {shard}", flush=True)
     for e in exs:
         e.close()
