@@ -539,6 +539,9 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 #ifndef SB_DESC_EXACT_GEOM
 #define SB_DESC_EXACT_GEOM 0
 #endif
+#ifndef SB_DESC_PAIR
+#define SB_DESC_PAIR 1   // two samples per lane and step, packed f32x2 arithmetic (descriptor_sample2)
+#endif
 constexpr int DESC_WARPS = SB_DESC_WARPS;
 constexpr int DESC_COPIES = SB_DESC_COPIES;
 constexpr int DESC_MAXROWS = 256;  // window rows: 2 * radius + 1 with radius <= 127 (+ the sentinel entry)
@@ -699,6 +702,102 @@ __device__ __forceinline__ void descriptor_sample(const DescGeom& G, const DescA
     __syncwarp();
 }
 
+// ---- two samples per lane and step (SB_DESC_PAIR) ----
+// The sample step is bound by instruction issue, and about a quarter of its instructions are plain f32 adds, multiplies
+// and FMAs.  A lane that takes TWO samples per step -- its samples of two consecutive batches of 32 -- runs those as
+// packed f32x2 operations (SASS FFMA2 / FADD2 / FMUL2: the same IEEE results as the scalar instructions, half the issue
+// slots); the SFU approximations, the float -> int conversions, the octant folding and the shared-memory accumulation
+// stay per sample.  Operation for operation the arithmetic of descriptor_sample, and the two samples are accumulated one
+// after the other, so every histogram word receives its contributions in the same order: bit-identical descriptors.
+__device__ __forceinline__ float2 dup2(const float v) { return make_float2(v, v); }
+
+__device__ __forceinline__ float2 fast_atan2_bins2(const float2 y, const float2 x) {
+    const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    const float2 a = mul2(make_float2(mn0, mn1), make_float2(rcp_approx(fmaxf(mx0, 1e-30f)), rcp_approx(fmaxf(mx1, 1e-30f))));
+    const float2 s = mul2(a, a);
+    float2 p = dup2(0x1.1c32bcp-7f);
+    p = fma2(p, s, dup2(-0x1.5e8130p-5f));
+    p = fma2(p, s, dup2(0x1.9f40a4p-4f));
+    p = fma2(p, s, dup2(-0x1.59126ap-3f));
+    p = fma2(p, s, dup2(0x1.0240f6p-2f));
+    p = fma2(p, s, dup2(-0x1.b26416p-2f));
+    p = fma2(p, s, dup2(0x1.45f2b4p+0f));
+    float2 r = mul2(p, a);
+    if (ay0 > ax0) r.x = 2.0f - r.x;
+    if (x.x < 0.f) r.x = 4.0f - r.x;
+    if (y.x < 0.f) r.x = 8.0f - r.x;
+    if (ay1 > ax1) r.y = 2.0f - r.y;
+    if (x.y < 0.f) r.y = 4.0f - r.y;
+    if (y.y < 0.f) r.y = 8.0f - r.y;
+    return r;
+}
+
+// the accumulation half of descriptor_sample for one sample: spatial parts sp-split into first / second orientation bin
+__device__ __forceinline__ void descriptor_scatter(float* hist, const int lane, const float row_floor, const float col_floor,
+                                                   const float ori_floor, const float vF0, const float vF1, const float vF2,
+                                                   const float vF3, const float vS0, const float vS1, const float vS2,
+                                                   const float vS3) {
+    const int r1 = (int)row_floor, q1 = (int)col_floor;
+    const int oi = (int)ori_floor;
+    const int hl = lane >> 4;
+    const int oF = ((oi + 1 - hl) & (6 | hl)) | hl;
+    const int oS = ((oi + hl) & (7 - hl)) | (1 - hl);
+    const int r2 = r1 + 1, q2 = q1 + 1;
+    const bool ok[4] = {((r1 | q1) & ~3) == 0, ((r1 | q2) & ~3) == 0, ((r2 | q1) & ~3) == 0, ((r2 | q2) & ~3) == 0};
+    constexpr int CO[4] = {0, DESC_CELL_WORDS, 4 * DESC_CELL_WORDS, 5 * DESC_CELL_WORDS};
+    float* const cellb = hist + (lane & (DESC_COPIES - 1)) + (r1 * 4 + q1) * DESC_CELL_WORDS;
+    float* const bF = cellb + oF * DESC_COPIES;
+    float* const bS = cellb + oS * DESC_COPIES;
+    const float vF[4] = {vF0, vF1, vF2, vF3}, vS[4] = {vS0, vS1, vS2, vS3};
+    float old[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (ok[k]) old[k] = bF[CO[k]];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (ok[k]) bF[CO[k]] = old[k] + vF[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (ok[k]) old[k] = bS[CO[k]];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (ok[k]) bS[CO[k]] = old[k] + vS[k];
+    __syncwarp();
+}
+
+__device__ __forceinline__ void descriptor_sample2(const DescGeom& G, const DescAt atA, const DescAt atB, const DescPix pA,
+                                                   const DescPix pB, float* hist, const int lane) {
+    const float2 fx = make_float2((float)atA.xw, (float)atB.xw), fy = make_float2((float)atA.yw, (float)atB.yw);
+    const float2 sin2 = dup2(G.sin_s), cos2 = dup2(G.cos_s), nsin2 = dup2(-G.sin_s);
+    const float2 rb = fma2(fx, sin2, fma2(fy, cos2, dup2(1.5f)));
+    const float2 cbn = fma2(fx, cos2, fma2(fy, nsin2, dup2(1.5f)));
+    const float2 wexp = mul2(fma2(fx, fx, mul2(fy, fy)), dup2(G.wscale));
+    const float2 dx = sub2(make_float2(pA.xp, pB.xp), make_float2(pA.xm, pB.xm));
+    const float2 dy = sub2(make_float2(pA.ym, pB.ym), make_float2(pA.yp, pB.yp));
+    const float2 d2 = fma2(dx, dx, mul2(dy, dy));
+    const float2 root = mul2(d2, make_float2(rsqrt_approx(fmaxf(d2.x, 1e-36f)), rsqrt_approx(fmaxf(d2.y, 1e-36f))));
+    const float2 mag = mul2(root, make_float2(ex2_approx(wexp.x), ex2_approx(wexp.y)));
+    const float2 obin = sub2(fast_atan2_bins2(dy, dx), dup2(G.ori_bins));
+    const float2 row_floor = make_float2(floorf(rb.x), floorf(rb.y));
+    const float2 col_floor = make_float2(floorf(cbn.x), floorf(cbn.y));
+    const float2 ori_floor = make_float2(floorf(obin.x), floorf(obin.y));
+    const float2 row_frac = sub2(rb, row_floor), col_frac = sub2(cbn, col_floor), ori_frac = sub2(obin, ori_floor);
+    const float2 c1 = mul2(mag, row_frac), c0 = sub2(mag, c1);
+    float2 sp[4];
+    sp[3] = mul2(c1, col_frac); sp[2] = sub2(c1, sp[3]);
+    sp[1] = mul2(c0, col_frac); sp[0] = sub2(c0, sp[1]);
+    // weight of the orientation bin a lane adds first: ori_frac or 1 - ori_frac (see descriptor_sample)
+    const float2 omf = sub2(dup2(1.0f), ori_frac);
+    const int hl = lane >> 4;
+    const float2 wF = make_float2((((int)ori_floor.x ^ hl) & 1) ? ori_frac.x : omf.x,
+                                  (((int)ori_floor.y ^ hl) & 1) ? ori_frac.y : omf.y);
+    float2 vF[4], vS[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { vF[k] = mul2(sp[k], wF); vS[k] = sub2(sp[k], vF[k]); }
+    descriptor_scatter(hist, lane, row_floor.x, col_floor.x, ori_floor.x, vF[0].x, vF[1].x, vF[2].x, vF[3].x,
+                       vS[0].x, vS[1].x, vS[2].x, vS[3].x);
+    descriptor_scatter(hist, lane, row_floor.y, col_floor.y, ori_floor.y, vF[0].y, vF[1].y, vF[2].y, vF[3].y,
+                       vS[0].y, vS[1].y, vS[2].y, vS[3].y);
+}
+
 // Window radius limit of the row table (8-bit spans): scale <= DESC_MAX_SCALE.  The extraction path stays below
 // scale 3.6 (radius 38); compute_descriptor on caller-supplied keypoints reports larger scales as invalid
 // arguments (SB200_E_INVALID) instead of computing something the crate would not.
@@ -813,6 +912,28 @@ __device__ __forceinline__ bool descriptor_warp(const DescTarget t, float* wsm /
         at.xw = (int)((cur_w & 255u) + cur_xo) - G.radius;
         return cur_k < n_rows;
     };
+#if SB_DESC_PAIR
+    if (total) {
+        // two batches of 32 samples per step; a cursor is never moved more than 63 samples past the last one, so it
+        // cannot leave the 255-column sentinel entry
+        DescAt at_a, at_b;
+        bool act = lookup(0, at_a);
+        DescPix p_a = descriptor_fetch(G, at_a, act);
+        act = lookup(32, at_b);
+        DescPix p_b = descriptor_fetch(G, at_b, act);
+        for (uint32_t base = 0; base < total; base += 64) {
+            const DescAt ca = at_a, cb = at_b;
+            const DescPix qa = p_a, qb = p_b;
+            if (base + 64 < total) {
+                act = lookup(32, at_a);
+                p_a = descriptor_fetch(G, at_a, act);
+                act = lookup(32, at_b);
+                p_b = descriptor_fetch(G, at_b, act);
+            }
+            descriptor_sample2(G, ca, cb, qa, qb, hist, lane);
+        }
+    }
+#else
     if (total) {
         DescAt at_next;
         bool a_next = lookup(0, at_next);
@@ -827,6 +948,7 @@ __device__ __forceinline__ bool descriptor_warp(const DescTarget t, float* wsm /
             descriptor_sample(G, at, px, hist, lane);
         }
     }
+#endif
     __syncwarp();
     // sum the private copies: lane owns flat[4*lane .. 4*lane+3]; rotated start => conflict-free reads
     float f[4];

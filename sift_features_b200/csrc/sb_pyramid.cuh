@@ -43,32 +43,6 @@ __device__ __forceinline__ float tap(const int l, const int i) { return FL == FL
 template <int FL>
 __device__ __forceinline__ float2 tap2(const int l, const int i) { return FL == FL_OPENCV ? c_taps2[l][i] : c_taps2_b[l][i]; }
 
-// Blackwell packed single precision (SASS FFMA2 / FADD2 / FMUL2): two independent IEEE round-to-nearest
-// operations per instruction, i.e. the same bits as the scalar fmaf / + / * -- but half the issue slots,
-// which is what bounds the wide-tap blurs.
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;"
-        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
-          "l"(*reinterpret_cast<unsigned long long*>(&c)));
-    return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    float2 d;
-    asm("add.rn.f32x2 %0, %1, %2;"
-        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    float2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;"
-        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return d;
-}
-
 // acc + a * k per half with a separately rounded product (the imageproc flavour's accumulation).  Scalar intrinsics:
 // ptxas contracts a mul.rn.f32x2 followed by an add.rn.f32x2 into one FFMA2 (observed in SASS; the explicit rounding
 // modifier does not stop it for the packed forms), which __fmul_rn / __fadd_rn are documented never to allow.
@@ -975,13 +949,6 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float d;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) {   // FADD2 with a negated operand: a - b, both halves
-    float2 d;
-    asm("sub.rn.f32x2 %0, %1, %2;"
-        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
     return d;
 }
 // rolling three-row state of one warp: the DoG values of rows (c-1, c, c+1) for the lane's two columns
