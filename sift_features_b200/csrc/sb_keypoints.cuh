@@ -540,7 +540,16 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
 #define SB_DESC_EXACT_GEOM 0
 #endif
 #ifndef SB_DESC_PAIR
-#define SB_DESC_PAIR 1   // two samples per lane and step, packed f32x2 arithmetic (descriptor_sample2)
+#define SB_DESC_PAIR 2   // 1: two samples per lane and step, packed f32x2 arithmetic (descriptor_sample2); 2: + two register sets
+#endif
+#ifndef SB_DESC_LIST_PAIR
+#define SB_DESC_LIST_PAIR 1   // the same choice for compute_descriptor on caller-supplied keypoints (k_descriptor_list)
+#endif
+#ifndef SB_DESC_LIST_MINB
+#define SB_DESC_LIST_MINB 3
+#endif
+#ifndef SB_DESC_MINB
+#define SB_DESC_MINB 3   // resident CTAs per SM the extraction kernel is compiled for (shared memory allows 3)
 #endif
 constexpr int DESC_WARPS = SB_DESC_WARPS;
 constexpr int DESC_COPIES = SB_DESC_COPIES;
@@ -562,6 +571,7 @@ struct DescGeom {
     const float* img;
     int w, h, pitch, x, y, radius;
     float sin_s, cos_s, orientation;
+    int park;         // pixel offset a lane without a sample loads around: the keypoint's pixel, clamped into the interior
     float ori_bins;   // orientation in histogram bins (8 per turn)
     float wscale;     // -(1/8) log2(e) / hist_width^2: exponent of the Gaussian weight per squared window distance
 };
@@ -604,11 +614,11 @@ struct DescAt { int yw, xw; };              // window coordinates of a lane's sa
 
 // A lane without a sample is parked in the row table's sentinel entry: window columns >= 255 - radius, which are
 // outside the rotated 4x4 grid for every orientation (|column| > radius = 2.5 sqrt(2) cells), so nothing of it is
-// accumulated whatever pixels it carries -- it loads the keypoint's own pixel neighbourhood (always inside the image)
-// instead of branching.
+// accumulated whatever pixels it carries -- it loads the neighbourhood of the keypoint's own pixel, clamped into the
+// image interior (DescGeom::park), instead of branching.
 __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const DescAt at, const bool active) {
     const int i = active ? (G.y + at.yw) * G.pitch + (G.x + at.xw)   // a layer holds < 2^31 floats: 32-bit offsets
-                         : G.y * G.pitch + G.x;
+                         : G.park;
     // one 64-bit address, kept opaque so that the neighbours are pointer +- pitch (two adds each) instead of
     // three more base + 64-bit index computations
     const float* pc = G.img + i;
@@ -807,6 +817,7 @@ __host__ __device__ __forceinline__ int descriptor_radius(const float scale) {
 }
 
 // returns false (warp-uniform, nothing written) when the keypoint's window exceeds DESC_MAX_RADIUS
+template <int PAIR>
 __device__ __forceinline__ bool descriptor_warp(const DescTarget t, float* wsm /* smem [DESC_SMEM_WORDS] */, int lane,
                                                 uint8_t* out /* 128 B */) {
     float* hist = wsm;
@@ -824,6 +835,8 @@ __device__ __forceinline__ bool descriptor_warp(const DescTarget t, float* wsm /
     const float xr = roundf(t.x), yr = roundf(t.y);
     G.x = xr > 0.f ? (int)fminf(xr, 1e9f) : 0;
     G.y = yr > 0.f ? (int)fminf(yr, 1e9f) : 0;
+    // (a caller-supplied keypoint may sit on the border or outside the image: its own neighbourhood is not loadable)
+    G.park = min(max(G.y, 1), max(G.h - 2, 1)) * G.pitch + min(max(G.x, 1), max(G.w - 2, 1));
     const float hist_width = 3.0f * t.scale;
     G.radius = descriptor_radius(t.scale);  // :800 (<= 38 on the extraction path)
     if (G.radius > DESC_MAX_RADIUS || !(t.scale > 0.f)) return false;
@@ -912,7 +925,38 @@ __device__ __forceinline__ bool descriptor_warp(const DescTarget t, float* wsm /
         at.xw = (int)((cur_w & 255u) + cur_xo) - G.radius;
         return cur_k < n_rows;
     };
-#if SB_DESC_PAIR
+    if constexpr (PAIR == 2) {
+    if (total) {
+        // two batches of 32 samples per step; a cursor is never moved more than 63 samples past the last one, so it
+        // cannot leave the 255-column sentinel entry
+        // two register sets take turns (the loop body is unrolled twice): the pixels of the next pair of batches are
+        // loaded into the set the current pair does not use, so nothing is moved between registers
+        DescAt a0, b0, a1, b1;
+        DescPix pa0, pb0, pa1, pb1;
+        bool act = lookup(0, a0);
+        pa0 = descriptor_fetch(G, a0, act);
+        act = lookup(32, b0);
+        pb0 = descriptor_fetch(G, b0, act);
+        for (uint32_t base = 0; base < total; base += 128) {
+            const bool more = base + 64 < total;
+            if (more) {
+                act = lookup(32, a1);
+                pa1 = descriptor_fetch(G, a1, act);
+                act = lookup(32, b1);
+                pb1 = descriptor_fetch(G, b1, act);
+            }
+            descriptor_sample2(G, a0, b0, pa0, pb0, hist, lane);
+            if (!more) break;
+            if (base + 128 < total) {
+                act = lookup(32, a0);
+                pa0 = descriptor_fetch(G, a0, act);
+                act = lookup(32, b0);
+                pb0 = descriptor_fetch(G, b0, act);
+            }
+            descriptor_sample2(G, a1, b1, pa1, pb1, hist, lane);
+        }
+    }
+    } else if constexpr (PAIR == 1) {
     if (total) {
         // two batches of 32 samples per step; a cursor is never moved more than 63 samples past the last one, so it
         // cannot leave the 255-column sentinel entry
@@ -933,7 +977,7 @@ __device__ __forceinline__ bool descriptor_warp(const DescTarget t, float* wsm /
             descriptor_sample2(G, ca, cb, qa, qb, hist, lane);
         }
     }
-#else
+    } else {
     if (total) {
         DescAt at_next;
         bool a_next = lookup(0, at_next);
@@ -948,7 +992,7 @@ __device__ __forceinline__ bool descriptor_warp(const DescTarget t, float* wsm /
             descriptor_sample(G, at, px, hist, lane);
         }
     }
-#endif
+    }
     __syncwarp();
     // sum the private copies: lane owns flat[4*lane .. 4*lane+3]; rotated start => conflict-free reads
     float f[4];
@@ -1061,7 +1105,7 @@ constexpr int DESC_CHUNK = SB_DESC_CHUNK;
 
 // The output keypoints of all images of the group form one work list (out_off is their exclusive prefix sum);
 // warps pull chunks from an atomic counter (see k_orient).
-__global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams P, const int n_img,
+__global__ void __launch_bounds__(32 * DESC_WARPS, SB_DESC_MINB) k_descriptor(const DescParams P, const int n_img,
                                                                 uint32_t* __restrict__ work) {
     extern __shared__ __align__(16) unsigned char desc_smem[];  // DESC_SMEM_BYTES, dynamic (> 48 KB)
     uint64_t* s_tab = reinterpret_cast<uint64_t*>(desc_smem);
@@ -1085,7 +1129,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams
             const float f = pow2i(-kp.octave);  // 2_f32.powi(-octave), src/lib.rs:768
             t.x = kp.x * f; t.y = kp.y * f; t.scale = kp.size * f;
             t.orientation = 360.0f - kp.angle;   // :766
-            descriptor_warp(t, s_hist[warp], lane, P.out_desc + (size_t)g * DESC_SIZE);
+            descriptor_warp<SB_DESC_PAIR>(t, s_hist[warp], lane, P.out_desc + (size_t)g * DESC_SIZE);
             if (lane == 0) {
                 OutKeyPoint o;  // DELTA_MIN = 0.5 undoes the seed upsampling, src/lib.rs:168-170
                 o.x = kp.x * 0.5f; o.y = kp.y * 0.5f; o.size = kp.size * 0.5f;
@@ -1099,7 +1143,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor(const DescParams
 // compute_descriptor on caller-supplied keypoints and a dense f32 image
 // (benches/descriptor.rs:18-32 shape; src/lib.rs:785).
 struct DescIn { float x, y, scale, orientation; };
-__global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor_list(const float* __restrict__ img, int w, int h,
+__global__ void __launch_bounds__(32 * DESC_WARPS, SB_DESC_LIST_MINB) k_descriptor_list(const float* __restrict__ img, int w, int h,
                                                                       int pitch, const DescIn* __restrict__ kps,
                                                                       unsigned long long n, uint8_t* __restrict__ out,
                                                                       uint32_t* __restrict__ err) {
@@ -1115,7 +1159,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_descriptor_list(const float
         DescTarget t;
         t.img = img; t.w = w; t.h = h; t.pitch = pitch;
         t.x = k.x; t.y = k.y; t.scale = k.scale; t.orientation = k.orientation;
-        if (!descriptor_warp(t, s_hist[warp], lane, out + j * DESC_SIZE)) {
+        if (!descriptor_warp<SB_DESC_LIST_PAIR>(t, s_hist[warp], lane, out + j * DESC_SIZE)) {
             reinterpret_cast<uint32_t*>(out + j * DESC_SIZE)[lane] = 0u;
             if (lane == 0) atomicOr(err, 1u);   // reported as SB200_E_INVALID by the next synchronising call
         }
