@@ -1201,7 +1201,10 @@ __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema_tma(const __grid_c
 // written by this CTA).
 // ---------------------------------------------------------------------------
 constexpr int TAIL_MAX_PX = 2304;     // 9 KB per buffer, e.g. 64 x 36: larger octaves keep one CTA busy for too long
-constexpr int TAIL_THREADS = 512;
+#ifndef SB_TAIL_THREADS
+#define SB_TAIL_THREADS 512
+#endif
+constexpr int TAIL_THREADS = SB_TAIL_THREADS;
 constexpr size_t TAIL_SMEM = 2 * (size_t)TAIL_MAX_PX * sizeof(float);
 
 struct TailParams {
