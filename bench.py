@@ -448,9 +448,20 @@ def kernel_table(m, w, h, B, peak, sf, sm_mhz):
         rows.append(r)
 
     groups = max(1, imgs // B)
+    desc_extra = {"ns_per_keypoint": 1e6 * st["descriptor"]["ms"] / imgs / max(m["kp_per_image"], 1)}
+    try:   # the roofline this kernel is bound by: warp-instructions (ncu smsp__inst_executed.sum of the same kernel on the
+        # 1080p noise workload, profiles/traffic.json) against the issue slots of the SMs, 4 per SM and clock
+        wipk = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_descriptor_1080p"]["warp_instructions_per_keypoint"]
+        if sm_mhz and st["descriptor"]["ms"] > 0:
+            desc_extra["warp_instructions_per_keypoint"] = wipk
+            desc_extra["issue_slot_frac"] = (wipk * m["kp_per_image"] * imgs / (st["descriptor"]["ms"] * 1e-3)
+                                             / (148 * 4 * sm_mhz * 1e6))
+    except Exception:
+        pass
     add("k_descriptor", st["descriptor"]["ms"], groups, m["desc_bytes_per_image"],
-        "issue", "instruction-issue bound on L2-resident patches (ncu: profiles/r02_*): the HBM fraction is low by nature",
-        {"ns_per_keypoint": 1e6 * st["descriptor"]["ms"] / imgs / max(m["kp_per_image"], 1)})
+        "issue", "instruction-issue bound on L2-resident patches (ncu: profiles/r02_*): the HBM fraction is low by nature; "
+                 "issue_slot_frac = measured warp-instructions per second against 4 issue slots per SM and clock",
+        desc_extra)
     add("k_orient (+ k_kpscan, k_emit)", st["orient"]["ms"], groups, 0.0, "issue / latency",
         "ordered per-bin accumulation on L2-resident patches")
     ex_ms = sum(v[0] for (o, k), v in fine.items() if k == "extrema")

@@ -1,9 +1,15 @@
 #!/bin/bash
 # Round-2 evidence for profiles/ (run on the GPU box through gpurun; every ncu pass follows the same command exiting 0
-# without ncu).  Produces under gpurun_out/: launch lists of the 1080p and 640x480 bench workloads and of ONE
-# single-image 1080p call, and --set full captures (source view included) of the heaviest kernels.
+# without ncu).  Produces under gpurun_out/: the bench lines of both arms, per-launch CUDA-event profiles, launch lists
+# of the 1080p and 640x480 bench workloads and of ONE single-image 1080p call, and --set full captures (source view
+# included) of the heaviest kernels.  tools/r02_profiles.py turns them into the files of profiles/.
 set -x
 mkdir -p gpurun_out
+python bench.py > gpurun_out/r02_bench_1080p.json 2> gpurun_out/r02_bench_1080p.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_1080p.json 2> /dev/null
+python tools/fine_profile.py 1080p > gpurun_out/r02_fine_1080p.txt 2>&1
+python tools/fine_profile.py vga > gpurun_out/r02_fine_vga.txt 2>&1
+python tools/fine_profile.py 4k > gpurun_out/r02_fine_4k.txt 2>&1
 B="python bench.py --steps 2 --warmup 3 --no-cpu --no-extra"
 $B > gpurun_out/r02_plain_1080p.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/r02_launches_1080p_b32.csv $B > /dev/null 2>&1
@@ -14,7 +20,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 S="python bench.py --steps 1 --warmup 3 --no-cpu --no-extra"
 ncu --set full --clock-control none --import-source on -k regex:k_descriptor -c 1 -o gpurun_out/r02_desc -f $S > gpurun_out/r02_ncu_desc.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_orient -c 1 -o gpurun_out/r02_orient -f $S > gpurun_out/r02_ncu_orient.log 2>&1
-ncu --set full --clock-control none -k 'regex:k_blur_march|k_extrema_tma|k_upsample' -c 8 -o gpurun_out/r02_pyr -f $S > gpurun_out/r02_ncu_pyr.log 2>&1
+ncu --set full --clock-control none -k 'regex:k_blur_march|k_extrema_tma|k_upsample' -c 14 -o gpurun_out/r02_pyr -f $S > gpurun_out/r02_ncu_pyr.log 2>&1
 M="python bench.py --workload match --steps 2 --warmup 3 --no-cpu"
 $M > gpurun_out/r02_plain_match.log 2>&1 &&
 ncu --set full --clock-control none -k regex:k_match_nn -c 1 -o gpurun_out/r02_match -f $M > gpurun_out/r02_ncu_match.log 2>&1
