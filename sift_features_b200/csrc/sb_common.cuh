@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace sb {
 
@@ -84,6 +85,22 @@ struct DevKeyPoint {
 struct OutKeyPoint {
     float x, y, size, angle, response;
 };
+
+// Debug build (-DSB_BOUNDS_CHECK, tools/bounds_check.sh): the data-dependent global loads of the keypoint kernels
+// (refinement, orientation, descriptor) verify their address against the extent of the layer they read and trap with a
+// message when it lies outside -- compute-sanitizer is not available on the GPU pool.
+#ifdef SB_BOUNDS_CHECK
+#define SB_CHECK_LOAD(ptr, base, elems, what)                                                                       \
+    do {                                                                                                            \
+        if ((ptr) < (base) || (ptr) >= (base) + (elems)) {                                                          \
+            printf("SB_BOUNDS_CHECK: %s reads element %lld of a %lld-element layer\n", what,                        \
+                   (long long)((ptr) - (base)), (long long)(elems));                                                \
+            __trap();                                                                                               \
+        }                                                                                                           \
+    } while (0)
+#else
+#define SB_CHECK_LOAD(ptr, base, elems, what) do { } while (0)
+#endif
 
 // Blackwell packed single precision (SASS FFMA2 / FADD2 / FMUL2): two independent IEEE round-to-nearest
 // operations per instruction, i.e. the same bits as the scalar fmaf / + / * -- but half the issue slots,

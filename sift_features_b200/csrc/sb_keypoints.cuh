@@ -55,6 +55,8 @@ struct DogView {
     int pitch;
     __device__ __forceinline__ float operator()(int l, int y, int x) const {
         const float* p = g + (long long)l * ls + (long long)y * pitch + x;
+        SB_CHECK_LOAD(p, g, N_LAYERS * ls, "k_refine DoG (lower layer)");
+        SB_CHECK_LOAD(p + ls, g, N_LAYERS * ls, "k_refine DoG (upper layer)");
         return __ldg(p + ls) - __ldg(p);
     }
 };
@@ -263,6 +265,8 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
                 const float* c = I + (yi * pitch + xi);
                 asm volatile("" : "+l"(c));   // one address; the neighbours are pointer +- pitch
                 const ptrdiff_t dp = pitch;
+                SB_CHECK_LOAD(c - dp, I, (long long)h * pitch, "k_orient (row above)");
+                SB_CHECK_LOAD(c + dp, I, (long long)h * pitch, "k_orient (row below)");
                 q = make_float4(__ldg(c + 1), __ldg(c - 1), __ldg(c - dp), __ldg(c + dp));
             }
             xq_n += 32;
@@ -624,6 +628,10 @@ __device__ __forceinline__ DescPix descriptor_fetch(const DescGeom& G, const Des
     const float* pc = G.img + i;
     asm volatile("" : "+l"(pc));
     const ptrdiff_t pitch = G.pitch;
+    SB_CHECK_LOAD(pc - pitch, G.img, (long long)G.h * G.pitch, "descriptor_fetch (row above)");
+    SB_CHECK_LOAD(pc + pitch, G.img, (long long)G.h * G.pitch, "descriptor_fetch (row below)");
+    SB_CHECK_LOAD(pc - 1, G.img, (long long)G.h * G.pitch, "descriptor_fetch (left)");
+    SB_CHECK_LOAD(pc + 1, G.img, (long long)G.h * G.pitch, "descriptor_fetch (right)");
     DescPix q;
     q.xp = __ldg(pc + 1); q.xm = __ldg(pc - 1);
     q.ym = __ldg(pc - pitch); q.yp = __ldg(pc + pitch);

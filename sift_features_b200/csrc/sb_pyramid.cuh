@@ -1357,19 +1357,22 @@ __global__ void __launch_bounds__(256) k_compact(const PyrLayout L, const uint32
     const int ridx = blockIdx.x * 8 + warp;
     const long long img = blockIdx.y;
     if (ridx >= L.img_rows) return;
-    const uint32_t cnt = rows[img * L.img_rows + ridx];
-    if (cnt == 0) return;
     int o = 0;
     while (o + 1 < L.n_oct && ridx >= L.o[o + 1].row_base) o++;
     const OctLayout& ol = L.o[o];
     const int local = ridx - ol.row_base;
     const int s = local / ol.h + 1, y = local - (s - 1) * ol.h;
     const uint2* words = reinterpret_cast<const uint2*>(mask + img * L.img_mask_words + ol.mask_off + (long long)local * ol.mask_pitch);
-    uint32_t pos0 = rowoff[img * L.img_rows + ridx];
-    CandKey* out = keys + img * (long long)cap;
     const int ns = ol.mask_pitch >> 1;
+    // the row's count, its scanned offset and its first 32 mask word pairs are independent loads: all three are in
+    // flight before the count decides whether the row has anything to emit (the kernel is a chain of round trips)
+    const uint32_t cnt = rows[img * L.img_rows + ridx];
+    uint32_t pos0 = rowoff[img * L.img_rows + ridx];
+    uint2 first = (lane < ns) ? words[lane] : make_uint2(0u, 0u);
+    if (cnt == 0) return;
+    CandKey* out = keys + img * (long long)cap;
     for (int sb = 0; sb < ns; sb += 32) {
-        uint2 word = (sb + lane < ns) ? words[sb + lane] : make_uint2(0u, 0u);
+        uint2 word = sb == 0 ? first : ((sb + lane < ns) ? words[sb + lane] : make_uint2(0u, 0u));
         uint32_t c = __popc(word.x) + __popc(word.y), incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
