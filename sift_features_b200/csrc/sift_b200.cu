@@ -91,6 +91,8 @@ struct Slot {
     uint64_t first_img = 0;
     int64_t limit = -1;
     bool busy = false;
+    bool staged = false;          // the slot's pinned staging buffer already holds the group starting at staged_first
+    uint64_t staged_first = 0;
 };
 
 // chunks of bitstreams in flight: JPEG_AHEAD chunks are decoding (round-robin over JPEG_STREAMS streams, so that
@@ -1037,7 +1039,7 @@ int run_pipeline(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, ui
 // counter: one core moves ~10 GB/s, a 32-image 1080p group is 66 MB and the results of 8192 VGA images 1.5 GB.
 struct CopyJob { void* dst; const void* src; size_t bytes; };
 void parallel_copy(const std::vector<CopyJob>& jobs) {
-    constexpr size_t CHUNK = (size_t)4 << 20;
+    constexpr size_t CHUNK = (size_t)2 << 20;
     struct Piece { char* d; const char* s; size_t n; };
     std::vector<Piece> pieces;
     size_t total = 0;
@@ -1047,7 +1049,11 @@ void parallel_copy(const std::vector<CopyJob>& jobs) {
             total += pieces.back().n;
         }
     unsigned hw = std::thread::hardware_concurrency();
-    const size_t nt = std::min<size_t>({pieces.size(), (size_t)std::max(1u, std::min(hw ? hw : 4u, 16u)), total / ((size_t)8 << 20) + 1});
+    size_t nt = std::min<size_t>({pieces.size(), (size_t)std::max(1u, std::min(hw ? hw : 4u, 16u)), total / ((size_t)3 << 20) + 1});
+    if (const char* e = getenv("SB200_COPY_THREADS")) {   // experiments; 0 skips the copy altogether (timing only)
+        if (atoi(e) == 0) return;
+        nt = std::min<size_t>(pieces.size(), (size_t)std::max(1, atoi(e)));
+    }
     if (nt <= 1) {
         for (auto& q : pieces) memcpy(q.d, q.s, q.n);
         return;
@@ -1175,6 +1181,39 @@ int fetch_decoded(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img
 
 // upload (or decode) + full pipeline + async read-back of the counts for one group; channels = 1 (gray) or 3 / 4
 // (RGB / RGBA, converted to luma on the device)
+// Pageable input: packs the group's pixels into the slot's pinned staging buffer (host work only).  The buffer is free
+// as soon as the previous copy OUT of it is over -- long before the slot's previous group has finished on the GPU --,
+// so the batch loop calls this for the next group while it waits for that previous group, and by the time the slot is
+// collected the upload can be issued at once, as for pinned input.
+int stage_group(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img, uint32_t n, uint32_t w, uint32_t h) {
+    if (src.jpeg) return SB200_OK;
+    const uint32_t channels = src.channels, stride = src.stride;
+    const uint64_t image_stride = src.image_stride;
+    const uint8_t* img = src.img + first_img * image_stride;
+    if (is_device_accessible_host(img)) return SB200_OK;
+    const size_t rowb = (size_t)w * channels;   // bytes per packed row
+    if (channels > 1) {
+        int rc = ensure_rgb(ctx, s, rowb * h * ctx->max_batch);
+        if (rc) return rc;
+    }
+    uint8_t* const h_up = channels > 1 ? s.h_rgb : s.h_in;
+    const bool contiguous = (image_stride == (uint64_t)stride * h);
+    CU(cudaEventSynchronize(s.ev_upload));
+    std::vector<CopyJob> jobs;
+    if (stride == rowb) {
+        if (contiguous) jobs.push_back({h_up, img, rowb * h * n});
+        else for (uint32_t i = 0; i < n; i++) jobs.push_back({h_up + (size_t)i * rowb * h, img + i * image_stride, rowb * h});
+    } else {
+        for (uint32_t i = 0; i < n; i++)
+            for (uint32_t y = 0; y < h; y++)
+                jobs.push_back({h_up + ((size_t)i * h + y) * rowb, img + i * image_stride + (size_t)y * stride, rowb});
+    }
+    parallel_copy(jobs);
+    s.staged = true;
+    s.staged_first = first_img;
+    return SB200_OK;
+}
+
 int launch_group(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img, uint32_t n, uint32_t w, uint32_t h,
                  int64_t limit) {
     cudaStream_t st = s.stream;
@@ -1204,20 +1243,13 @@ int launch_group(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img,
                                          cudaMemcpyHostToDevice, st));
             }
         } else {
-            // pageable memory: pack into the slot's pinned staging buffer, then one async copy.  Only the previous copy
-            // OUT of that buffer has to be over (it was issued a whole group ago), not the slot's previous group, so the
-            // packing of group g+1 runs on the host while the GPU computes group g
-            CU(cudaEventSynchronize(s.ev_upload));
-            std::vector<CopyJob> jobs;
-            if (stride == rowb) {
-                if (contiguous) jobs.push_back({h_up, img, rowb * h * n});
-                else for (uint32_t i = 0; i < n; i++) jobs.push_back({h_up + (size_t)i * rowb * h, img + i * image_stride, rowb * h});
-            } else {
-                for (uint32_t i = 0; i < n; i++)
-                    for (uint32_t y = 0; y < h; y++)
-                        jobs.push_back({h_up + ((size_t)i * h + y) * rowb, img + i * image_stride + (size_t)y * stride, rowb});
+            // pageable memory: packed into the slot's pinned staging buffer (stage_group, normally already done by
+            // the batch loop while the slot's previous group was still running), then one async copy
+            if (!(s.staged && s.staged_first == first_img)) {
+                int rc = stage_group(ctx, s, src, first_img, n, w, h);
+                if (rc) return rc;
             }
-            parallel_copy(jobs);
+            s.staged = false;
             CU(cudaMemcpyAsync(d_up, h_up, rowb * h * n, cudaMemcpyHostToDevice, st));
             CU(cudaEventRecord(s.ev_upload, st));
         }
@@ -1639,6 +1671,7 @@ static int extract_batch_impl(sb200_ctx* ctx, const Source& src, uint32_t n, uin
     for (auto& s : ctx->slot) {
         CU(cudaStreamSynchronize(s.stream));  // results of the previous call are released
         s.busy = false;                        // groups a failed call left behind are dropped, not collected
+        s.staged = false;
     }
     ctx->res_n = 0;
     ctx->have_pyramid = false;
@@ -1674,6 +1707,11 @@ static int extract_batch_impl(sb200_ctx* ctx, const Source& src, uint32_t n, uin
         // groups complete in launch order; the slot's previous group was collected before this launch (below)
         rc = launch_group(ctx, s, src, first, sizes[g], w, h, features_limit);
         if (rc) return rc;
+        // pageable input: pack the next group now, while the GPU works (its staging buffer is free long before its slot)
+        if (g + 1 < sizes.size()) {
+            rc = stage_group(ctx, ctx->slot[(g + 1) % N_SLOTS], src, first + sizes[g], sizes[g + 1], w, h);
+            if (rc) return rc;
+        }
         // the slot the NEXT group will use must be free again: collect the group that ran in it
         if (g + 1 >= (uint32_t)N_SLOTS) {
             rc = collect_group(ctx, ctx->slot[(g + 1) % N_SLOTS]);
