@@ -605,13 +605,15 @@ int set_imageproc_attrs(sb200_ctx* ctx) {
     return set_march_attr<LI, false, FL_IMAGEPROC>(ctx);
 }
 
-// Launch shape of the marching blur: the (strip, image) columns of the launch are cut into bands of 32 output rows
-// and dealt out evenly, in order, to the CTAs of the grid (k_blur_march).  A CTA marches down a contiguous run of
-// bands -- the rest of one column, the head of the next.  The run length is chosen so that the grid is a whole number
-// of waves of the machine's resident-CTA slots (no partially filled last wave, whatever the image height, strip count
-// and batch size) with runs of about MARCH_TARGET_BANDS bands: long enough to amortise a piece's pipeline start and
-// 2R halo rows, short enough that the CTAs in flight at any time work on neighbouring strips of a few images (their
-// halos hit in L2 and their rows share DRAM pages -- one wave of very long runs measured 1.3-1.5x slower).
+// Launch shape of the marching blur (k_blur_march): the (strip, image) columns of the launch are cut into bands of 32
+// output rows.
+//   * A launch of less than about 1.5 waves of the machine's resident-CTA slots (the small octaves, single images) deals
+//     the bands of all columns out as ONE sequence in equal runs, one run per slot: a CTA marches the rest of one column
+//     and the head of the next, every slot gets the same number of bands whatever the image height, strip count and batch
+//     size are, and a launch that cannot fill the machine at all gives every CTA a single band.
+//   * A launch of several waves cuts every column into k pieces of (almost) equal length, one piece per CTA (see below):
+//     one pipeline start per CTA, the CTAs of neighbouring strips walk the same rows at the same time (their halos hit
+//     in L2, their rows share DRAM pages), and the hardware's CTA scheduler balances the waves.
 constexpr int MARCH_MIN_BANDS = 2;
 constexpr int MARCH_TARGET_BANDS = 17;
 template <int LI, bool DEC, int FL = FL_OPENCV>
