@@ -154,15 +154,16 @@ def test_blur_aligned_pieces(sf, oracle, monkeypatch, pieces, size):
     _check_image(sf, oracle, noise_image(size[0], size[1], 33 + pieces))
 
 
-def test_blur_batch_distribution(sf, oracle):
+@pytest.mark.parametrize("w,h,n", [(640, 480, 48), (1000, 700, 24)])
+def test_blur_batch_distribution(sf, oracle, w, h, n):
     """A batch large enough for the multi-wave (aligned pieces) distribution on octave 0 and the single-wave one on
-    the small octaves: every image of the batch equals the single-image result, and image 0 equals the oracle."""
-    w, h, n = 640, 480, 48
+    the small octaves (the second shape: strips and bands that end inside the image, three pieces per column): every
+    image of the batch equals the single-image result, and image 0 equals the oracle."""
     imgs = np.stack([noise_image(w, h, 900 + i) for i in range(n)])
     with sf.Extractor(w, h, n) as ex:
         off, kps, desc = ex.sift_batch(imgs)
     with sf.Extractor(w, h, 1) as ex1:
-        for i in (0, 17, n - 1):
+        for i in (0, n // 3 + 1, n - 1):
             one = ex1.sift(imgs[i])
             a, b = int(off[i]), int(off[i + 1])
             assert b - a == len(one) and b > a
