@@ -277,6 +277,39 @@ struct UpsampleParams {
 
 constexpr int UPS_ROWS = 8;   // input row pairs per CTA (amortises the table set-up and the CTA launch)
 
+// One 2 x 4 block of the upsampled image: output rows {2y+1, 2y+2} (y = -1 yields output row 0 only), output columns
+// {4k .. 4k+3}, from input rows (y, y+1) and input columns 2k-1 .. 2k+2, all clamped at the border (where the lerp
+// degenerates to fma(0, t, a) = a exactly as the reference's clamped index does).  s_norm = v / 255 for the 256 pixel
+// values.  Horizontal pass first, then vertical (OpenCV's resize order).
+__device__ __forceinline__ void upsample_block(const uint8_t* __restrict__ in, const int W, const int H, const int in_stride,
+                                               const float* __restrict__ s_norm, const int k, const int y, float o[2][4]) {
+    const int y0 = max(y, 0), y1 = min(y + 1, H - 1);
+    float a[2][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int x = min(max(2 * k - 1 + c, 0), W - 1);
+        a[0][c] = s_norm[in[(long long)y0 * in_stride + x]];
+        a[1][c] = s_norm[in[(long long)y1 * in_stride + x]];
+    }
+    // horizontal pass: out col 4k = lerp(c0, c1, .75), 4k+1 = lerp(c1, c2, .25), 4k+2 = lerp(c1, c2, .75), 4k+3 = lerp(c2, c3, .25)
+    float hrow[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        hrow[r][0] = fmaf(a[r][1] - a[r][0], 0.75f, a[r][0]);
+        hrow[r][1] = fmaf(a[r][2] - a[r][1], 0.25f, a[r][1]);
+        hrow[r][2] = fmaf(a[r][2] - a[r][1], 0.75f, a[r][1]);
+        hrow[r][3] = fmaf(a[r][3] - a[r][2], 0.25f, a[r][2]);
+    }
+    // the reference clamps the source index and zeroes the weight at the borders (column 0 and 2W-1)
+    if (k == 0) { hrow[0][0] = a[0][1]; hrow[1][0] = a[1][1]; }   // 2k-1 < 0: both taps are column 0
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const float f = r ? 0.75f : 0.25f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) o[r][c] = fmaf(hrow[1][c] - hrow[0][c], f, hrow[0][c]);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
     // v / 255 for the 256 possible pixel values (the IEEE division itself, done once per CTA instead of 8x per thread)
     __shared__ float s_norm[256];
@@ -293,36 +326,15 @@ __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
   for (int yy = 0; yy < UPS_ROWS; yy++) {
     const int y = (int)blockIdx.y * UPS_ROWS + yy - 1;        // input row pair (y, y+1); y = -1 yields output row 0
     if (y >= H) break;
-    const int y0 = max(y, 0), y1 = min(y + 1, H - 1);
-    float a[2][4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const int x = min(max(2 * k - 1 + c, 0), W - 1);
-        a[0][c] = s_norm[in[(long long)y0 * p.in_stride + x]];
-        a[1][c] = s_norm[in[(long long)y1 * p.in_stride + x]];
-    }
-    // horizontal pass: out col 4k = lerp(c0, c1, .75), 4k+1 = lerp(c1, c2, .25), 4k+2 = lerp(c1, c2, .75), 4k+3 = lerp(c2, c3, .25)
-    float hrow[2][4];
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        hrow[r][0] = fmaf(a[r][1] - a[r][0], 0.75f, a[r][0]);
-        hrow[r][1] = fmaf(a[r][2] - a[r][1], 0.25f, a[r][1]);
-        hrow[r][2] = fmaf(a[r][2] - a[r][1], 0.75f, a[r][1]);
-        hrow[r][3] = fmaf(a[r][3] - a[r][2], 0.25f, a[r][2]);
-    }
-    // the reference clamps the source index and zeroes the weight at the borders (column 0 and 2W-1)
-    if (k == 0) { hrow[0][0] = a[0][1]; hrow[1][0] = a[1][1]; }   // 2k-1 < 0: both taps are column 0
+    float o[2][4];
+    upsample_block(in, W, H, p.in_stride, s_norm, k, y, o);
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const int Y = 2 * y + 1 + r;
         if (Y < 0 || Y >= 2 * H) continue;
-        const float f = r ? 0.75f : 0.25f;
-        float o[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) o[c] = fmaf(hrow[1][c] - hrow[0][c], f, hrow[0][c]);
         float* q = dst + (long long)Y * p.pitch + 4 * k;
-        if (full) *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
-        else for (int c = 0; c < 4 && 4 * k + c < 2 * W; c++) q[c] = o[c];
+        if (full) *reinterpret_cast<float4*>(q) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
+        else for (int c = 0; c < 4 && 4 * k + c < 2 * W; c++) q[c] = o[r][c];
     }
   }
 }
@@ -653,12 +665,23 @@ struct MarchCfg {
     static_assert((TW / 2) * (BH / PY) == THREADS, "one column-pass task per thread");
 };
 
-template <int L, bool DECIMATE, int FL = FL_OPENCV>
+// SEEDF (the seed blur of the OpenCV flavour, L = 0): the input bands are not loaded but COMPUTED -- the CTA upsamples
+// the u8 input into its stage buffer (upsample_block: the arithmetic of k_upsample2x, 2 x 4 output blocks aligned with the
+// band: band rows start at an odd row of the upsampled image and box columns at a multiple of 4) -- so the upsampled image
+// is never written to and read back from HBM (12.25 -> 4.25 bytes per seed pixel).  One stage buffer, no TMA, no
+// mbarriers: produce band j+1, barrier, row pass of j+1 and column pass of j-1, barrier.  Columns / rows outside the image
+// are left to the border logic below, exactly as for a loaded band.  Bit-identical to the two-kernel seed, and measured
+// SLOWER (the u8 loads of the produce phase are exposed and the phases serialise: 731 against 563 us per 32-image 1080p
+// group), so the pipeline only takes it with SB200_SEED=fused.
+template <int L, bool DECIMATE, int FL = FL_OPENCV, bool SEEDF = false>
 __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTAS_PER_SM) k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
                                                         const int src_layer, const int bands_per_cta, const int strips,
                                                         const long long total_bands) {
     static_assert(FL == FL_OPENCV || !DECIMATE, "the imageproc flavour decimates in its own kernel");
+    static_assert(!SEEDF || (L == 0 && FL == FL_OPENCV && !DECIMATE), "the fused seed is layer 0 of the OpenCV flavour");
     using C = MarchCfg<L, FL>;
+    static_assert(!SEEDF || (C::RA % 4 == 0 && C::BW % 4 == 0 && C::TW % 4 == 0 && C::BH % 2 == 0 && (C::R & 1) == 1 && C::THREADS >= 256),
+                  "upsample blocks are aligned with the band");
     constexpr int R = C::R;
     constexpr int STAGE_FLOATS = C::BH * C::BW, SLOT_FLOATS = C::BH * C::IPITCH;
     extern __shared__ __align__(1024) float smem_march[];
@@ -667,6 +690,8 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
     float* const inter = smem_march + C::NSTG * STAGE_FLOATS;      // RING_ROWS x IPITCH
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = p.w, h = p.h;
+    __shared__ float s_norm[SEEDF ? 256 : 1];   // v / 255 for the 256 pixel values (the IEEE division, once per CTA)
+    if (SEEDF && tid < 256) s_norm[tid] = (float)tid / 255.0f;
     // Work distribution: the (strip, image) columns of the launch, each cut into bands of BH output rows, form one
     // sequence of total_bands bands; CTA c owns the bands [c * bands_per_cta, (c + 1) * bands_per_cta) of it and marches
     // down every piece of a column that falls into its range.  Every CTA gets the same number of bands whatever the
@@ -697,7 +722,7 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
     const int n_in = (yb - ya + 2 * R + C::BH - 1) / C::BH;    // input bands (n_out or n_out + 1)
     const int in0 = ya - R;                                    // first input row of band 0
     const bool hedge = tx0 - R < 0 || tx0 + C::TW + R > w;
-    if (tid == 0) {   // fresh barriers per piece (every load of the previous piece has been waited for)
+    if (!SEEDF && tid == 0) {   // fresh barriers per piece (every load of the previous piece has been waited for)
 #pragma unroll
         for (int b = 0; b < C::NSTG; b++) {
             if (!first_piece) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar[b])) : "memory");
@@ -716,16 +741,36 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
               "r"(src_layer), "r"(img), "r"(bar_a)
             : "memory");
     };
-    if (tid == 0) {
+    if (!SEEDF && tid == 0) {
 #pragma unroll
         for (int b = 0; b < C::NSTG; b++)
             if (b < n_in) issue(b, b);
     }
+    // SEEDF: input band b, upsampled from the u8 image straight into stage buffer 0.  Band row pair rp holds the rows
+    // {2y+1, 2y+2} of the upsampled image with y = (band_y0 - 1) / 2 + rp (band_y0 is odd), box column group g its
+    // columns {4k .. 4k+3} with k = (tx0 - RA) / 4 + g.
+    auto produce = [&](const int b) {
+        const int ypair0 = (in0 + b * C::BH - 1) >> 1;
+        const int kg0 = (tx0 - C::RA) >> 2;
+        const uint8_t* const in = p.in + (long long)img * p.in_img_stride;
+        constexpr int NG = C::BW / 4;
+        for (int t = tid; t < (C::BH / 2) * NG; t += C::THREADS) {
+            const int rp = t / NG, g = t - rp * NG;
+            const int y = ypair0 + rp, k = kg0 + g;
+            if (k < 0 || 4 * k >= w || y < -1 || y >= p.in_h) continue;   // wholly outside the image: never read
+            float o[2][4];
+            upsample_block(in, p.in_w, p.in_h, p.in_stride, s_norm, k, y, o);
+            float4* const q = reinterpret_cast<float4*>(stage + (2 * rp) * C::BW + 4 * g);
+            q[0] = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+            q[C::BW / 4] = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+        }
+    };
 
     // ---- row pass of input band b (stage buffer stg, its mbarrier at `parity`; ring slot `slot`):
     //      warp = the band's 32 rows x one 8-pixel segment ----
-    auto row_pass = [&](const int b, const int stg, const uint32_t parity, const int slot) {
-        {
+    auto row_pass = [&](const int b, const int stg_, const uint32_t parity, const int slot) {
+        const int stg = SEEDF ? 0 : stg_;
+        if (!SEEDF) {
             const uint32_t bar_a = smem_u32(&bar[stg]);
             uint32_t done = 0;
             while (!done) {
@@ -888,6 +933,7 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
         if (DECIMATE) dband += (long long)(C::BH / 2) * p.dec_pitch;
     };
 
+    if (SEEDF) { produce(0); __syncthreads(); }
     row_pass(0, 0, 0u, 0);
     __syncthreads();
     int rslot = 1, cslot = 0;   // ring slots of band j+1 (row pass) and band j-1 (column pass)
@@ -896,8 +942,9 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
     uint32_t rpar = 0;          // ... and the phase of its mbarrier, == ((j+1) / NSTG) & 1
     for (int j = 0; j <= n_out; j++) {
         // band j was row-passed before the last barrier: its stage buffer is free for band j+NSTG
-        if (tid == 0 && j + C::NSTG < n_in) issue(j + C::NSTG, fstg);
+        if (!SEEDF && tid == 0 && j + C::NSTG < n_in) issue(j + C::NSTG, fstg);
         fstg = fstg == C::NSTG - 1 ? 0 : fstg + 1;
+        if (SEEDF && j + 1 < n_in) { produce(j + 1); __syncthreads(); }   // (band j was row-passed before the last barrier)
         if (j + 1 < n_in) row_pass(j + 1, rstg, rpar, rslot);
         if (rstg == C::NSTG - 1) { rstg = 0; rpar ^= 1u; } else rstg++;
         rslot = rslot == 2 ? 0 : rslot + 1;

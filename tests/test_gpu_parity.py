@@ -172,10 +172,12 @@ def test_blur_batch_distribution(sf, oracle, w, h, n):
     _check_image(sf, oracle, imgs[0])
 
 
-@pytest.mark.parametrize("env", [{"SB200_BLUR": "tile"}, {"SB200_TAIL": "0"}, {"SB200_GRAPHS": "0", "SB200_FORK": "0"}])
+@pytest.mark.parametrize("env", [{"SB200_BLUR": "tile"}, {"SB200_TAIL": "0"}, {"SB200_GRAPHS": "0", "SB200_FORK": "0"},
+                                 {"SB200_SEED": "fused"}])
 def test_alternative_paths(sf, oracle, monkeypatch, env):
-    """The debugging switches select older / simpler code paths (independent-tile TMA blur, per-layer launches for
-    the small octaves, plain single-stream launches without graph capture): same bit-exact results."""
+    """The debugging switches select older / simpler / alternative code paths (independent-tile TMA blur, per-layer
+    launches for the small octaves, plain single-stream launches without graph capture, the seed blur that upsamples
+    its own input bands): same bit-exact results."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     _check_image(sf, oracle, noise_image(520, 390, 77))
