@@ -281,16 +281,21 @@ constexpr int UPS_ROWS = 8;   // input row pairs per CTA (amortises the table se
 // {4k .. 4k+3}, from input rows (y, y+1) and input columns 2k-1 .. 2k+2, all clamped at the border (where the lerp
 // degenerates to fma(0, t, a) = a exactly as the reference's clamped index does).  s_norm = v / 255 for the 256 pixel
 // values.  Horizontal pass first, then vertical (OpenCV's resize order).
-__device__ __forceinline__ void upsample_block(const uint8_t* __restrict__ in, const int W, const int H, const int in_stride,
-                                               const float* __restrict__ s_norm, const int k, const int y, float o[2][4]) {
+// (split into the eight pixel loads and the arithmetic so that a caller can have the loads of several blocks in flight)
+__device__ __forceinline__ void upsample_load(const uint8_t* __restrict__ in, const int W, const int H, const int in_stride,
+                                              const int k, const int y, uint32_t raw[8]) {
     const int y0 = max(y, 0), y1 = min(y + 1, H - 1);
-    float a[2][4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const int x = min(max(2 * k - 1 + c, 0), W - 1);
-        a[0][c] = s_norm[in[(long long)y0 * in_stride + x]];
-        a[1][c] = s_norm[in[(long long)y1 * in_stride + x]];
+        raw[c] = in[(long long)y0 * in_stride + x];
+        raw[4 + c] = in[(long long)y1 * in_stride + x];
     }
+}
+__device__ __forceinline__ void upsample_math(const uint32_t raw[8], const float* __restrict__ s_norm, const int k, float o[2][4]) {
+    float a[2][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { a[0][c] = s_norm[raw[c]]; a[1][c] = s_norm[raw[4 + c]]; }
     // horizontal pass: out col 4k = lerp(c0, c1, .75), 4k+1 = lerp(c1, c2, .25), 4k+2 = lerp(c1, c2, .75), 4k+3 = lerp(c2, c3, .25)
     float hrow[2][4];
 #pragma unroll
@@ -308,6 +313,12 @@ __device__ __forceinline__ void upsample_block(const uint8_t* __restrict__ in, c
 #pragma unroll
         for (int c = 0; c < 4; c++) o[r][c] = fmaf(hrow[1][c] - hrow[0][c], f, hrow[0][c]);
     }
+}
+__device__ __forceinline__ void upsample_block(const uint8_t* __restrict__ in, const int W, const int H, const int in_stride,
+                                               const float* __restrict__ s_norm, const int k, const int y, float o[2][4]) {
+    uint32_t raw[8];
+    upsample_load(in, W, H, in_stride, k, y, raw);
+    upsample_math(raw, s_norm, k, o);
 }
 
 __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
@@ -665,27 +676,41 @@ struct MarchCfg {
     static_assert((TW / 2) * (BH / PY) == THREADS, "one column-pass task per thread");
 };
 
-// SEEDF (the seed blur of the OpenCV flavour, L = 0): the input bands are not loaded but COMPUTED -- the CTA upsamples
-// the u8 input into its stage buffer (upsample_block: the arithmetic of k_upsample2x, 2 x 4 output blocks aligned with the
+// SEEDF != 0 (the seed blur of the OpenCV flavour, L = 0): the input bands are not loaded but COMPUTED -- the CTA upsamples
+// the u8 input into its stage buffers (upsample_block: the arithmetic of k_upsample2x, 2 x 4 output blocks aligned with the
 // band: band rows start at an odd row of the upsampled image and box columns at a multiple of 4) -- so the upsampled image
-// is never written to and read back from HBM (12.25 -> 4.25 bytes per seed pixel).  One stage buffer, no TMA, no
-// mbarriers: produce band j+1, barrier, row pass of j+1 and column pass of j-1, barrier.  Columns / rows outside the image
-// are left to the border logic below, exactly as for a loaded band.  Bit-identical to the two-kernel seed, and measured
-// SLOWER (the u8 loads of the produce phase are exposed and the phases serialise: 731 against 563 us per 32-image 1080p
-// group), so the pipeline only takes it with SB200_SEED=fused.
-template <int L, bool DECIMATE, int FL = FL_OPENCV, bool SEEDF = false>
-__global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTAS_PER_SM) k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
-                                                        const int src_layer, const int bands_per_cta, const int strips,
-                                                        const long long total_bands) {
+// is never written to and read back from HBM (12.25 -> 4.25 bytes per seed pixel).  Columns / rows outside the image are
+// left to the border logic below, exactly as for a loaded band; the results are bit-identical to the two-kernel seed.
+//   SEEDF == 1: all threads produce band j+1 into ONE stage buffer, barrier, row pass of j+1 and column pass of j-1,
+//     barrier.  Measured SLOWER than the two kernels (the u8 loads of the produce phase are exposed and the phases
+//     serialise: 731 against 563 us per 32-image 1080p group).
+//   SEEDF == 2: warp-specialised -- SEED_PRODUCERS extra threads (three warps) do nothing but produce bands, up to NSTG
+//     ahead of the eight filter warps, which run the unchanged marching code; a `full` mbarrier per stage buffer takes
+//     the place of the TMA's (one arrival per producer warp), an `empty` one hands the buffer back, and the filter warps
+//     synchronise among themselves on a named barrier.
+#ifndef SB_SEED_PRODUCERS
+#define SB_SEED_PRODUCERS 128
+#endif
+constexpr int SEED_PRODUCERS = SB_SEED_PRODUCERS;
+template <int L, bool DECIMATE, int FL = FL_OPENCV, int SEEDF = 0>
+__global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS + (SEEDF == 2 ? SEED_PRODUCERS : 0), MarchCfg<L, FL>::CTAS_PER_SM)
+k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p, const int src_layer, const int bands_per_cta,
+             const int strips, const long long total_bands) {
     static_assert(FL == FL_OPENCV || !DECIMATE, "the imageproc flavour decimates in its own kernel");
     static_assert(!SEEDF || (L == 0 && FL == FL_OPENCV && !DECIMATE), "the fused seed is layer 0 of the OpenCV flavour");
     using C = MarchCfg<L, FL>;
     static_assert(!SEEDF || (C::RA % 4 == 0 && C::BW % 4 == 0 && C::TW % 4 == 0 && C::BH % 2 == 0 && (C::R & 1) == 1 && C::THREADS >= 256),
                   "upsample blocks are aligned with the band");
+    // barrier among the filter warps (all threads of the CTA unless producer warps exist)
+    auto csync = [&]() {
+        if constexpr (SEEDF == 2) asm volatile("bar.sync 1, %0;" ::"n"(C::THREADS) : "memory");
+        else __syncthreads();
+    };
     constexpr int R = C::R;
     constexpr int STAGE_FLOATS = C::BH * C::BW, SLOT_FLOATS = C::BH * C::IPITCH;
     extern __shared__ __align__(1024) float smem_march[];
     __shared__ __align__(8) uint64_t bar[C::NSTG];
+    __shared__ __align__(8) uint64_t empty_bar[SEEDF == 2 ? C::NSTG : 1];
     float* const stage = smem_march;                               // NSTG x BH x BW (TMA box layout)
     float* const inter = smem_march + C::NSTG * STAGE_FLOATS;      // RING_ROWS x IPITCH
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -722,16 +747,20 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
     const int n_in = (yb - ya + 2 * R + C::BH - 1) / C::BH;    // input bands (n_out or n_out + 1)
     const int in0 = ya - R;                                    // first input row of band 0
     const bool hedge = tx0 - R < 0 || tx0 + C::TW + R > w;
-    if (!SEEDF && tid == 0) {   // fresh barriers per piece (every load of the previous piece has been waited for)
+    if (SEEDF != 1 && tid == 0) {   // fresh barriers per piece (every load of the previous piece has been waited for)
 #pragma unroll
         for (int b = 0; b < C::NSTG; b++) {
             if (!first_piece) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar[b])) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[b])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[b])), "n"(SEEDF == 2 ? SEED_PRODUCERS / 32 : 1));
+            if (SEEDF == 2) {
+                if (!first_piece) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&empty_bar[b])) : "memory");
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty_bar[b])));
+            }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     first_piece = false;
-    __syncthreads();
+    __syncthreads();   // (all threads of the CTA, producer warps included)
     auto issue = [&](const int b, const int stg) {   // band b into stage buffer stg == b % NSTG
         const uint32_t bar_a = smem_u32(&bar[stg]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(C::BAND_BYTES) : "memory");
@@ -749,36 +778,118 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
     // SEEDF: input band b, upsampled from the u8 image straight into stage buffer 0.  Band row pair rp holds the rows
     // {2y+1, 2y+2} of the upsampled image with y = (band_y0 - 1) / 2 + rp (band_y0 is odd), box column group g its
     // columns {4k .. 4k+3} with k = (tx0 - RA) / 4 + g.
-    auto produce = [&](const int b) {
+    auto produce = [&](const int b, float* const dst, const int t0, const int nt) {
         const int ypair0 = (in0 + b * C::BH - 1) >> 1;
         const int kg0 = (tx0 - C::RA) >> 2;
         const uint8_t* const in = p.in + (long long)img * p.in_img_stride;
         constexpr int NG = C::BW / 4;
-        for (int t = tid; t < (C::BH / 2) * NG; t += C::THREADS) {
+        for (int t = t0; t < (C::BH / 2) * NG; t += nt) {
             const int rp = t / NG, g = t - rp * NG;
             const int y = ypair0 + rp, k = kg0 + g;
             if (k < 0 || 4 * k >= w || y < -1 || y >= p.in_h) continue;   // wholly outside the image: never read
             float o[2][4];
             upsample_block(in, p.in_w, p.in_h, p.in_stride, s_norm, k, y, o);
-            float4* const q = reinterpret_cast<float4*>(stage + (2 * rp) * C::BW + 4 * g);
+            float4* const q = reinterpret_cast<float4*>(dst + (2 * rp) * C::BW + 4 * g);
             q[0] = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
             q[C::BW / 4] = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
         }
     };
+    auto mbar_wait = [&](uint64_t* const b, const uint32_t parity) {
+        const uint32_t a = smem_u32(b);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        }
+    };
+    if constexpr (SEEDF == 2) {
+        if (tid >= C::THREADS) {   // producer warps: band after band of this piece, at most NSTG ahead of the filter warps
+            for (int b = 0; b < n_in; b++) {
+                const int stg = b % C::NSTG;
+                if (b >= C::NSTG) {   // the producers run ahead: wait politely (a tight poll takes issue slots from the filter warps)
+                    const uint32_t a = smem_u32(&empty_bar[stg]), parity = (uint32_t)((b / C::NSTG - 1) & 1);
+                    for (;;) {
+                        uint32_t done;
+                        asm volatile(
+                            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                            : "=r"(done) : "r"(a), "r"(parity) : "memory");
+                        if (done) break;
+                        __nanosleep(256);
+                    }
+                }
+                {   // A producer thread owns one group of four box columns and walks down a third of the band's 16 row
+                    // pairs: every input row is loaded and interpolated horizontally once and serves the pair above and
+                    // the pair below it; all (at most 28) pixel loads of a thread are in flight together.
+                    float* const dst = stage + stg * STAGE_FLOATS;
+                    const int ypair0 = (in0 + b * C::BH - 1) >> 1;
+                    const uint8_t* const in = p.in + (long long)img * p.in_img_stride;
+                    constexpr int NG = C::BW / 4;
+                    static_assert(C::BH == 32 && 3 * NG <= SEED_PRODUCERS, "three producer threads per column group");
+                    const int pt = tid - C::THREADS;
+                    const int seg = pt / NG, g = pt - seg * NG;
+                    const int k = ((tx0 - C::RA) >> 2) + g;
+                    if (seg < 3 && k >= 0 && 4 * k < w) {
+                        const int W = p.in_w, H = p.in_h;
+                        const int rp0 = seg == 0 ? 0 : (seg == 1 ? 6 : 11), np = seg == 0 ? 6 : 5;   // row pairs [rp0, rp0 + np)
+                        uint32_t raw[7][4];
+                        if (k >= 1 && 2 * k + 2 < W) {   // interior columns: four consecutive bytes from one row address
+#pragma unroll
+                            for (int r = 0; r < 7; r++) {   // input rows of the pairs: pair rp reads rows rp and rp + 1 (clamped)
+                                const int yr = min(max(ypair0 + rp0 + min(r, np), 0), H - 1);
+                                const uint8_t* const row = in + ((long long)yr * p.in_stride + (2 * k - 1));
+#pragma unroll
+                                for (int c = 0; c < 4; c++) raw[r][c] = row[c];
+                            }
+                        } else {
+                            int xo[4];
+#pragma unroll
+                            for (int c = 0; c < 4; c++) xo[c] = min(max(2 * k - 1 + c, 0), W - 1);
+#pragma unroll
+                            for (int r = 0; r < 7; r++) {
+                                const int yr = min(max(ypair0 + rp0 + min(r, np), 0), H - 1);
+                                const uint8_t* const row = in + (long long)yr * p.in_stride;
+#pragma unroll
+                                for (int c = 0; c < 4; c++) raw[r][c] = row[xo[c]];
+                            }
+                        }
+                        float2 hr[7][2];   // horizontally interpolated rows, as the column pairs the packed vertical pass takes
+#pragma unroll
+                        for (int r = 0; r < 7; r++) {
+                            const float a0 = s_norm[raw[r][0]], a1 = s_norm[raw[r][1]], a2 = s_norm[raw[r][2]], a3 = s_norm[raw[r][3]];
+                            hr[r][0].x = k == 0 ? a1 : fmaf(a1 - a0, 0.75f, a0);   // 2k-1 < 0: both taps are column 0
+                            hr[r][0].y = fmaf(a2 - a1, 0.25f, a1);
+                            hr[r][1].x = fmaf(a2 - a1, 0.75f, a1);
+                            hr[r][1].y = fmaf(a3 - a2, 0.25f, a2);
+                        }
+                        const float2 f25 = make_float2(0.25f, 0.25f), f75 = make_float2(0.75f, 0.75f);
+#pragma unroll
+                        for (int q = 0; q < 6; q++) {
+                            const int y = ypair0 + rp0 + q;
+                            if (q < np && y >= -1 && y < H) {
+                                // fma(bottom - top, f, top) per output, two columns per packed operation
+                                const float2 d0 = sub2(hr[q + 1][0], hr[q][0]), d1 = sub2(hr[q + 1][1], hr[q][1]);
+                                const float2 u0 = fma2(d0, f25, hr[q][0]), u1 = fma2(d1, f25, hr[q][1]);
+                                const float2 v0 = fma2(d0, f75, hr[q][0]), v1 = fma2(d1, f75, hr[q][1]);
+                                float4* const out = reinterpret_cast<float4*>(dst + (2 * (rp0 + q)) * C::BW + 4 * g);
+                                out[0] = make_float4(u0.x, u0.y, u1.x, u1.y);
+                                out[C::BW / 4] = make_float4(v0.x, v0.y, v1.x, v1.y);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[stg])) : "memory");
+            }
+            continue;   // next piece (its barriers are initialised behind the CTA-wide barrier above)
+        }
+    }
 
     // ---- row pass of input band b (stage buffer stg, its mbarrier at `parity`; ring slot `slot`):
     //      warp = the band's 32 rows x one 8-pixel segment ----
     auto row_pass = [&](const int b, const int stg_, const uint32_t parity, const int slot) {
-        const int stg = SEEDF ? 0 : stg_;
-        if (!SEEDF) {
-            const uint32_t bar_a = smem_u32(&bar[stg]);
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile(
-                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                    : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
-            }
-        }
+        const int stg = SEEDF == 1 ? 0 : stg_;
+        if (SEEDF != 1) mbar_wait(&bar[stg], parity);
         float* const st = stage + stg * STAGE_FLOATS;
         const int band_y0 = in0 + b * C::BH;
         if (hedge) {  // block-uniform: box element (row, XO + col) holds image pixel (band_y0 + row, tx0 - R + col)
@@ -794,7 +905,7 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
                     for (int row = lane; row < C::BH; row += 32) st[row * C::BW + C::XO + col] = st[row * C::BW + C::XO + rx];
                 }
             }
-            __syncthreads();
+            csync();
         }
         float* const ib = inter + slot * SLOT_FLOATS;
         const bool vedge = band_y0 < 0 || band_y0 + C::BH > h;                      // block-uniform
@@ -933,9 +1044,9 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
         if (DECIMATE) dband += (long long)(C::BH / 2) * p.dec_pitch;
     };
 
-    if (SEEDF) { produce(0); __syncthreads(); }
+    if (SEEDF == 1) { produce(0, stage, tid, C::THREADS); csync(); }
     row_pass(0, 0, 0u, 0);
-    __syncthreads();
+    csync();
     int rslot = 1, cslot = 0;   // ring slots of band j+1 (row pass) and band j-1 (column pass)
     int fstg = 0;               // stage buffer of band j (free again), == j % NSTG
     int rstg = 1;               // stage buffer of band j+1, == (j+1) % NSTG
@@ -943,8 +1054,10 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
     for (int j = 0; j <= n_out; j++) {
         // band j was row-passed before the last barrier: its stage buffer is free for band j+NSTG
         if (!SEEDF && tid == 0 && j + C::NSTG < n_in) issue(j + C::NSTG, fstg);
+        if (SEEDF == 2 && tid == 0)   // hand the buffer back to the producer warps
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[fstg])) : "memory");
         fstg = fstg == C::NSTG - 1 ? 0 : fstg + 1;
-        if (SEEDF && j + 1 < n_in) { produce(j + 1); __syncthreads(); }   // (band j was row-passed before the last barrier)
+        if (SEEDF == 1 && j + 1 < n_in) { produce(j + 1, stage, tid, C::THREADS); csync(); }   // (band j was row-passed before the last barrier)
         if (j + 1 < n_in) row_pass(j + 1, rstg, rpar, rslot);
         if (rstg == C::NSTG - 1) { rstg = 0; rpar ^= 1u; } else rstg++;
         rslot = rslot == 2 ? 0 : rslot + 1;
@@ -952,7 +1065,7 @@ __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS, MarchCfg<L, FL>::CTA
             col_pass(j - 1, cslot);
             cslot = cslot == 2 ? 0 : cslot + 1;
         }
-        __syncthreads();
+        csync();
     }
     }   // pieces
 }

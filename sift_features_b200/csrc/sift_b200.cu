@@ -137,7 +137,8 @@ struct sb200_ctx {
     bool march = true;                         // SB200_BLUR=tile selects the independent-tile TMA blur (debugging aid)
     int seg_rows_override = 0;                 // SB200_SEG_ROWS: fixed segment height of the marching blur (tests)
     int pieces_override = 0;                   // SB200_PIECES: pieces per column of the aligned distribution (experiments)
-    bool seed_fused = false;                   // SB200_SEED=fused: the seed blur upsamples its own input bands (measured slower)
+    int seed_fused = 2;                        // the seed blur upsamples its own input bands: 2 = producer warps (default), 1 = in
+                                               // line (SB200_SEED=fused), 0 = separate upsample kernel (SB200_SEED=split)
     bool tail = true;                          // SB200_TAIL=0: per-layer launches for the small octaves too (debugging aid)
     bool use_graphs = true;                    // SB200_GRAPHS=0: plain stream launches
     bool fork_octaves = true;                  // SB200_FORK=0: every kernel of a group on one stream
@@ -592,7 +593,7 @@ void launch_blur_tma(cudaStream_t st, const CUtensorMap& tm, const BlurParams& p
     k_blur_tma<LI, DEC><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer);
 }
 
-template <int LI, bool DEC, int FL = FL_OPENCV, bool SEEDF = false>
+template <int LI, bool DEC, int FL = FL_OPENCV, int SEEDF = 0>
 int set_march_attr(sb200_ctx* ctx) {
     CU(cudaFuncSetAttribute(k_blur_march<LI, DEC, FL, SEEDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MarchCfg<LI, FL>::SMEM));
     CU(cudaFuncSetAttribute(k_blur_march<LI, DEC, FL, SEEDF>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -617,7 +618,7 @@ int set_imageproc_attrs(sb200_ctx* ctx) {
 //     in L2, their rows share DRAM pages), and the hardware's CTA scheduler balances the waves.
 constexpr int MARCH_MIN_BANDS = 2;
 constexpr int MARCH_TARGET_BANDS = 17;
-template <int LI, bool DEC, int FL = FL_OPENCV, bool SEEDF = false>
+template <int LI, bool DEC, int FL = FL_OPENCV, int SEEDF = 0>
 void launch_blur_march(sb200_ctx* ctx, cudaStream_t st, const CUtensorMap& tm, const BlurParams& p, uint32_t n, int src_layer) {
     using C = MarchCfg<LI, FL>;
     const int strips = (p.w + C::TW - 1) / C::TW;
@@ -641,7 +642,7 @@ void launch_blur_march(sb200_ctx* ctx, cudaStream_t st, const CUtensorMap& tm, c
         per = -k;
         grid = (long long)strips * n * k;
     }
-    k_blur_march<LI, DEC, FL, SEEDF><<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer, (int)per, strips, total);
+    k_blur_march<LI, DEC, FL, SEEDF><<<(unsigned)grid, C::THREADS + (SEEDF == 2 ? SEED_PRODUCERS : 0), C::SMEM, st>>>(tm, p, src_layer, (int)per, strips, total);
 }
 
 // one blur of the imageproc flavour: marching TMA kernel for octaves that own a tensor map, generic tiles otherwise
@@ -776,10 +777,11 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
         p.in = d_in; p.in_img_stride = (long long)in_img_stride;
         p.in_w = (int)w; p.in_h = (int)h; p.in_stride = (int)in_stride;
         if (ctx->tmap_ok[0] && ctx->march && ctx->seed_fused) {
-            // SB200_SEED=fused: the marching seed blur upsamples its input bands itself (k_blur_march<0, .., SEEDF>): one
-            // launch and the upsampled image never exists in HBM -- but the produce phase and its extra barrier cost more
-            // than the round trip saves (731 against 563 us per 32-image 1080p group), so it is not the default
-            launch_blur_march<0, false, FL_OPENCV, true>(ctx, st, ctx->tmap_m[s.index][0][0], p, n, 5);
+            // the marching seed blur upsamples its input bands itself (k_blur_march<0, .., SEEDF>): one launch and the
+            // upsampled image never exists in HBM.  Producer warps (SEEDF = 2) are the default; SB200_SEED=fused takes the
+            // in-line variant, SB200_SEED=split the separate upsample kernel below (both slower, kept as cross-checks)
+            if (ctx->seed_fused == 2) launch_blur_march<0, false, FL_OPENCV, 2>(ctx, st, ctx->tmap_m[s.index][0][0], p, n, 5);
+            else launch_blur_march<0, false, FL_OPENCV, 1>(ctx, st, ctx->tmap_m[s.index][0][0], p, n, 5);
             count_launch(ctx, SB200_STAGE_SEED);
         } else if (ctx->tmap_ok[0]) {
             // upsample into layer 5 of octave 0 (free until the last blur of the octave overwrites it),
@@ -1547,7 +1549,8 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
         if ((r = set_tma_attr<0, false>(ctx)) || (r = set_tma_attr<1, false>(ctx)) || (r = set_tma_attr<2, false>(ctx)) || (r = set_tma_attr<3, false>(ctx)) ||
             (r = set_tma_attr<3, true>(ctx)) || (r = set_tma_attr<4, false>(ctx)) || (r = set_tma_attr<5, false>(ctx)))
             return r;
-        if ((r = set_march_attr<0, false, FL_OPENCV, true>(ctx)) || (r = set_march_attr<0, false>(ctx)) || (r = set_march_attr<1, false>(ctx)) || (r = set_march_attr<2, false>(ctx)) ||
+        if ((r = set_march_attr<0, false, FL_OPENCV, 1>(ctx)) || (r = set_march_attr<0, false, FL_OPENCV, 2>(ctx)) ||
+            (r = set_march_attr<0, false>(ctx)) || (r = set_march_attr<1, false>(ctx)) || (r = set_march_attr<2, false>(ctx)) ||
             (r = set_march_attr<3, false>(ctx)) || (r = set_march_attr<3, true>(ctx)) || (r = set_march_attr<4, false>(ctx)) ||
             (r = set_march_attr<5, false>(ctx)))
             return r;
@@ -1566,7 +1569,7 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
             const char* sr = getenv("SB200_SEG_ROWS");
             if (sr && atoi(sr) >= 32) ctx->seg_rows_override = atoi(sr) / 32 * 32;
             const char* sd = getenv("SB200_SEED");
-            ctx->seed_fused = sd && !strcmp(sd, "fused");
+            ctx->seed_fused = !sd ? 2 : !strcmp(sd, "fused") ? 1 : !strcmp(sd, "split") ? 0 : 2;
             const char* pc = getenv("SB200_PIECES");
             if (pc && atoi(pc) >= 1) ctx->pieces_override = atoi(pc);
         }
