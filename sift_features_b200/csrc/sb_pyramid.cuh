@@ -684,13 +684,28 @@ struct MarchCfg {
 //   SEEDF == 1: all threads produce band j+1 into ONE stage buffer, barrier, row pass of j+1 and column pass of j-1,
 //     barrier.  Measured SLOWER than the two kernels (the u8 loads of the produce phase are exposed and the phases
 //     serialise: 731 against 563 us per 32-image 1080p group).
-//   SEEDF == 2: warp-specialised -- SEED_PRODUCERS extra threads (three warps) do nothing but produce bands, up to NSTG
-//     ahead of the eight filter warps, which run the unchanged marching code; a `full` mbarrier per stage buffer takes
-//     the place of the TMA's (one arrival per producer warp), an `empty` one hands the buffer back, and the filter warps
-//     synchronise among themselves on a named barrier.
+//   SEEDF == 2 (what the pipeline uses): warp-specialised -- SEED_PRODUCERS extra threads (four warps) do nothing but
+//     produce bands, up to NSTG ahead of the eight filter warps, which run the unchanged marching code; a `full` mbarrier
+//     per stage buffer takes the place of the TMA's (one arrival per producer warp), an `empty` one hands the buffer back,
+//     and the filter warps synchronise among themselves on a named barrier.  A producer thread owns a group of four box
+//     columns and a third of the band's 16 row pairs, loads its input bytes in one round and interpolates every input row
+//     horizontally once.  450 against 565 us (two kernels) per 32-image 1080p group.
 #ifndef SB_SEED_PRODUCERS
 #define SB_SEED_PRODUCERS 128
 #endif
+#ifndef SB_SEED_PREFETCH
+#define SB_SEED_PREFETCH 0   // L1 prefetch of the next band's input lines by the producer warps: measured 2 % slower
+#endif
+#ifndef SB_SEED_LUT
+#define SB_SEED_LUT 0        // 1: v / 255 from the shared-memory table (random banks: conflicts) instead of norm255()
+#endif
+// v / 255 for an 8-bit v, the correctly rounded f32 quotient without a division: one Newton step on v * RN(1/255)
+// (verified equal to the IEEE division for all 256 values; the bit-exact pyramid tests would catch any other)
+__device__ __forceinline__ float norm255(const uint32_t v) {
+    const float f = (float)v, r = 1.0f / 255.0f;
+    const float q = f * r;
+    return fmaf(fmaf(-q, 255.0f, f), r, q);
+}
 constexpr int SEED_PRODUCERS = SB_SEED_PRODUCERS;
 template <int L, bool DECIMATE, int FL = FL_OPENCV, int SEEDF = 0>
 __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS + (SEEDF == 2 ? SEED_PRODUCERS : 0), MarchCfg<L, FL>::CTAS_PER_SM)
@@ -853,10 +868,23 @@ k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p, const
                                 for (int c = 0; c < 4; c++) raw[r][c] = row[xo[c]];
                             }
                         }
+#if SB_SEED_PREFETCH
+                        if (b + 1 < n_in) {   // the same columns one band further down: pull their lines into L1 for the next round
+#pragma unroll
+                            for (int r = 1; r < 7; r++) {
+                                const int yr = min(max(ypair0 + C::BH / 2 + rp0 + min(r, np), 0), H - 1);
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(in + ((long long)yr * p.in_stride + max(2 * k - 1, 0))));
+                            }
+                        }
+#endif
                         float2 hr[7][2];   // horizontally interpolated rows, as the column pairs the packed vertical pass takes
 #pragma unroll
                         for (int r = 0; r < 7; r++) {
+#if SB_SEED_LUT
                             const float a0 = s_norm[raw[r][0]], a1 = s_norm[raw[r][1]], a2 = s_norm[raw[r][2]], a3 = s_norm[raw[r][3]];
+#else
+                            const float a0 = norm255(raw[r][0]), a1 = norm255(raw[r][1]), a2 = norm255(raw[r][2]), a3 = norm255(raw[r][3]);
+#endif
                             hr[r][0].x = k == 0 ? a1 : fmaf(a1 - a0, 0.75f, a0);   // 2k-1 < 0: both taps are column 0
                             hr[r][0].y = fmaf(a2 - a1, 0.25f, a1);
                             hr[r][1].x = fmaf(a2 - a1, 0.75f, a1);
