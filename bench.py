@@ -477,9 +477,14 @@ def kernel_table(m, w, h, B, peak, sf, sm_mhz):
         add(f"k_blur_march<{l}>", ms, sum(v[1] for (o, k), v in fine.items() if k == f"blur{l}"), 8.0 * px,
             "hbm" if l <= 2 else "fp32 pipe / hbm", f"{[11, 13, 17, 21, 27][l - 1]}-tap separable Gaussian, 8 B/px, all octaves >= 32 px", extra)
     seed_ms = sum(v[0] for (o, k), v in fine.items() if k == "seed")
-    add("k_upsample2x + k_blur_march<0>", seed_ms, 2 * groups, a_seed + 8.0 * dims[0][0] * dims[0][1], "hbm",
-        "u8 -> f32 2x upsample, then the 11-tap seed blur (the upsampled image is written and read once more than "
-        "the algorithmic model counts)")
+    if os.environ.get("SB200_SEED") == "split":
+        add("k_upsample2x + k_blur_march<0>", seed_ms, 2 * groups, a_seed + 8.0 * dims[0][0] * dims[0][1], "hbm",
+            "u8 -> f32 2x upsample, then the 11-tap seed blur (the upsampled image is written and read once more than "
+            "the algorithmic model counts)")
+    else:
+        add("k_blur_march<0, seed>", seed_ms, groups, a_seed, "issue / shared memory",
+            "u8 -> f32 2x upsample by producer warps straight into the stage buffers of the 11-tap seed blur: "
+            "0.25 B in + 4 B out per seed pixel, the upsampled image never goes through HBM")
     tail_ms = sum(v[0] for (o, k), v in fine.items() if k == "tail")
     add("k_tail", tail_ms, groups, 0.0, "latency", "all octaves of at most 64x36 px in one launch")
     rows.sort(key=lambda r: -r["share_of_step"])
