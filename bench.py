@@ -259,10 +259,11 @@ class Measure:
     def __init__(self, lib, sf, dist, rank, local_rank, world):
         self.lib, self.sf, self.dist, self.rank, self.local_rank, self.world = lib, sf, dist, rank, local_rank, world
 
-    def run(self, w, h, B, G, steps, warmup, natural=False, profile=True, pageable=False, keep_sets=False):
+    def run(self, w, h, B, G, steps, warmup, natural=False, profile=True, pageable=False, keep_sets=False,
+            processing=None):
         lib, sf, dist = self.lib, self.sf, self.dist
         per_step = B * G
-        ex = sf.Extractor(w, h, B, device=self.local_rank)
+        ex = sf.Extractor(w, h, B, device=self.local_rank, processing=processing or sf.OpenCVProcessing)
         H = ex.handle
 
         def chk(st):
@@ -563,11 +564,14 @@ def sub_workloads(args, M, lib, sf, dist, rank, local_rank, world, peak):
     out = {}
     steps = max(3, min(args.steps, 6))
 
-    def shape(name, natural=False, pageable=False):
+    def shape(name, natural=False, pageable=False, processing=None):
         w, h, B, G = WORKLOADS[name]
-        m = M.run(w, h, B, G, steps, 3, natural=natural, pageable=pageable)
+        m = M.run(w, h, B, G, steps, 3, natural=natural, pageable=pageable, processing=processing)
         m["world"] = world
-        r = {"workload": workload_text(name, w, h, natural), "images_per_step_per_gpu": B * G, "steps": steps,
+        text = workload_text(name, w, h, natural)
+        if processing is not None:
+            text += " -- pyramid in the arithmetic of the crate's default Processing (ImageprocProcessing, src/lib.rs:992-1007)"
+        r = {"workload": text, "images_per_step_per_gpu": B * G, "steps": steps,
              "value": m["value"], "unit": "images/s", "e2e": m["e2e"], "keypoints_per_image": m["kp_per_image"],
              "keypoints_per_s": m["kp_per_s"]}
         if "e2e_pageable" in m:
@@ -582,6 +586,7 @@ def sub_workloads(args, M, lib, sf, dist, rank, local_rank, world, peak):
     out["vga"] = shape("vga")
     out["4k"] = shape("4k")
     out["natural_1080p"] = shape("1080p", natural=True)
+    out["imageproc_1080p"] = shape("1080p", processing=sf.ImageprocProcessing)
     out["desc"] = desc_measure(args, lib, sf, dist, rank, local_rank, world, steps, peak)
     if rank == 0:
         out["single_image"] = single_image(lib, sf, local_rank)

@@ -1381,19 +1381,33 @@ __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema_tma(const __grid_c
 }
 
 // ---------------------------------------------------------------------------
-// Tail of the pyramid: every octave small enough for a whole layer to sit in shared memory (w*h <= TAIL_MAX_PX)
-// is processed by ONE CTA per image in ONE launch -- five blurs, decimation into the next octave and the
+// Tail of the pyramid: every octave small enough for a whole layer to sit in shared memory (tail_fits) is
+// processed by ONE CTA per image in ONE launch -- five blurs, decimation into the next octave and the
 // DoG/extrema scan, octave after octave -- instead of six launch-latency-bound kernels per octave.  Same
 // arithmetic as k_blur (row pass left-to-right FMA chain, column pass symmetric-folded chain,
 // BORDER_REFLECT_101) and the same extrema code as k_extrema (generic loads, coherent path: the layers were
 // written by this CTA).
+// In octaves this small nearly every pixel is a border pixel (a 27-tap window on a 60 x 33 layer), and resolving
+// BORDER_REFLECT_101 per tap made the kernel instruction-bound on index arithmetic (one CTA: 92 us per image, a
+// quarter of a single image's pyramid).  Both shared-memory layers are therefore PADDED: `a` (the blur's source)
+// carries TAIL_RMAX mirrored columns on either side of every row, `b` (the row-pass result) TAIL_RMAX mirrored rows
+// above and below, filled by a short pass of their own (one border_index per halo element instead of one per tap),
+// so that both filter passes are plain sliding windows.  Four block barriers per blur instead of two, each phase a
+// fraction of the old ones.
 // ---------------------------------------------------------------------------
-constexpr int TAIL_MAX_PX = 2304;     // 9 KB per buffer, e.g. 64 x 36: larger octaves keep one CTA busy for too long
+constexpr int TAIL_MAX_PX = 2304;     // e.g. 64 x 36: larger octaves keep one CTA busy for too long
+constexpr int TAIL_RMAX = 13;         // widest blur radius (27 taps)
+constexpr int TAIL_A_FLOATS = 4096;   // (w + 2 RMAX) x h
+constexpr int TAIL_B_FLOATS = 4096;   // w x (h + 2 RMAX)
 #ifndef SB_TAIL_THREADS
 #define SB_TAIL_THREADS 512
 #endif
 constexpr int TAIL_THREADS = SB_TAIL_THREADS;
-constexpr size_t TAIL_SMEM = 2 * (size_t)TAIL_MAX_PX * sizeof(float);
+constexpr size_t TAIL_SMEM = (size_t)(TAIL_A_FLOATS + TAIL_B_FLOATS) * sizeof(float);
+static_assert(blur_radius(N_LAYERS - 1) <= TAIL_RMAX, "halo of the widest blur");
+__host__ __device__ constexpr bool tail_fits(const long long w, const long long h) {
+    return w * h <= TAIL_MAX_PX && (w + 2 * TAIL_RMAX) * h <= TAIL_A_FLOATS && w * (h + 2 * TAIL_RMAX) <= TAIL_B_FLOATS;
+}
 
 struct TailParams {
     PyrLayout L;
@@ -1403,42 +1417,46 @@ struct TailParams {
     uint32_t* rows;              // row counters, image 0
 };
 
-template <int LI>
-__device__ __forceinline__ void tail_blur(const float* __restrict__ a /* smem w x h */, float* __restrict__ b /* smem */,
-                                          float* __restrict__ a_next /* smem: becomes the next source */,
+// mirrored halo columns [-R, 0) and [w, w + R) of every row of `a` (pitch w + 2 RMAX, column 0 at offset RMAX)
+__device__ __forceinline__ void tail_halo_cols(float* __restrict__ a, const int R, const int w, const int h) {
+    const int wp = w + 2 * TAIL_RMAX;
+    for (int idx = threadIdx.x; idx < 2 * R * h; idx += TAIL_THREADS) {
+        const int y = idx / (2 * R), k = idx - y * (2 * R);
+        const int col = k < R ? k - R : w + (k - R);
+        float* const row = a + y * wp + TAIL_RMAX;
+        row[col] = row[reflect101(col, w)];
+    }
+}
+
+template <int LI, int R_NEXT>
+__device__ __forceinline__ void tail_blur(float* __restrict__ a /* smem, padded columns: source, then result */,
+                                          float* __restrict__ b /* smem, padded rows */,
                                           float* __restrict__ dst, float* __restrict__ dec, const int w, const int h,
                                           const int pitch, const int dec_w, const int dec_h, const int dec_pitch) {
     constexpr int R = blur_radius(LI);
-    const int n = w * h;
+    const int n = w * h, wp = w + 2 * TAIL_RMAX;
     for (int idx = threadIdx.x; idx < n; idx += TAIL_THREADS) {
         const int y = idx / w, x = idx - y * w;
-        const float* row = a + y * w;
-        float acc;
-        if (x >= R && x + R < w) {   // interior: no border arithmetic
-            const float* q = row + x - R;
-            acc = q[0] * c_taps[LI][0];
+        const float* q = a + y * wp + (TAIL_RMAX - R) + x;
+        float acc = q[0] * c_taps[LI][0];
 #pragma unroll
-            for (int i = 1; i <= 2 * R; i++) acc = fmaf(q[i], c_taps[LI][i], acc);
-        } else {
-            acc = row[reflect101(x - R, w)] * c_taps[LI][0];
-#pragma unroll
-            for (int i = 1; i <= 2 * R; i++) acc = fmaf(row[reflect101(x - R + i, w)], c_taps[LI][i], acc);
-        }
-        b[idx] = acc;
+        for (int i = 1; i <= 2 * R; i++) acc = fmaf(q[i], c_taps[LI][i], acc);
+        b[idx + TAIL_RMAX * w] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * R * w; idx += TAIL_THREADS) {   // mirrored rows [-R, 0) and [h, h + R)
+        const int k = idx / w, x = idx - k * w;
+        const int row = k < R ? k - R : h + (k - R);
+        b[(row + TAIL_RMAX) * w + x] = b[(reflect101(row, h) + TAIL_RMAX) * w + x];
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < n; idx += TAIL_THREADS) {
         const int y = idx / w, x = idx - y * w;
-        float acc = b[idx] * c_taps[LI][R];
-        if (y >= R && y + R < h) {
+        const float* c = b + idx + TAIL_RMAX * w;
+        float acc = c[0] * c_taps[LI][R];
 #pragma unroll
-            for (int i = 1; i <= R; i++) acc = fmaf(b[idx + i * w] + b[idx - i * w], c_taps[LI][R + i], acc);
-        } else {
-#pragma unroll
-            for (int i = 1; i <= R; i++)
-                acc = fmaf(b[reflect101(y + i, h) * w + x] + b[reflect101(y - i, h) * w + x], c_taps[LI][R + i], acc);
-        }
-        a_next[idx] = acc;
+        for (int i = 1; i <= R; i++) acc = fmaf(c[i * w] + c[-i * w], c_taps[LI][R + i], acc);
+        a[y * wp + TAIL_RMAX + x] = acc;
         dst[(long long)y * pitch + x] = acc;
         if (dec && !(y & 1) && !(x & 1)) {
             const int dy = y >> 1, dx = x >> 1;
@@ -1446,13 +1464,17 @@ __device__ __forceinline__ void tail_blur(const float* __restrict__ a /* smem w 
         }
     }
     __syncthreads();
+    if (R_NEXT > 0) {   // the next blur's halo columns
+        tail_halo_cols(a, R_NEXT, w, h);
+        __syncthreads();
+    }
 }
 
 template <bool KEEP_FLAT>
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
     extern __shared__ __align__(16) float tail_smem[];
-    float* const a = tail_smem;
-    float* const b = tail_smem + TAIL_MAX_PX;
+    float* const a = tail_smem;                    // (w + 2 RMAX) x h
+    float* const b = tail_smem + TAIL_A_FLOATS;    // w x (h + 2 RMAX)
     const long long img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* const gimg = p.gauss + img * p.L.img_floats;
@@ -1464,19 +1486,21 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
         // layer 0: written by the previous octave's decimation (an earlier launch for o_first, this CTA otherwise)
         for (int idx = tid; idx < w * h; idx += TAIL_THREADS) {
             const int y = idx / w, x = idx - y * w;
-            a[idx] = g0[(long long)y * ol.pitch + x];
+            a[y * (w + 2 * TAIL_RMAX) + TAIL_RMAX + x] = g0[(long long)y * ol.pitch + x];
         }
+        __syncthreads();
+        tail_halo_cols(a, blur_radius(1), w, h);
         __syncthreads();
         float* dec = nullptr;
         int dw = 0, dh = 0, dp = 0;
         if (o + 1 < p.L.n_oct && p.L.o[o + 1].w >= 1 && p.L.o[o + 1].h >= 1) {
             dec = gimg + p.L.o[o + 1].off; dw = p.L.o[o + 1].w; dh = p.L.o[o + 1].h; dp = p.L.o[o + 1].pitch;
         }
-        tail_blur<1>(a, b, a, g0 + 1 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<2>(a, b, a, g0 + 2 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<3>(a, b, a, g0 + 3 * ol.layer_stride, dec, w, h, ol.pitch, dw, dh, dp);
-        tail_blur<4>(a, b, a, g0 + 4 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<5>(a, b, a, g0 + 5 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<1, blur_radius(2)>(a, b, g0 + 1 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<2, blur_radius(3)>(a, b, g0 + 2 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<3, blur_radius(4)>(a, b, g0 + 3 * ol.layer_stride, dec, w, h, ol.pitch, dw, dh, dp);
+        tail_blur<4, blur_radius(5)>(a, b, g0 + 4 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<5, 0>(a, b, g0 + 5 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
         if (ol.scanned) {
             ExtremaParams e;
             e.gauss = p.gauss + ol.off; e.img_stride = p.L.img_floats; e.layer_stride = ol.layer_stride;

@@ -46,12 +46,16 @@ constexpr int N_SLOTS = SB_SLOTS;
 
 const char* kStageNames[SB200_STAGE_COUNT] = {"seed", "blur", "extrema", "refine", "orient", "descriptor", "top_blur"};
 
+constexpr int N_SIDE_MAX = 4;
 struct Slot {
     int index = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;       // layers 4, 5 and the extrema scan of an octave run here while the main stream
-    cudaEvent_t ev_fork = nullptr;     // already builds the next octave (which only needs layer 3)
-    cudaEvent_t ev_join = nullptr;
+    // layers 4, 5 and the extrema scan of octave o run on side stream o % n_side while the main stream already builds
+    // the next octave (which only needs layer 3); with several side streams the side work of consecutive octaves
+    // overlaps too -- on one side stream it, not the chain of octaves, was the critical path of a single image
+    cudaStream_t side[N_SIDE_MAX] = {nullptr};
+    cudaEvent_t ev_fork[MAX_OCT] = {nullptr};
+    cudaEvent_t ev_join[N_SIDE_MAX] = {nullptr};
     cudaEvent_t ev_counts = nullptr;
     cudaEvent_t ev_upload = nullptr;   // the last host->device copy out of the slot's pinned staging buffer
     // input
@@ -142,6 +146,7 @@ struct sb200_ctx {
     bool tail = true;                          // SB200_TAIL=0: per-layer launches for the small octaves too (debugging aid)
     bool use_graphs = true;                    // SB200_GRAPHS=0: plain stream launches
     bool fork_octaves = true;                  // SB200_FORK=0: every kernel of a group on one stream
+    int n_side = 3;                            // side streams per slot (SB200_SIDES=1..N_SIDE_MAX)
     uint64_t graph_clock = 0;
     CUtensorMap tmap_ex[N_SLOTS][MAX_OCT];  // [slot][octave]: (68 x 3 x 6) boxes of the extrema scan
     bool tmap_ok[MAX_OCT] = {false};
@@ -401,11 +406,11 @@ void free_cand_arrays(Slot& s) {
 int alloc_slot(sb200_ctx* ctx, Slot& s) {
     const size_t B = ctx->max_batch, cap = ctx->cap;
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+    for (auto& q : s.side) CU(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.ev_counts, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_upload, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+    for (auto& e : s.ev_fork) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : s.ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     s.in_cap = (size_t)ctx->max_w * ctx->max_h * B;
     CU(dalloc(&s.d_in, s.in_cap));
     CU(cudaHostAlloc((void**)&s.h_in, std::max<size_t>(s.in_cap, 1), cudaHostAllocDefault));
@@ -423,11 +428,11 @@ void free_slot(Slot& s) {
     for (auto& g : s.graphs) cudaGraphExecDestroy(g.exec);
     s.graphs.clear();
     if (s.stream) cudaStreamDestroy(s.stream);
-    if (s.side) cudaStreamDestroy(s.side);
+    for (auto q : s.side) if (q) cudaStreamDestroy(q);
     if (s.ev_counts) cudaEventDestroy(s.ev_counts);
     if (s.ev_upload) cudaEventDestroy(s.ev_upload);
-    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
-    if (s.ev_join) cudaEventDestroy(s.ev_join);
+    for (auto e : s.ev_fork) if (e) cudaEventDestroy(e);
+    for (auto e : s.ev_join) if (e) cudaEventDestroy(e);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_rgb); cudaFreeHost(s.h_rgb); cudaFree(s.d_gauss); cudaFree(s.d_mask); cudaFree(s.d_rows);
     cudaFree(s.d_rowoff); cudaFree(s.d_counts); cudaFree(s.d_sched); cudaFreeHost(s.h_counts);
     free_cand_arrays(s);
@@ -673,7 +678,7 @@ void launch_extrema(sb200_ctx* ctx, cudaStream_t st, int slot, int o, const Extr
 int tail_first_octave(const sb200_ctx* ctx) {
     if (!ctx->tail) return ctx->L.n_oct;
     int o = ctx->L.n_oct;
-    while (o > 1 && (long long)ctx->L.o[o - 1].w * ctx->L.o[o - 1].h <= TAIL_MAX_PX) o--;   // octave 0 always takes the seed path
+    while (o > 1 && tail_fits(ctx->L.o[o - 1].w, ctx->L.o[o - 1].h)) o--;   // octave 0 always takes the seed path
     return o;
 }
 
@@ -709,12 +714,24 @@ int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, u
         launch_blur_imageproc<0>(ctx, s, st, 0, blur_params(0, 5, 0), n, 5);
         count_launch(ctx, SB200_STAGE_SEED, 2);
     }
+    // layers 4 and 5 and the extrema scan of an octave on a side stream, as in enqueue_pyramid
+    const bool fork = ctx->fork_octaves && !ctx->profiling;
+    uint32_t forked = 0;
+    cudaStream_t const st_main = st;
     for (int o = 0; o < L.n_oct; o++) {
         const OctLayout& ol = L.o[o];
         if (ol.w < 1 || ol.h < 1) continue;
+        st = st_main;
         {
             StageScope sc(ctx, st, SB200_STAGE_BLUR);
             for (int l = 1; l < N_LAYERS; l++) {
+                if (fork && l == 4) {
+                    const int q = o % ctx->n_side;
+                    CU(cudaEventRecord(s.ev_fork[o], st_main));
+                    CU(cudaStreamWaitEvent(s.side[q], s.ev_fork[o], 0));
+                    st = s.side[q];
+                    forked |= 1u << q;
+                }
                 {
                     StageScope fine(ctx, st, SB200_STAGE_COUNT + o * 8 + l);
                     const BlurParams p = blur_params(o, l - 1, l);
@@ -755,6 +772,11 @@ int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, u
             launch_extrema<false>(ctx, st, s.index, o, e, n);
             count_launch(ctx, SB200_STAGE_EXTREMA);
         }
+    }
+    for (int q = 0; q < N_SIDE_MAX; q++) {
+        if (!(forked >> q & 1)) continue;
+        CU(cudaEventRecord(s.ev_join[q], s.side[q]));
+        CU(cudaStreamWaitEvent(st_main, s.ev_join[q], 0));
     }
     CU(cudaGetLastError());
     return SB200_OK;
@@ -806,7 +828,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
     // forked onto the slot's side stream so that the chain of octaves (the critical path of a small batch) does not
     // wait for them.  Stage timing needs one stream.
     const bool fork = ctx->fork_octaves && !ctx->profiling;
-    bool forked = false;
+    uint32_t forked = 0;   // side streams in use
     cudaStream_t const st_main = st;
     for (int o = 0; o < o_tail; o++) {
         const OctLayout& ol = L.o[o];
@@ -816,10 +838,11 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             StageScope sc(ctx, st, SB200_STAGE_BLUR);
             for (int l = 1; l < N_LAYERS; l++) {
                 if (fork && l == 4) {
-                    CU(cudaEventRecord(s.ev_fork, st_main));
-                    CU(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
-                    st = s.side;
-                    forked = true;
+                    const int q = o % ctx->n_side;
+                    CU(cudaEventRecord(s.ev_fork[o], st_main));
+                    CU(cudaStreamWaitEvent(s.side[q], s.ev_fork[o], 0));
+                    st = s.side[q];
+                    forked |= 1u << q;
                 }
                 BlurParams p{};
                 p.src = s.d_gauss + ol.off + (long long)(l - 1) * ol.layer_stride;
@@ -902,9 +925,10 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
         k_tail<false><<<n, TAIL_THREADS, TAIL_SMEM, st>>>(t);
         count_launch(ctx, SB200_STAGE_BLUR);
     }
-    if (forked) {   // join: the candidate scan needs every octave's mask
-        CU(cudaEventRecord(s.ev_join, s.side));
-        CU(cudaStreamWaitEvent(st_main, s.ev_join, 0));
+    for (int q = 0; q < N_SIDE_MAX; q++) {   // join: the candidate scan needs every octave's mask
+        if (!(forked >> q & 1)) continue;
+        CU(cudaEventRecord(s.ev_join[q], s.side[q]));
+        CU(cudaStreamWaitEvent(st_main, s.ev_join[q], 0));
     }
     CU(cudaGetLastError());
     return SB200_OK;
@@ -1256,12 +1280,26 @@ int launch_group(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img,
         } else {
             // pageable memory: packed into the slot's pinned staging buffer (stage_group, normally already done by
             // the batch loop while the slot's previous group was still running), then one async copy
-            if (!(s.staged && s.staged_first == first_img)) {
-                int rc = stage_group(ctx, s, src, first_img, n, w, h);
-                if (rc) return rc;
+            const size_t total = rowb * h * n;
+            if (!(s.staged && s.staged_first == first_img) && stride == rowb && contiguous && total <= ((size_t)12 << 20)) {
+                // a small densely packed group nobody staged ahead (a single image, the first group of a call): packed
+                // and uploaded piece by piece on this thread, so that the copy engine moves piece k while piece k + 1 is
+                // packed -- the upload costs the packing time alone
+                CU(cudaEventSynchronize(s.ev_upload));
+                constexpr size_t PIECE = (size_t)512 << 10;
+                for (size_t o = 0; o < total; o += PIECE) {
+                    const size_t nb = std::min(PIECE, total - o);
+                    memcpy(h_up + o, img + o, nb);
+                    CU(cudaMemcpyAsync(d_up + o, h_up + o, nb, cudaMemcpyHostToDevice, st));
+                }
+            } else {
+                if (!(s.staged && s.staged_first == first_img)) {
+                    int rc = stage_group(ctx, s, src, first_img, n, w, h);
+                    if (rc) return rc;
+                }
+                CU(cudaMemcpyAsync(d_up, h_up, total, cudaMemcpyHostToDevice, st));
             }
             s.staged = false;
-            CU(cudaMemcpyAsync(d_up, h_up, rowb * h * n, cudaMemcpyHostToDevice, st));
             CU(cudaEventRecord(s.ev_upload, st));
         }
         if (channels > 1) {
@@ -1289,7 +1327,7 @@ int launch_group(sb200_ctx* ctx, Slot& s, const Source& src, uint64_t first_img,
 int grow_capacity(sb200_ctx* ctx, uint32_t need) {
     for (auto& t : ctx->slot) {
         CU(cudaStreamSynchronize(t.stream));
-        CU(cudaStreamSynchronize(t.side));
+        for (auto q : t.side) CU(cudaStreamSynchronize(q));
     }
     const uint64_t nc = std::max<uint64_t>((uint64_t)need + need / 4 + 1024, (uint64_t)ctx->cap * 2);
     if (nc > 0x3fffffffull) return fail(ctx, SB200_E_CAPACITY, "%u candidates per image exceed the supported maximum", need);
@@ -1559,6 +1597,7 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
             ctx->march = !(e && !strcmp(e, "tile"));
             const char* fk = getenv("SB200_FORK");
             ctx->fork_octaves = !(fk && !strcmp(fk, "0"));
+            if (const char* sd = getenv("SB200_SIDES")) ctx->n_side = std::min(std::max(atoi(sd), 1), N_SIDE_MAX);
             const char* gr = getenv("SB200_GRAPHS");
             ctx->use_graphs = !(gr && !strcmp(gr, "0"));
             const char* jc = getenv("SB200_JPEG_CHUNK");
@@ -1650,7 +1689,7 @@ int sb200_set_processing(sb200_ctx* ctx, int processing) {
     if (processing == ctx->flavour) return SB200_OK;
     for (auto& t : ctx->slot) {
         CU(cudaStreamSynchronize(t.stream));
-        CU(cudaStreamSynchronize(t.side));
+        for (auto q : t.side) CU(cudaStreamSynchronize(q));
         for (auto& g : t.graphs) cudaGraphExecDestroy(g.exec);   // captured with the other flavour's kernels
         t.graphs.clear();
         t.busy = false;

@@ -1,6 +1,6 @@
 """Per-launch device times of the pyramid stages (CUDA events, no profiler attached): which octave / layer costs what.
 
-    python tools/fine_profile.py [1080p|vga|4k] [images per group] [repeats]
+    python tools/fine_profile.py [1080p|vga|4k] [images per group] [repeats] [opencv|imageproc]
 
 Prints, per (octave, kind), the average launch time, the pixels it covers, and the algorithmic GB/s
 (8 B/px for a blur, 24 B/px for the extrema scan) against the measured HBM peak.
@@ -28,8 +28,9 @@ try:
     peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
+flavour = sys.argv[4] if len(sys.argv) > 4 else "opencv"
 lib = _ffi.load()
-ex = sf.Extractor(w, h, B)
+ex = sf.Extractor(w, h, B, processing=sf.ImageprocProcessing if flavour == "imageproc" else sf.OpenCVProcessing)
 H = ex.handle
 imgs = np.stack([np.random.default_rng([1234, i]).integers(0, 256, (h, w), dtype=np.uint8) for i in range(B)])
 d = C.c_void_p()
@@ -53,7 +54,7 @@ while True:
     if len(dims) >= 16 or min(cw, ch) <= 1:
         break
     cw, ch = cw // 2, ch // 2
-print(f"# {name}: {B} images per launch, {reps} repeats, HBM peak {peak} GB/s")
+print(f"# {name} ({flavour} flavour): {B} images per launch, {reps} repeats, HBM peak {peak} GB/s")
 tot = 0.0
 for (o, kind), (ms, n) in sorted(fine.items()):
     us = 1e3 * ms / n
