@@ -607,8 +607,34 @@ def single_image(lib, sf, device):
             for _ in range(n):
                 r = ex.sift(img)
             dt = (time.perf_counter() - t0) / n
+            # the same call at the C ABI (no numpy result copies), from pinned memory, and with the image resident
+            H = ex.handle
+            res = _ffi_result()
+            pin = C.c_void_p()
+            lib.sb200_host_alloc(img.nbytes, C.byref(pin))
+            C.memmove(pin, img.ctypes.data, img.nbytes)
+            dev = C.c_void_p()
+            lib.sb200_device_alloc(H, img.nbytes, C.byref(dev))
+            lib.sb200_memcpy_h2d(H, dev, img.ctypes.data, img.nbytes)
+
+            def med(f):
+                for _ in range(3):
+                    f()
+                ts = []
+                for _ in range(n):
+                    t0 = time.perf_counter(); f(); ts.append(time.perf_counter() - t0)
+                return 1e3 * float(np.median(ts))
+            abi = {
+                "pageable_host_ms": med(lambda: lib.sb200_extract_batch(H, img.ctypes.data, 1, w, h, w, w * h, -1, C.byref(res))),
+                "pinned_host_ms": med(lambda: lib.sb200_extract_batch(H, pin, 1, w, h, w, w * h, -1, C.byref(res))),
+                "device_resident_ms": med(lambda: (lib.sb200_extract_batch_device(H, dev, 1, w, h, w, w * h, -1), lib.sb200_sync(H))),
+                "pyramid_only_ms": med(lambda: (lib.sb200_pyramid_batch_device(H, dev, 1, w, h, w, w * h), lib.sb200_sync(H))),
+            }
+            lib.sb200_device_free(H, dev)
+            lib.sb200_host_free(pin)
         out[name] = {"ms_per_image": 1e3 * dt, "images_s": 1.0 / dt, "keypoints": len(r),
-                     "call": "sift(img) on one pageable host image, result copied back"}
+                     "call": "sift(img) on one pageable host image, result copied back into numpy arrays",
+                     "c_abi": abi}
     bird = np.load(os.path.join(ROOT, "tests", "golden", "bird_gray.npy"))
     with sf.Extractor(bird.shape[1], bird.shape[0], 1, device=device) as ex:
         for _ in range(5):

@@ -1417,45 +1417,55 @@ struct TailParams {
     uint32_t* rows;              // row counters, image 0
 };
 
-// mirrored halo columns [-R, 0) and [w, w + R) of every row of `a` (pitch w + 2 RMAX, column 0 at offset RMAX)
+// halo columns [-R, 0) and [w, w + R) of every row of `a` (pitch w + 2 RMAX, column 0 at offset RMAX): mirrored
+// (BORDER_REFLECT_101) or clamped to the edge pixel (imageproc flavour)
+template <int FL>
 __device__ __forceinline__ void tail_halo_cols(float* __restrict__ a, const int R, const int w, const int h) {
     const int wp = w + 2 * TAIL_RMAX;
     for (int idx = threadIdx.x; idx < 2 * R * h; idx += TAIL_THREADS) {
         const int y = idx / (2 * R), k = idx - y * (2 * R);
         const int col = k < R ? k - R : w + (k - R);
         float* const row = a + y * wp + TAIL_RMAX;
-        row[col] = row[reflect101(col, w)];
+        row[col] = row[border_index<FL>(col, w)];
     }
 }
 
-template <int LI, int R_NEXT>
+template <int LI, int R_NEXT, int FL>
 __device__ __forceinline__ void tail_blur(float* __restrict__ a /* smem, padded columns: source, then result */,
                                           float* __restrict__ b /* smem, padded rows */,
                                           float* __restrict__ dst, float* __restrict__ dec, const int w, const int h,
                                           const int pitch, const int dec_w, const int dec_h, const int dec_pitch) {
-    constexpr int R = blur_radius(LI);
+    constexpr int R = blur_radius(LI, FL);
     const int n = w * h, wp = w + 2 * TAIL_RMAX;
     for (int idx = threadIdx.x; idx < n; idx += TAIL_THREADS) {
         const int y = idx / w, x = idx - y * w;
         const float* q = a + y * wp + (TAIL_RMAX - R) + x;
-        float acc = q[0] * c_taps[LI][0];
+        float acc = q[0] * tap<FL>(LI, 0);
 #pragma unroll
-        for (int i = 1; i <= 2 * R; i++) acc = fmaf(q[i], c_taps[LI][i], acc);
+        for (int i = 1; i <= 2 * R; i++)
+            acc = FL == FL_OPENCV ? fmaf(q[i], tap<FL>(LI, i), acc) : __fadd_rn(acc, __fmul_rn(q[i], tap<FL>(LI, i)));
         b[idx + TAIL_RMAX * w] = acc;
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < 2 * R * w; idx += TAIL_THREADS) {   // mirrored rows [-R, 0) and [h, h + R)
         const int k = idx / w, x = idx - k * w;
         const int row = k < R ? k - R : h + (k - R);
-        b[(row + TAIL_RMAX) * w + x] = b[(reflect101(row, h) + TAIL_RMAX) * w + x];
+        b[(row + TAIL_RMAX) * w + x] = b[(border_index<FL>(row, h) + TAIL_RMAX) * w + x];
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < n; idx += TAIL_THREADS) {
         const int y = idx / w, x = idx - y * w;
         const float* c = b + idx + TAIL_RMAX * w;
-        float acc = c[0] * c_taps[LI][R];
+        float acc;
+        if (FL == FL_OPENCV) {
+            acc = c[0] * tap<FL>(LI, R);
 #pragma unroll
-        for (int i = 1; i <= R; i++) acc = fmaf(c[i * w] + c[-i * w], c_taps[LI][R + i], acc);
+            for (int i = 1; i <= R; i++) acc = fmaf(c[i * w] + c[-i * w], tap<FL>(LI, R + i), acc);
+        } else {   // top to bottom, a multiply and an add per tap
+            acc = c[-R * w] * tap<FL>(LI, 0);
+#pragma unroll
+            for (int i = 1; i <= 2 * R; i++) acc = __fadd_rn(acc, __fmul_rn(c[(i - R) * w], tap<FL>(LI, i)));
+        }
         a[y * wp + TAIL_RMAX + x] = acc;
         dst[(long long)y * pitch + x] = acc;
         if (dec && !(y & 1) && !(x & 1)) {
@@ -1465,12 +1475,12 @@ __device__ __forceinline__ void tail_blur(float* __restrict__ a /* smem, padded 
     }
     __syncthreads();
     if (R_NEXT > 0) {   // the next blur's halo columns
-        tail_halo_cols(a, R_NEXT, w, h);
+        tail_halo_cols<FL>(a, R_NEXT, w, h);
         __syncthreads();
     }
 }
 
-template <bool KEEP_FLAT>
+template <bool KEEP_FLAT, int FL = FL_OPENCV>
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
     extern __shared__ __align__(16) float tail_smem[];
     float* const a = tail_smem;                    // (w + 2 RMAX) x h
@@ -1489,18 +1499,31 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
             a[y * (w + 2 * TAIL_RMAX) + TAIL_RMAX + x] = g0[(long long)y * ol.pitch + x];
         }
         __syncthreads();
-        tail_halo_cols(a, blur_radius(1), w, h);
+        tail_halo_cols<FL>(a, blur_radius(1, FL), w, h);
         __syncthreads();
         float* dec = nullptr;
         int dw = 0, dh = 0, dp = 0;
         if (o + 1 < p.L.n_oct && p.L.o[o + 1].w >= 1 && p.L.o[o + 1].h >= 1) {
             dec = gimg + p.L.o[o + 1].off; dw = p.L.o[o + 1].w; dh = p.L.o[o + 1].h; dp = p.L.o[o + 1].pitch;
         }
-        tail_blur<1, blur_radius(2)>(a, b, g0 + 1 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<2, blur_radius(3)>(a, b, g0 + 2 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<3, blur_radius(4)>(a, b, g0 + 3 * ol.layer_stride, dec, w, h, ol.pitch, dw, dh, dp);
-        tail_blur<4, blur_radius(5)>(a, b, g0 + 4 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<5, 0>(a, b, g0 + 5 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<1, blur_radius(2, FL), FL>(a, b, g0 + 1 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<2, blur_radius(3, FL), FL>(a, b, g0 + 2 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<3, blur_radius(4, FL), FL>(a, b, g0 + 3 * ol.layer_stride, FL == FL_OPENCV ? dec : nullptr, w, h, ol.pitch,
+                                             dw, dh, dp);
+        if (FL != FL_OPENCV && dec) {
+            // the imageproc flavour's Nearest resize of layer 3 (k_decimate_b): source pixel floor((d + 0.5) * (n_src /
+            // n_dst)) in f32, result clamped to [0, 1]; `a` holds layer 3 until the column pass of the next blur, two
+            // barriers from here
+            const float ry = (float)h / (float)dh, rx = (float)w / (float)dw;
+            for (int idx = tid; idx < dw * dh; idx += TAIL_THREADS) {
+                const int dy = idx / dw, dx = idx - dy * dw;
+                const int sy = min(max((int)floorf(((float)dy + 0.5f) * ry), 0), h - 1);
+                const int sx = min(max((int)floorf(((float)dx + 0.5f) * rx), 0), w - 1);
+                dec[(long long)dy * dp + dx] = fminf(fmaxf(a[sy * (w + 2 * TAIL_RMAX) + TAIL_RMAX + sx], 0.0f), 1.0f);
+            }
+        }
+        tail_blur<4, blur_radius(5, FL), FL>(a, b, g0 + 4 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<5, 0, FL>(a, b, g0 + 5 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
         if (ol.scanned) {
             ExtremaParams e;
             e.gauss = p.gauss + ol.off; e.img_stride = p.L.img_floats; e.layer_stride = ol.layer_stride;

@@ -684,7 +684,7 @@ int tail_first_octave(const sb200_ctx* ctx) {
 
 // The pyramid in the arithmetic of the crate's default Processing (ImageprocProcessing, src/lib.rs:992-1007): the same
 // stages as below with the imageproc tap sets / clamp borders, the image crate's two resizes as kernels of their own,
-// every octave through the per-layer launches (no fused tail).  The extrema scan and everything after it do not
+// the small octaves through the fused tail kernel in its imageproc instantiation.  The extrema scan and everything after it do not
 // depend on the flavour.
 int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h, uint32_t in_stride,
                               uint64_t in_img_stride, const uint8_t* d_in) {
@@ -718,7 +718,8 @@ int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, u
     const bool fork = ctx->fork_octaves && !ctx->profiling;
     uint32_t forked = 0;
     cudaStream_t const st_main = st;
-    for (int o = 0; o < L.n_oct; o++) {
+    const int o_tail = tail_first_octave(ctx);
+    for (int o = 0; o < o_tail; o++) {
         const OctLayout& ol = L.o[o];
         if (ol.w < 1 || ol.h < 1) continue;
         st = st_main;
@@ -772,6 +773,17 @@ int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, u
             launch_extrema<false>(ctx, st, s.index, o, e, n);
             count_launch(ctx, SB200_STAGE_EXTREMA);
         }
+    }
+    st = st_main;
+    if (o_tail < L.n_oct && L.o[o_tail].w >= 1 && L.o[o_tail].h >= 1) {
+        // blurs + decimation + extrema of all the remaining (small) octaves: one CTA per image, one launch
+        StageScope sc(ctx, st, SB200_STAGE_BLUR);
+        StageScope fine(ctx, st, SB200_STAGE_COUNT + o_tail * 8 + 7);
+        TailParams t{};
+        t.L = L; t.o_first = o_tail;
+        t.gauss = s.d_gauss; t.mask = s.d_mask; t.rows = s.d_rows;
+        k_tail<false, FL_IMAGEPROC><<<n, TAIL_THREADS, TAIL_SMEM, st>>>(t);
+        count_launch(ctx, SB200_STAGE_BLUR);
     }
     for (int q = 0; q < N_SIDE_MAX; q++) {
         if (!(forked >> q & 1)) continue;
@@ -1605,6 +1617,7 @@ int sb200_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
             const char* tl = getenv("SB200_TAIL");
             ctx->tail = !(tl && !strcmp(tl, "0"));
             CU(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM));
+            CU(cudaFuncSetAttribute(k_tail<false, FL_IMAGEPROC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM));
             const char* sr = getenv("SB200_SEG_ROWS");
             if (sr && atoi(sr) >= 32) ctx->seg_rows_override = atoi(sr) / 32 * 32;
             const char* sd = getenv("SB200_SEED");

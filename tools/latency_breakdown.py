@@ -1,4 +1,4 @@
-"""Where a single-image call spends its time: python tools/latency_breakdown.py [WxH]
+"""Where a single-image call spends its time: python tools/latency_breakdown.py [WxH] [opencv|imageproc]
    sift() from pageable / pinned host memory, the device-resident call (no copies), the pyramid alone."""
 import ctypes as C, os, sys, time
 import numpy as np
@@ -7,6 +7,8 @@ import sift_features_b200 as sf
 from sift_features_b200 import _ffi
 size = sys.argv[1] if len(sys.argv) > 1 else "1920x1080"
 w, h = map(int, size.split("x"))
+flavour = sys.argv[2] if len(sys.argv) > 2 else "opencv"
+P = sf.ImageprocProcessing if flavour == "imageproc" else sf.OpenCVProcessing
 lib = _ffi.load()
 g = np.random.default_rng(1234).integers(0, 256, (h, w), dtype=np.uint8)
 
@@ -20,7 +22,7 @@ def med(f, n=40):
     return 1e3 * float(np.median(ts))
 
 
-with sf.Extractor(w, h, 1) as ex:
+with sf.Extractor(w, h, 1, processing=P) as ex:
     H = ex.handle
     t_sift = med(lambda: ex.sift(g))
     p = C.c_void_p(); assert lib.sb200_host_alloc(g.nbytes, C.byref(p)) == 0
@@ -38,5 +40,5 @@ with sf.Extractor(w, h, 1) as ex:
         lib.sb200_pyramid_batch_device(H, d, 1, w, h, w, w * h); lib.sb200_sync(H)
     t_dev = med(dev)
     t_pyr = med(pyr)
-    print(f"{size} fork={os.environ.get('SB200_FORK', '1')}: sift() {t_sift:.3f} ms | C ABI pageable {t_abi_pageable:.3f} pinned {t_abi_pinned:.3f} | "
+    print(f"{size} {flavour} tail={os.environ.get('SB200_TAIL', '1')} fork={os.environ.get('SB200_FORK', '1')}: sift() {t_sift:.3f} ms | C ABI pageable {t_abi_pageable:.3f} pinned {t_abi_pinned:.3f} | "
           f"device-resident {t_dev:.3f} | pyramid only {t_pyr:.3f} | keypoints {int(res.n)}")
