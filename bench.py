@@ -586,7 +586,7 @@ def sub_workloads(args, M, lib, sf, dist, rank, local_rank, world, peak):
     out["vga"] = shape("vga")
     out["4k"] = shape("4k")
     out["natural_1080p"] = shape("1080p", natural=True)
-    out["imageproc_1080p"] = shape("1080p", processing=sf.ImageprocProcessing)
+    out["imageproc_natural_1080p"] = shape("1080p", natural=True, processing=sf.ImageprocProcessing)
     out["desc"] = desc_measure(args, lib, sf, dist, rank, local_rank, world, steps, peak)
     if rank == 0:
         out["single_image"] = single_image(lib, sf, local_rank)
