@@ -102,6 +102,12 @@ struct OutKeyPoint {
 #define SB_CHECK_LOAD(ptr, base, elems, what) do { } while (0)
 #endif
 
+// Programmatic dependent launch (griddepcontrol.wait; SASS ACQBULK / DEPBAR on the grid dependency): the kernels of a
+// group are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs may be scheduled while
+// the kernel before it in the stream (or graph chain) is still draining; nothing that kernel wrote -- or still reads --
+// may be touched before this returns, so it is the first statement of every kernel.  No-op for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Blackwell packed single precision (SASS FFMA2 / FADD2 / FMUL2): two independent IEEE round-to-nearest
 // operations per instruction, i.e. the same bits as the scalar fmaf / + / * -- but half the issue slots,
 // which is what bounds the wide-tap blurs.

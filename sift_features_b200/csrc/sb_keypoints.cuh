@@ -64,6 +64,7 @@ struct DogView {
 // interpolate_extremum + extremum_contrast + extremum_is_on_edge + keypoint geometry
 // (src/lib.rs:334-380, 525-653).  One thread per candidate.
 __global__ void __launch_bounds__(128) k_refine(const KpParams P) {
+    pdl_wait();
     __shared__ uint64_t s_tab[32];
     if (threadIdx.x < 32) s_tab[threadIdx.x] = sbm::d_exp2_tab[threadIdx.x];
     __syncthreads();
@@ -216,6 +217,7 @@ constexpr int ORI_CHUNK = SB_ORI_CHUNK;
 // per-candidate cost, and its grid is exactly the number of resident CTAs.
 __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, const uint32_t* __restrict__ cand_off,
                                                             const int n_img, uint32_t* __restrict__ work) {
+    pdl_wait();
     __shared__ uint64_t s_tab[32];
     __shared__ float s_val[ORI_WARPS][32];
     __shared__ float s_raw[ORI_WARPS][40];
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(32 * ORI_WARPS) k_orient(const KpParams P, con
 
 // exclusive scan of n_ori over the candidates of one image (one CTA per image)
 __global__ void __launch_bounds__(1024) k_kpscan(const KpParams P) {
+    pdl_wait();
     __shared__ uint32_t wsum[32];
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = min(P.cand_count[img], P.cap);
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(1024) k_kpscan(const KpParams P) {
 
 // SiftKeyPoint records in natural order (src/lib.rs:419-427)
 __global__ void __launch_bounds__(256) k_emit(const KpParams P) {
+    pdl_wait();
     const long long img = blockIdx.y;
     const uint32_t n = min(P.cand_count[img], P.cap);
     const Refined* refined = P.refined + img * (long long)P.cap;
@@ -437,6 +441,7 @@ __global__ void __launch_bounds__(1024) k_sort_response(const DevKeyPoint* __res
                                                          const uint32_t* __restrict__ kp_count, uint32_t kcap,
                                                          uint32_t* __restrict__ scratch /* [img][4*kcap] */,
                                                          uint32_t* __restrict__ order /* [img][kcap] */) {
+    pdl_wait();
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_wcnt[32][257];
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1064,6 +1069,7 @@ struct DescParams {
 __global__ void __launch_bounds__(1024) k_out_offsets(const uint32_t* __restrict__ kp_count, uint32_t kcap,
                                                        long long limit, int n_img, uint32_t* __restrict__ out_count,
                                                        uint32_t* __restrict__ out_off) {
+    pdl_wait();
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t s_run;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1115,6 +1121,7 @@ constexpr int DESC_CHUNK = SB_DESC_CHUNK;
 // warps pull chunks from an atomic counter (see k_orient).
 __global__ void __launch_bounds__(32 * DESC_WARPS, SB_DESC_MINB) k_descriptor(const DescParams P, const int n_img,
                                                                 uint32_t* __restrict__ work) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char desc_smem[];  // DESC_SMEM_BYTES, dynamic (> 48 KB)
     uint64_t* s_tab = reinterpret_cast<uint64_t*>(desc_smem);
     float (*s_hist)[DESC_SMEM_WORDS] = reinterpret_cast<float (*)[DESC_SMEM_WORDS]>(desc_smem + 256);
@@ -1155,6 +1162,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS, SB_DESC_LIST_MINB) k_descript
                                                                       int pitch, const DescIn* __restrict__ kps,
                                                                       unsigned long long n, uint8_t* __restrict__ out,
                                                                       uint32_t* __restrict__ err) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char desc_smem[];  // DESC_SMEM_BYTES, dynamic (> 48 KB)
     uint64_t* s_tab = reinterpret_cast<uint64_t*>(desc_smem);
     float (*s_hist)[DESC_SMEM_WORDS] = reinterpret_cast<float (*)[DESC_SMEM_WORDS]>(desc_smem + 256);

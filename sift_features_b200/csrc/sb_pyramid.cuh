@@ -112,6 +112,7 @@ struct BlurParams {
 // src/lib.rs:196-210); DECIMATE also writes the even pixels into the next octave.
 template <int L, bool SEED, bool DECIMATE, int FL = FL_OPENCV>
 __global__ void __launch_bounds__(256, 2) k_blur(const BlurParams p) {
+    pdl_wait();
     static_assert(FL == FL_OPENCV || (!SEED && !DECIMATE), "the imageproc flavour upsamples and decimates in its own kernels");
     using C = BlurCfg<L, FL>;
     constexpr int R = C::R;
@@ -322,6 +323,7 @@ __device__ __forceinline__ void upsample_block(const uint8_t* __restrict__ in, c
 }
 
 __global__ void __launch_bounds__(256) k_upsample2x(const UpsampleParams p) {
+    pdl_wait();
     // v / 255 for the 256 possible pixel values (the IEEE division itself, done once per CTA instead of 8x per thread)
     __shared__ float s_norm[256];
     s_norm[threadIdx.x] = (float)threadIdx.x / 255.0f;
@@ -367,6 +369,7 @@ __device__ __forceinline__ float tri2x(const float a, const float b, const bool 
 }
 
 __global__ void __launch_bounds__(256) k_upsample2x_b(const UpsampleParams p) {
+    pdl_wait();
     __shared__ float s_norm[256];
     s_norm[threadIdx.x] = (float)threadIdx.x / 255.0f;
     __syncthreads();
@@ -409,6 +412,7 @@ struct DecimateParams {
     int w, h, pitch, dw, dh, dpitch;
 };
 __global__ void __launch_bounds__(256) k_decimate_b(const DecimateParams p) {
+    pdl_wait();
     const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
     const long long img = blockIdx.z;
     if (dx >= p.dw) return;
@@ -469,6 +473,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 template <int L, bool DECIMATE>
 __global__ void __launch_bounds__(256, TmaCfg<L>::CTAS_PER_SM) k_blur_tma(const __grid_constant__ CUtensorMap tmap, const BlurParams p,
                                                       const int src_layer) {
+    pdl_wait();
     using C = TmaCfg<L>;
     constexpr int R = C::R;
     extern __shared__ __align__(1024) float smem_tma[];  // own symbol: `smem` above is declared 16-byte aligned
@@ -711,6 +716,7 @@ template <int L, bool DECIMATE, int FL = FL_OPENCV, int SEEDF = 0>
 __global__ void __launch_bounds__(MarchCfg<L, FL>::THREADS + (SEEDF == 2 ? SEED_PRODUCERS : 0), MarchCfg<L, FL>::CTAS_PER_SM)
 k_blur_march(const __grid_constant__ CUtensorMap tmap, const BlurParams p, const int src_layer, const int bands_per_cta,
              const int strips, const long long total_bands) {
+    pdl_wait();
     static_assert(FL == FL_OPENCV || !DECIMATE, "the imageproc flavour decimates in its own kernel");
     static_assert(!SEEDF || (L == 0 && FL == FL_OPENCV && !DECIMATE), "the fused seed is layer 0 of the OpenCV flavour");
     using C = MarchCfg<L, FL>;
@@ -1281,6 +1287,7 @@ __device__ __forceinline__ void ex_strip(const ExtremaParams& p, const int strip
 
 template <bool KEEP_FLAT>
 __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema(const ExtremaParams p) {
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = (blockIdx.y * EX_WARPS + warp) * EX_ROWS;
     if (y0 >= p.h) return;
@@ -1321,6 +1328,7 @@ __device__ __forceinline__ void ext_step(const ExWarp& W, ExState& S, const floa
 
 template <bool KEEP_FLAT>
 __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema_tma(const __grid_constant__ CUtensorMap tmap, const ExtremaParams p) {
+    pdl_wait();
     extern __shared__ __align__(1024) float ext_smem[];
     __shared__ __align__(8) uint64_t bar[EX_WARPS][EXT_NS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1482,6 +1490,7 @@ __device__ __forceinline__ void tail_blur(float* __restrict__ a /* smem, padded 
 
 template <bool KEEP_FLAT, int FL = FL_OPENCV>
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
+    pdl_wait();
     extern __shared__ __align__(16) float tail_smem[];
     float* const a = tail_smem;                    // (w + 2 RMAX) x h
     float* const b = tail_smem + TAIL_A_FLOATS;    // w x (h + 2 RMAX)
@@ -1545,6 +1554,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
 // Exclusive scan of the per-row candidate counts of one image (one CTA per image).
 __global__ void __launch_bounds__(1024) k_rowscan(const uint32_t* __restrict__ rows, uint32_t* __restrict__ rowoff,
                                                    int n_rows, uint32_t* __restrict__ cand_count) {
+    pdl_wait();
     __shared__ uint32_t wsum[32];
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     rows += (long long)img * n_rows;
@@ -1588,6 +1598,7 @@ __global__ void __launch_bounds__(256) k_compact(const PyrLayout L, const uint32
                                                   const uint32_t* __restrict__ rows,
                                                   const uint32_t* __restrict__ rowoff, CandKey* __restrict__ keys,
                                                   uint32_t cap) {
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ridx = blockIdx.x * 8 + warp;
     const long long img = blockIdx.y;
@@ -1631,6 +1642,7 @@ __global__ void __launch_bounds__(256) k_compact(const PyrLayout L, const uint32
 // dense copy of a DoG layer for the PrecomputedImages.dog accessor (src/lib.rs:126)
 __global__ void k_dog_layer(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int w,
                             int h, int pitch) {
+    pdl_wait();
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x < w && y < h) out[(long long)y * w + x] = b[(long long)y * pitch + x] - a[(long long)y * pitch + x];
 }

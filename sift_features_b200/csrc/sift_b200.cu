@@ -570,6 +570,28 @@ int set_image_size(sb200_ctx* ctx, uint32_t w, uint32_t h) {
 }
 
 // ---- launches -----------------------------------------------------------------
+// Launch of a kernel of the group pipeline.  With programmatic dependent launch on (default; SB200_PDL=0 turns it off)
+// the launch carries cudaLaunchAttributeProgrammaticStreamSerialization: the kernel may be scheduled while its
+// predecessor in the stream -- inside a captured graph: on its chain -- is still draining, and waits for it in its first
+// statement (pdl_wait, griddepcontrol.wait), which takes the launch latency out of the ~35 dependent launches on the
+// critical path of a group.  No kernel triggers its dependents early (a dependent's CTAs would only sit on SM slots the
+// other slot's kernels could use): the trigger is the implicit one at the exit of the predecessor's last CTA.
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SB200_PDL"); return !(e && !strcmp(e, "0")); }();
+    return on;
+}
+template <typename... KA, typename... A>
+void klaunch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);   // errors surface at the enqueue functions' cudaGetLastError
+}
+
 template <int LI, bool SEED, bool DEC>
 int set_blur_attr(sb200_ctx* ctx) {
     CU(cudaFuncSetAttribute(k_blur<LI, SEED, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -581,7 +603,7 @@ template <int LI, bool SEED, bool DEC>
 void launch_blur(cudaStream_t st, const BlurParams& p, uint32_t n) {
     using C = BlurCfg<LI>;
     dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + C::TH - 1) / C::TH, n);
-    k_blur<LI, SEED, DEC><<<grid, C::THREADS, C::SMEM, st>>>(p);
+    klaunch(k_blur<LI, SEED, DEC>, dim3(grid), dim3(C::THREADS), C::SMEM, st, p);
 }
 
 template <int LI, bool DEC>
@@ -595,7 +617,7 @@ template <int LI, bool DEC>
 void launch_blur_tma(cudaStream_t st, const CUtensorMap& tm, const BlurParams& p, uint32_t n, int src_layer) {
     using C = TmaCfg<LI>;
     dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + C::TH - 1) / C::TH, n);
-    k_blur_tma<LI, DEC><<<grid, C::THREADS, C::SMEM, st>>>(tm, p, src_layer);
+    klaunch(k_blur_tma<LI, DEC>, dim3(grid), dim3(C::THREADS), C::SMEM, st, tm, p, src_layer);
 }
 
 template <int LI, bool DEC, int FL = FL_OPENCV, int SEEDF = 0>
@@ -647,7 +669,7 @@ void launch_blur_march(sb200_ctx* ctx, cudaStream_t st, const CUtensorMap& tm, c
         per = -k;
         grid = (long long)strips * n * k;
     }
-    k_blur_march<LI, DEC, FL, SEEDF><<<(unsigned)grid, C::THREADS + (SEEDF == 2 ? SEED_PRODUCERS : 0), C::SMEM, st>>>(tm, p, src_layer, (int)per, strips, total);
+    klaunch(k_blur_march<LI, DEC, FL, SEEDF>, dim3((unsigned)grid), dim3(C::THREADS + (SEEDF == 2 ? SEED_PRODUCERS : 0)), C::SMEM, st, tm, p, src_layer, (int)per, strips, total);
 }
 
 // one blur of the imageproc flavour: marching TMA kernel for octaves that own a tensor map, generic tiles otherwise
@@ -658,7 +680,7 @@ void launch_blur_imageproc(sb200_ctx* ctx, Slot& s, cudaStream_t st, int o, cons
     } else {
         using C = BlurCfg<LI, FL_IMAGEPROC>;
         dim3 grid((p.w + C::TW - 1) / C::TW, (p.h + C::TH - 1) / C::TH, n);
-        k_blur<LI, false, false, FL_IMAGEPROC><<<grid, C::THREADS, C::SMEM, st>>>(p);
+        klaunch(k_blur<LI, false, false, FL_IMAGEPROC>, dim3(grid), dim3(C::THREADS), C::SMEM, st, p);
     }
 }
 
@@ -667,10 +689,10 @@ void launch_extrema(sb200_ctx* ctx, cudaStream_t st, int slot, int o, const Extr
     const OctLayout& ol = ctx->L.o[o];
     if (ctx->tmap_ok[o]) {
         dim3 grid(ex_strips(ol.w), (ol.h + EXT_ROWS * EX_WARPS - 1) / (EXT_ROWS * EX_WARPS), n);
-        k_extrema_tma<KEEP_FLAT><<<grid, 32 * EX_WARPS, EXT_SMEM, st>>>(ctx->tmap_ex[slot][o], e);
+        klaunch(k_extrema_tma<KEEP_FLAT>, dim3(grid), dim3(32 * EX_WARPS), EXT_SMEM, st, ctx->tmap_ex[slot][o], e);
     } else {
         dim3 grid(ex_strips(ol.w), (ol.h + EX_ROWS * EX_WARPS - 1) / (EX_ROWS * EX_WARPS), n);
-        k_extrema<KEEP_FLAT><<<grid, 32 * EX_WARPS, 0, st>>>(e);
+        klaunch(k_extrema<KEEP_FLAT>, dim3(grid), dim3(32 * EX_WARPS), 0, st, e);
     }
 }
 
@@ -710,7 +732,7 @@ int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, u
         u.dst = s.d_gauss + L.o[0].off + 5 * L.o[0].layer_stride;
         u.img_stride = L.img_floats; u.pitch = L.o[0].pitch;
         dim3 grid((((int)w + 1) / 2 + 255) / 256, 2 * h, n);
-        k_upsample2x_b<<<grid, 256, 0, st>>>(u);
+        klaunch(k_upsample2x_b, dim3(grid), dim3(256), 0, st, u);
         launch_blur_imageproc<0>(ctx, s, st, 0, blur_params(0, 5, 0), n, 5);
         count_launch(ctx, SB200_STAGE_SEED, 2);
     }
@@ -752,7 +774,7 @@ int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, u
                     d.img_stride = L.img_floats;
                     d.w = ol.w; d.h = ol.h; d.pitch = ol.pitch;
                     d.dw = L.o[o + 1].w; d.dh = L.o[o + 1].h; d.dpitch = L.o[o + 1].pitch;
-                    k_decimate_b<<<dim3((d.dw + 255) / 256, d.dh, n), 256, 0, st>>>(d);
+                    klaunch(k_decimate_b, dim3(dim3((d.dw + 255) / 256, d.dh, n)), dim3(256), 0, st, d);
                     count_launch(ctx, SB200_STAGE_BLUR);
                 }
             }
@@ -782,7 +804,7 @@ int enqueue_pyramid_imageproc(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, u
         TailParams t{};
         t.L = L; t.o_first = o_tail;
         t.gauss = s.d_gauss; t.mask = s.d_mask; t.rows = s.d_rows;
-        k_tail<false, FL_IMAGEPROC><<<n, TAIL_THREADS, TAIL_SMEM, st>>>(t);
+        klaunch(k_tail<false, FL_IMAGEPROC>, dim3(n), dim3(TAIL_THREADS), TAIL_SMEM, st, t);
         count_launch(ctx, SB200_STAGE_BLUR);
     }
     for (int q = 0; q < N_SIDE_MAX; q++) {
@@ -826,7 +848,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
             u.dst = s.d_gauss + L.o[0].off + 5 * L.o[0].layer_stride;
             u.img_stride = L.img_floats; u.pitch = L.o[0].pitch;
             dim3 grid((((int)w + 1) / 2 + 255) / 256, (h + 1 + UPS_ROWS - 1) / UPS_ROWS, n);
-            k_upsample2x<<<grid, 256, 0, st>>>(u);
+            klaunch(k_upsample2x, dim3(grid), dim3(256), 0, st, u);
             if (ctx->march) launch_blur_march<0, false>(ctx, st, ctx->tmap_m[s.index][0][0], p, n, 5);
             else launch_blur_tma<0, false>(st, ctx->tmap[s.index][0][0], p, n, 5);
             count_launch(ctx, SB200_STAGE_SEED, 2);
@@ -934,7 +956,7 @@ int enqueue_pyramid(sb200_ctx* ctx, Slot& s, uint32_t n, uint32_t w, uint32_t h,
         TailParams t{};
         t.L = L; t.o_first = o_tail;
         t.gauss = s.d_gauss; t.mask = s.d_mask; t.rows = s.d_rows;
-        k_tail<false><<<n, TAIL_THREADS, TAIL_SMEM, st>>>(t);
+        klaunch(k_tail<false>, dim3(n), dim3(TAIL_THREADS), TAIL_SMEM, st, t);
         count_launch(ctx, SB200_STAGE_BLUR);
     }
     for (int q = 0; q < N_SIDE_MAX; q++) {   // join: the candidate scan needs every octave's mask
@@ -979,31 +1001,31 @@ int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
     CU(cudaMemsetAsync(work, 0, 4 * sizeof(uint32_t), st));
     {
         StageScope sc(ctx, st, SB200_STAGE_EXTREMA);
-        k_rowscan<<<n, 1024, 0, st>>>(s.d_rows, s.d_rowoff, L.img_rows, cand_count);
+        klaunch(k_rowscan, dim3(n), dim3(1024), 0, st, s.d_rows, s.d_rowoff, L.img_rows, cand_count);
         dim3 grid((L.img_rows + 7) / 8, n);
-        k_compact<<<grid, 256, 0, st>>>(L, s.d_mask, s.d_rows, s.d_rowoff, s.d_keys, ctx->cap);
+        klaunch(k_compact, dim3(grid), dim3(256), 0, st, L, s.d_mask, s.d_rows, s.d_rowoff, s.d_keys, ctx->cap);
         count_launch(ctx, SB200_STAGE_EXTREMA, 2);
     }
     {
         StageScope sc(ctx, st, SB200_STAGE_REFINE);
-        k_refine<<<dim3(gx, n), 128, 0, st>>>(P);
+        klaunch(k_refine, dim3(dim3(gx, n)), dim3(128), 0, st, P);
         count_launch(ctx, SB200_STAGE_REFINE);
     }
     {
         StageScope sc(ctx, st, SB200_STAGE_ORIENT);
-        k_out_offsets<<<1, 1024, 0, st>>>(cand_count, ctx->cap, -1LL, (int)n, s.d_sched + 4, cand_off);
-        k_orient<<<ctx->ori_ctas, 32 * ORI_WARPS, 0, st>>>(P, cand_off, (int)n, work);
-        k_kpscan<<<n, 1024, 0, st>>>(P);
-        k_emit<<<dim3(gx, n), 256, 0, st>>>(P);
+        klaunch(k_out_offsets, dim3(1), dim3(1024), 0, st, cand_count, ctx->cap, -1LL, (int)n, s.d_sched + 4, cand_off);
+        klaunch(k_orient, dim3(ctx->ori_ctas), dim3(32 * ORI_WARPS), 0, st, P, cand_off, (int)n, work);
+        klaunch(k_kpscan, dim3(n), dim3(1024), 0, st, P);
+        klaunch(k_emit, dim3(dim3(gx, n)), dim3(256), 0, st, P);
         count_launch(ctx, SB200_STAGE_ORIENT, 4);
     }
     {
         StageScope sc(ctx, st, SB200_STAGE_DESCRIPTOR);
         if (limit >= 0) {
-            k_sort_response<<<n, 1024, 0, st>>>(s.d_kps, kp_count, ctx->cap, s.d_sort, s.d_order);
+            klaunch(k_sort_response, dim3(n), dim3(1024), 0, st, s.d_kps, kp_count, ctx->cap, s.d_sort, s.d_order);
             count_launch(ctx, SB200_STAGE_DESCRIPTOR);
         }
-        k_out_offsets<<<1, 1024, 0, st>>>(kp_count, ctx->cap, (long long)limit, (int)n, out_count, out_off);
+        klaunch(k_out_offsets, dim3(1), dim3(1024), 0, st, kp_count, ctx->cap, (long long)limit, (int)n, out_count, out_off);
         DescParams D{};
         D.L = L;
         D.gauss = s.d_gauss;
@@ -1016,7 +1038,7 @@ int enqueue_detect(sb200_ctx* ctx, Slot& s, uint32_t n, int64_t limit) {
         D.out_off = out_off;
         D.out_kps = s.d_out_kps;
         D.out_desc = s.d_out_desc;
-        k_descriptor<<<ctx->desc_ctas, 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(D, (int)n, work + 1);
+        klaunch(k_descriptor, dim3(ctx->desc_ctas), dim3(32 * DESC_WARPS), DESC_SMEM_BYTES, st, D, (int)n, work + 1);
         count_launch(ctx, SB200_STAGE_DESCRIPTOR, 2);
     }
     CU(cudaGetLastError());

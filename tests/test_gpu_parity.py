@@ -174,12 +174,14 @@ def test_blur_batch_distribution(sf, oracle, w, h, n):
 
 @pytest.mark.parametrize("env", [{"SB200_BLUR": "tile"}, {"SB200_TAIL": "0"}, {"SB200_GRAPHS": "0", "SB200_FORK": "0"},
                                  {"SB200_SEED": "fused"}, {"SB200_SEED": "split"}, {"SB200_SIDES": "1"},
-                                 {"SB200_SIDES": "4", "SB200_GRAPHS": "0"}])
+                                 {"SB200_SIDES": "4", "SB200_GRAPHS": "0"}, {"SB200_PDL": "0"},
+                                 {"SB200_PDL": "0", "SB200_GRAPHS": "0"}])
 def test_alternative_paths(sf, oracle, monkeypatch, env):
     """The debugging switches select older / simpler / alternative code paths (independent-tile TMA blur, per-layer
     launches for the small octaves, plain single-stream launches without graph capture, the seed blur that upsamples
     its own input bands in line instead of with producer warps, the separate upsample kernel, one / four side streams
-    for the off-chain work of the octaves -- the latter as plain multi-stream launches): same bit-exact results."""
+    for the off-chain work of the octaves -- the latter as plain multi-stream launches --, launches without the
+    programmatic-dependent-launch attribute): same bit-exact results."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     _check_image(sf, oracle, noise_image(520, 390, 77))
