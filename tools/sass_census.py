@@ -6,6 +6,7 @@
   UTCIMMA   tcgen05.mma kind::i8 (5th-gen tensor cores) LDTM     tcgen05.ld (TMEM -> registers)
   UTCBAR    tcgen05.commit onto an mbarrier             SYNCS    mbarrier operations
   FFMA2 / FADD2 / FMUL2   packed f32x2 arithmetic       FMNMX3 / VIMNMX3  three-input float / integer min-max
+  ACQBULK   griddepcontrol.wait (programmatic dependent launch: first statement of every kernel of a group)
 """
 import collections
 import os
@@ -16,7 +17,7 @@ import sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 LIB = os.path.join(ROOT, "sift_features_b200", "libsift_b200.so")
 OPS = ["UTMALDG", "UTMASTG", "UTCIMMA", "LDTM", "UTCBAR", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FMNMX3", "VIMNMX3",
-       "MATCH", "MUFU", "DFMA", "LDS", "STS", "LDG", "STG", "BAR"]
+       "MATCH", "MUFU", "DFMA", "LDS", "STS", "LDG", "STG", "BAR", "ACQBULK"]
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 demangle = subprocess.run(["cu++filt"], input="\n".join(re.findall(r"Function : (\S+)", sass)), capture_output=True, text=True).stdout.split("\n")
 names = iter(demangle)
