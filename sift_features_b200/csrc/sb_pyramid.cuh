@@ -1401,7 +1401,8 @@ __global__ void __launch_bounds__(32 * EX_WARPS, 5) k_extrema_tma(const __grid_c
 // carries TAIL_RMAX mirrored columns on either side of every row, `b` (the row-pass result) TAIL_RMAX mirrored rows
 // above and below, filled by a short pass of their own (one border_index per halo element instead of one per tap),
 // so that both filter passes are plain sliding windows.  Four block barriers per blur instead of two, each phase a
-// fraction of the old ones.
+// fraction of the old ones.  All six layers of the octave also stay in shared memory (dense, even pitch), and the
+// extrema scan reads them there instead of through L2: its warps walk down a chain of dependent row loads.
 // ---------------------------------------------------------------------------
 constexpr int TAIL_MAX_PX = 2304;     // e.g. 64 x 36: larger octaves keep one CTA busy for too long
 constexpr int TAIL_RMAX = 13;         // widest blur radius (27 taps)
@@ -1411,10 +1412,12 @@ constexpr int TAIL_B_FLOATS = 4096;   // w x (h + 2 RMAX)
 #define SB_TAIL_THREADS 512
 #endif
 constexpr int TAIL_THREADS = SB_TAIL_THREADS;
-constexpr size_t TAIL_SMEM = (size_t)(TAIL_A_FLOATS + TAIL_B_FLOATS) * sizeof(float);
+constexpr int TAIL_L_FLOATS = 2560;   // one dense layer at an even pitch, (w + 1 & ~1) x h: the extrema scan's copy
+constexpr size_t TAIL_SMEM = (size_t)(TAIL_A_FLOATS + TAIL_B_FLOATS + N_LAYERS * TAIL_L_FLOATS) * sizeof(float);
 static_assert(blur_radius(N_LAYERS - 1) <= TAIL_RMAX, "halo of the widest blur");
 __host__ __device__ constexpr bool tail_fits(const long long w, const long long h) {
-    return w * h <= TAIL_MAX_PX && (w + 2 * TAIL_RMAX) * h <= TAIL_A_FLOATS && w * (h + 2 * TAIL_RMAX) <= TAIL_B_FLOATS;
+    return w * h <= TAIL_MAX_PX && (w + 2 * TAIL_RMAX) * h <= TAIL_A_FLOATS && w * (h + 2 * TAIL_RMAX) <= TAIL_B_FLOATS &&
+           ((w + 1) / 2 * 2) * h <= TAIL_L_FLOATS;
 }
 
 struct TailParams {
@@ -1441,7 +1444,8 @@ __device__ __forceinline__ void tail_halo_cols(float* __restrict__ a, const int 
 template <int LI, int R_NEXT, int FL>
 __device__ __forceinline__ void tail_blur(float* __restrict__ a /* smem, padded columns: source, then result */,
                                           float* __restrict__ b /* smem, padded rows */,
-                                          float* __restrict__ dst, float* __restrict__ dec, const int w, const int h,
+                                          float* __restrict__ lay /* smem, dense copy of the result at pitch ps */,
+                                          const int ps, float* __restrict__ dst, float* __restrict__ dec, const int w, const int h,
                                           const int pitch, const int dec_w, const int dec_h, const int dec_pitch) {
     constexpr int R = blur_radius(LI, FL);
     const int n = w * h, wp = w + 2 * TAIL_RMAX;
@@ -1475,6 +1479,7 @@ __device__ __forceinline__ void tail_blur(float* __restrict__ a /* smem, padded 
             for (int i = 1; i <= 2 * R; i++) acc = __fadd_rn(acc, __fmul_rn(c[(i - R) * w], tap<FL>(LI, i)));
         }
         a[y * wp + TAIL_RMAX + x] = acc;
+        lay[y * ps + x] = acc;
         dst[(long long)y * pitch + x] = acc;
         if (dec && !(y & 1) && !(x & 1)) {
             const int dy = y >> 1, dx = x >> 1;
@@ -1494,6 +1499,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
     extern __shared__ __align__(16) float tail_smem[];
     float* const a = tail_smem;                    // (w + 2 RMAX) x h
     float* const b = tail_smem + TAIL_A_FLOATS;    // w x (h + 2 RMAX)
+    float* const lay = b + TAIL_B_FLOATS;          // N_LAYERS x TAIL_L_FLOATS: the octave's layers, dense
     const long long img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* const gimg = p.gauss + img * p.L.img_floats;
@@ -1503,9 +1509,18 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
         if (w < 1 || h < 1) break;
         float* const g0 = gimg + ol.off;
         // layer 0: written by the previous octave's decimation (an earlier launch for o_first, this CTA otherwise)
+        const int ps = (w + 1) & ~1;   // even pitch of the dense copies: the scan loads aligned column pairs
         for (int idx = tid; idx < w * h; idx += TAIL_THREADS) {
             const int y = idx / w, x = idx - y * w;
-            a[y * (w + 2 * TAIL_RMAX) + TAIL_RMAX + x] = g0[(long long)y * ol.pitch + x];
+            const float v = g0[(long long)y * ol.pitch + x];
+            a[y * (w + 2 * TAIL_RMAX) + TAIL_RMAX + x] = v;
+            lay[y * ps + x] = v;
+        }
+        if (ps != w) {   // the padding column (never a candidate, never a candidate's neighbour): defined values all the same
+            for (int idx = tid; idx < N_LAYERS * h; idx += TAIL_THREADS) {
+                const int l = idx / h, y = idx - l * h;
+                lay[l * TAIL_L_FLOATS + y * ps + w] = 0.0f;
+            }
         }
         __syncthreads();
         tail_halo_cols<FL>(a, blur_radius(1, FL), w, h);
@@ -1515,10 +1530,10 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
         if (o + 1 < p.L.n_oct && p.L.o[o + 1].w >= 1 && p.L.o[o + 1].h >= 1) {
             dec = gimg + p.L.o[o + 1].off; dw = p.L.o[o + 1].w; dh = p.L.o[o + 1].h; dp = p.L.o[o + 1].pitch;
         }
-        tail_blur<1, blur_radius(2, FL), FL>(a, b, g0 + 1 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<2, blur_radius(3, FL), FL>(a, b, g0 + 2 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<3, blur_radius(4, FL), FL>(a, b, g0 + 3 * ol.layer_stride, FL == FL_OPENCV ? dec : nullptr, w, h, ol.pitch,
-                                             dw, dh, dp);
+        tail_blur<1, blur_radius(2, FL), FL>(a, b, lay + 1 * TAIL_L_FLOATS, ps, g0 + 1 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<2, blur_radius(3, FL), FL>(a, b, lay + 2 * TAIL_L_FLOATS, ps, g0 + 2 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<3, blur_radius(4, FL), FL>(a, b, lay + 3 * TAIL_L_FLOATS, ps, g0 + 3 * ol.layer_stride, FL == FL_OPENCV ? dec : nullptr,
+                                             w, h, ol.pitch, dw, dh, dp);
         if (FL != FL_OPENCV && dec) {
             // the imageproc flavour's Nearest resize of layer 3 (k_decimate_b): source pixel floor((d + 0.5) * (n_src /
             // n_dst)) in f32, result clamped to [0, 1]; `a` holds layer 3 until the column pass of the next blur, two
@@ -1531,12 +1546,13 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const TailParams p) {
                 dec[(long long)dy * dp + dx] = fminf(fmaxf(a[sy * (w + 2 * TAIL_RMAX) + TAIL_RMAX + sx], 0.0f), 1.0f);
             }
         }
-        tail_blur<4, blur_radius(5, FL), FL>(a, b, g0 + 4 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
-        tail_blur<5, 0, FL>(a, b, g0 + 5 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<4, blur_radius(5, FL), FL>(a, b, lay + 4 * TAIL_L_FLOATS, ps, g0 + 4 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
+        tail_blur<5, 0, FL>(a, b, lay + 5 * TAIL_L_FLOATS, ps, g0 + 5 * ol.layer_stride, nullptr, w, h, ol.pitch, 0, 0, 0);
         if (ol.scanned) {
             ExtremaParams e;
-            e.gauss = p.gauss + ol.off; e.img_stride = p.L.img_floats; e.layer_stride = ol.layer_stride;
-            e.w = w; e.h = h; e.pitch = ol.pitch;
+            // the layers where this CTA keeps them in shared memory (generic loads; image stride 0: every CTA its own)
+            e.gauss = lay; e.img_stride = 0; e.layer_stride = TAIL_L_FLOATS;
+            e.w = w; e.h = h; e.pitch = ps;
             e.mask = p.mask + ol.mask_off; e.mask_img_stride = p.L.img_mask_words; e.mask_pitch = ol.mask_pitch;
             e.rows = p.rows + ol.row_base; e.rows_img_stride = p.L.img_rows;
             // short row blocks: the scan is a chain of dependent row loads, so the CTA's 16 warps want many short tasks
