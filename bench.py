@@ -732,7 +732,8 @@ def run_b200(args, rank, local_rank, world):
         G = args.groups
     peak, peak_src = peaks()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    m = M.run(w, h, B, G, args.steps, args.warmup, profile=args.profile_stages, pageable=True, keep_sets=True)
+    m = M.run(w, h, B, G, args.steps, args.warmup, profile=args.profile_stages, pageable=True, keep_sets=True,
+              natural=args.natural)
     m["world"] = world
     ex, sets_h, sets_d, device_step, chk = m.pop("ctx")
     H = ex.handle
@@ -757,6 +758,8 @@ def run_b200(args, rank, local_rank, world):
     dist.barrier()
 
     cfg = headline_config(args.workload, world)
+    if args.natural:
+        cfg["workload"] = workload_text(args.workload, w, h, True)
     if args.batch or args.groups:
         cfg.update({"images_per_step_per_gpu": B * G, "groups_per_step": G, "images_per_group": B})
     line = {
@@ -1010,6 +1013,8 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS) + ["desc", "match", "jpeg"])
     ap.add_argument("--batch", type=int, default=0, help="images per group (context max_batch)")
     ap.add_argument("--groups", type=int, default=0, help="groups per step")
+    ap.add_argument("--natural", action="store_true",
+                    help="tiled tree.jpg instead of noise as the headline workload's input (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="headline workload only (no sub-workloads, no config 4)")
     ap.add_argument("--jpeg-colour", action="store_true", help="jpeg workload: three-component 4:2:0 streams")
