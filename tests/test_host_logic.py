@@ -54,3 +54,27 @@ def test_descriptor_byte_model():
     kp["size"] = [2.1 / 2, 2.1, 2.1 * 4]
     assert bench.descriptor_bytes(kp) == 3 * (45 * 45 * 4 + 144)
     assert bench.descriptor_bytes(kp[:0]) == 0.0
+
+
+def test_every_pipeline_kernel_waits_for_its_predecessor():
+    """Programmatic dependent launch: the kernels of a group are launched through `klaunch` with
+    the programmatic-stream-serialization attribute, so a kernel may start while its predecessor is still draining.
+    That is only safe because every kernel's FIRST statement is `pdl_wait()` (griddepcontrol.wait) -- a kernel added
+    without it would race silently.  Static check of the sources: every __global__ in the kernel headers opens with
+    the wait, and the enqueue functions launch through the helper only."""
+    import os
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.abspath(sf.__file__)), "csrc")
+    n = 0
+    for name in ("sb_pyramid.cuh", "sb_keypoints.cuh"):
+        src = open(os.path.join(csrc, name)).read()
+        for m in re.finditer(r"__global__[^{;]*\{\s*", src):
+            n += 1
+            assert src[m.end():].startswith("pdl_wait();"), f"{name}: kernel at offset {m.start()} does not open with pdl_wait()"
+    assert n >= 20
+    host = open(os.path.join(csrc, "sift_b200.cu")).read()
+    for fn in ("int enqueue_pyramid_imageproc(", "int enqueue_pyramid(", "int enqueue_detect("):
+        a = host.index(fn)
+        b = host.index("\n}\n", a)
+        assert "<<<" not in host[a:b], f"{fn} launches a kernel without the helper"
+        assert "klaunch(" in host[a:b] or "launch_blur" in host[a:b]
